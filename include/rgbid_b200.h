@@ -1,0 +1,298 @@
+/*
+ * rgbid_b200.h -- C ABI of the B200-native dense frame-to-keyframe alignment path.
+ *
+ * This is the drop-in boundary.  The reference (dangut/RGBiD-SLAM) has no FFI layer: its seam is the
+ * C++ free-function API RGBID_SLAM::device::* declared in src/internal.h:187-453 and consumed only by
+ * src/visodo.cpp and src/keyframe_align.cpp.  Every entry point below replaces one of those bridge
+ * functions (cited per function) or fuses a sequence of them; include/rgbid_b200/internal.hpp
+ * re-exposes the reference's exact C++ signatures on top of this ABI.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all image pointers are DEVICE pointers unless the name ends in
+ *    _host; `pitch` is the row stride in BYTES (the reference's DeviceArray2D::step()); images are
+ *    float32 with NaN = invalid, RGB is 3 x uint8 interleaved, depth is uint16 millimetres;
+ *  - transforms are passed in "pixel space" exactly as the reference passes them: Rp = K R K^-1
+ *    (row-major 3x3 float), tp = K t (3 floats);
+ *  - every call takes a context (device, stream, pre-allocated scratch: no hidden cudaMalloc on the
+ *    hot path) and returns an int status: 0 ok, RGBID_ERR_* (< 0), or 1000 + cudaError_t;
+ *    nothing calls exit() (the reference's cudaSafeCall does, ThirdParty/pcl_gpu_containers/src/error.cpp:42-46);
+ *  - functions that return scalars through host pointers synchronise the context's stream before
+ *    returning (the reference synchronises in every bridge function); all others are asynchronous
+ *    on the context's stream;
+ *  - one context per host thread; contexts on different streams may be used concurrently.
+ */
+#ifndef RGBID_B200_H_
+#define RGBID_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RGBID_B200_VERSION 100
+
+#define RGBID_OK 0
+#define RGBID_ERR_NAN (-1)      /* numerical failure: pose went NaN (reference: visodo.cpp:1265-1274) */
+#define RGBID_ERR_ARG (-2)      /* bad argument (null pointer, size mismatch, unsupported size) */
+#define RGBID_ERR_NOMEM (-3)
+#define RGBID_ERR_STATE (-4)    /* call sequence error (e.g. track before keyframe) */
+#define RGBID_ERR_TIMEOUT (-5)  /* device-side wait exceeded its budget */
+#define RGBID_ERR_CUDA_BASE 1000
+
+/* enums of src/internal.h:66-72 (same numeric values) */
+enum { RGBID_LSQ = 0, RGBID_HUBER = 1, RGBID_TUKEY = 2, RGBID_STUDENT = 3 };
+enum { RGBID_NO_MM = 0, RGBID_CONSTANT_VELOCITY = 1 };
+enum { RGBID_SIGMA_MAD = 0, RGBID_SIGMA_PDF = 1, RGBID_SIGMA_CONS = 2 };
+enum { RGBID_INDEPENDENT = 0, RGBID_MIN_WEIGHT = 1, RGBID_GEOM_ONLY = 2, RGBID_PHOT_ONLY = 3 };
+enum { RGBID_WARP_FIRST = 0, RGBID_PYR_FIRST = 1 };
+enum { RGBID_CHI_SQUARED = 0, RGBID_ALL_ITERS = 1 };
+enum { RGBID_NO_FILTERS = 0, RGBID_FILTER_GRADS = 1 };
+
+enum { RGBID_MODE_TRACKER = 0, RGBID_MODE_ALIGN = 1 };
+
+#define RGBID_MAX_LEVELS 8
+#define RGBID_SYSTEM_SIZE 27 /* TOTAL_SIZE, src/internal.h:59-64 */
+
+typedef struct rgbid_ctx rgbid_ctx;
+typedef struct rgbid_aligner rgbid_aligner;
+typedef struct rgbid_tracker rgbid_tracker;
+
+/* ---------------------------------------------------------------------------------------------- */
+/* Context                                                                                          */
+/* ---------------------------------------------------------------------------------------------- */
+
+/* stream: a cudaStream_t owned by the caller, or NULL to let the context create its own. */
+int rgbid_ctx_create(rgbid_ctx** ctx, int device, void* stream);
+int rgbid_ctx_destroy(rgbid_ctx* ctx);
+int rgbid_ctx_sync(rgbid_ctx* ctx);          /* replaces device::sync(), src/internal.h:456-457 */
+void* rgbid_ctx_stream(rgbid_ctx* ctx);
+int rgbid_version(void);
+const char* rgbid_status_string(int status);
+/* Number of kernels launched through this context since creation (bench.py's gpu_launches). */
+long long rgbid_ctx_launch_count(rgbid_ctx* ctx);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* Image preparation                                                                                */
+/* ---------------------------------------------------------------------------------------------- */
+
+/* convertDepth2InvDepth, src/internal.h:224 (src/cuda/misc.cu:365-374) */
+int rgbid_convert_depth_to_invdepth(rgbid_ctx* ctx, const uint16_t* src, size_t src_pitch, float* dst,
+                                    size_t dst_pitch, int rows, int cols, float factor_depth);
+/* computeIntensity, src/internal.h:231 (src/cuda/misc.cu:377-386) */
+int rgbid_compute_intensity(rgbid_ctx* ctx, const uint8_t* rgb, size_t src_pitch, float* dst, size_t dst_pitch,
+                            int rows, int cols);
+/* decomposeRGBInChannels, src/internal.h:234 (src/cuda/misc.cu:388-397) */
+int rgbid_decompose_rgb(rgbid_ctx* ctx, const uint8_t* rgb, size_t src_pitch, float* r, float* g, float* b,
+                        size_t dst_pitch, int rows, int cols);
+/* pyrDownIntensity / pyrDownDepth, src/internal.h:195,209 (src/cuda/pyrdown.cu:194-242); dst is
+ * (src_rows/2) x (src_cols/2) */
+int rgbid_pyr_down(rgbid_ctx* ctx, const float* src, size_t src_pitch, int src_rows, int src_cols, float* dst,
+                   size_t dst_pitch);
+/* computeGradientIntensity / computeGradientDepth, src/internal.h:242,250 (src/cuda/misc.cu:400-441) */
+int rgbid_compute_gradient(rgbid_ctx* ctx, const float* src, size_t src_pitch, int rows, int cols, float* grad_x,
+                           float* grad_y, size_t grad_pitch);
+/* bilateralFilter, src/internal.h:434 (src/cuda/filters.cu:139-162) */
+int rgbid_bilateral_filter(rgbid_ctx* ctx, const float* src, size_t src_pitch, int rows, int cols, float* dst,
+                           size_t dst_pitch, float sigma_floatmap);
+/* copyImage / copyImages, src/internal.h:260-264 (src/cuda/misc.cu:446-480) */
+int rgbid_copy_image(rgbid_ctx* ctx, const float* src, size_t src_pitch, float* dst, size_t dst_pitch, int rows,
+                     int cols);
+/* initialiseDeviceMemory2D<float>, initialiseWeightKeyframe, src/internal.h:271-274 */
+int rgbid_fill_image(rgbid_ctx* ctx, float* dst, size_t dst_pitch, int rows, int cols, float value);
+/* createVMap, src/internal.h:382 (src/cuda/maps.cu:300-344); vmap is (3*rows) x cols */
+int rgbid_create_vmap(rgbid_ctx* ctx, const float* depth_inv, size_t pitch, int rows, int cols, float fx, float fy,
+                      float cx, float cy, float* vmap, size_t vmap_pitch);
+/* createNMapGradients, src/internal.h:388 (src/cuda/maps.cu:396-443); nmap is (3*rows) x cols */
+int rgbid_create_nmap_gradients(rgbid_ctx* ctx, const float* depth_inv, const float* grad_x, const float* grad_y,
+                                size_t pitch, int rows, int cols, float fx, float fy, float cx, float cy,
+                                float* nmap, size_t nmap_pitch);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* Warping, visibility, fusion                                                                      */
+/* ---------------------------------------------------------------------------------------------- */
+
+/* warpInvDepthWithTrafo3D, src/internal.h:345-347 (src/cuda/warping_registration.cu:971-1019) */
+int rgbid_warp_invdepth(rgbid_ctx* ctx, const float* src, size_t src_pitch, const float* depth_prev,
+                        size_t prev_pitch, float* dst, size_t dst_pitch, int rows, int cols, const float* Rp,
+                        const float* tp);
+/* warpIntensityWithTrafo3DInvDepth, src/internal.h:333-334 (warping_registration.cu:920-967);
+ * bilinear sampling with the texture unit's 1/256 weight quantisation reproduced in software */
+int rgbid_warp_intensity(rgbid_ctx* ctx, const float* src, size_t src_pitch, const float* depth_prev,
+                         size_t prev_pitch, float* dst, size_t dst_pitch, int rows, int cols, const float* Rp,
+                         const float* tp);
+/* warpInvDepthWithTrafo3DWeighted, src/internal.h:349-351 (warping_registration.cu:1021-1069) */
+int rgbid_warp_invdepth_weighted(rgbid_ctx* ctx, const float* src, size_t src_pitch, const float* depth_prev,
+                                 size_t prev_pitch, float* dst, size_t dst_pitch, float* weight_warped,
+                                 size_t weight_pitch, int rows, int cols, const float* Rp, const float* tp);
+/* integrateWarpedFrame, src/internal.h:357-359 (warping_registration.cu:1072-1095) */
+int rgbid_integrate_warped_frame(rgbid_ctx* ctx, const float* warped_depthinv, size_t wd_pitch,
+                                 const float* warped_weight, size_t ww_pitch, float* depthinv_dst, size_t dd_pitch,
+                                 float* weight_dst, size_t dw_pitch, int rows, int cols);
+/* getVisibilityRatio / getVisibilityRatioWithOverlapMask, src/internal.h:370-377
+ * (warping_registration.cu:825-913).  overlap_mask may be NULL.  Synchronous. */
+int rgbid_visibility_ratio(rgbid_ctx* ctx, const float* depth_src, size_t src_pitch, const float* depth_dst,
+                           size_t dst_pitch, int rows, int cols, const float* Rp, const float* tp,
+                           uint8_t* overlap_mask, size_t mask_pitch, float* ratio_host);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* Residual sampling, scale estimation, chi-square                                                  */
+/* ---------------------------------------------------------------------------------------------- */
+
+/* Sampling geometry of computeErrorGridStride (src/cuda/sigmaFuncs.cu:711-747). Host only. */
+int rgbid_error_geometry(int rows, int cols, int min_nsamples, int* kept_rows, int* kept_cols, int* stride);
+/* computeErrorGridStride, src/internal.h:281 (sigmaFuncs.cu:701-765); error must hold
+ * kept_rows*kept_cols floats; *n_out (host, may be NULL) receives that count */
+int rgbid_compute_error(rgbid_ctx* ctx, const float* im1, size_t pitch1, const float* im0, size_t pitch0, int rows,
+                        int cols, int min_nsamples, float* error, int* n_out);
+/* computeSigmaAndNuStudent, src/internal.h:291-292 (sigmaFuncs.cu:858-1066). bias/sigma in-out. Synchronous. */
+int rgbid_sigma_nu_student(rgbid_ctx* ctx, const float* error, int n, float* bias_host, float* sigma_host,
+                           float* nu_host, int mestimator);
+/* computeNuStudent, src/internal.h:294-295 (sigmaFuncs.cu:1068-1222). Synchronous. */
+int rgbid_nu_student(rgbid_ctx* ctx, const float* error, int n, float bias, float sigma, float* nu_host);
+/* computeSigmaPdf, src/internal.h:288-289 (sigmaFuncs.cu:773-854). Synchronous. */
+int rgbid_sigma_pdf(rgbid_ctx* ctx, const float* error, int n, float* bias_host, float* sigma_host,
+                    int mestimator);
+/* computeChiSquare, src/internal.h:285-286 (sigmaFuncs.cu:1225-1297). Synchronous. */
+int rgbid_chi_square(rgbid_ctx* ctx, const float* error_int, const float* error_depth, int n, float sigma_int,
+                     float sigma_depth, int mestimator, float* chi_square_host, float* chi_test_host,
+                     float* ndof_host);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* Normal equations                                                                                 */
+/* ---------------------------------------------------------------------------------------------- */
+
+typedef struct {
+  float fx, fy, cx, cy; /* Intr of the level being processed (src/internal.h:119-140) */
+  int mestimator;       /* used when student_nu == 0 (buildSystemGridStride) */
+  int weighting;
+  int student_nu;       /* 1: buildSystemStudentNuGridStride, 0: buildSystemGridStride */
+  float sigma_depthinv, sigma_int, bias_depthinv, bias_int, nu_depthinv, nu_int;
+} rgbid_system_params;
+
+/* buildSystemGridStride / buildSystemStudentNuGridStride, src/internal.h:299-322
+ * (src/cuda/estimate_VO.cu:505-789): one launch (per-thread FP32 accumulation, FP64 from the warp
+ * level up, deterministic last-block final sum) instead of two kernels + two syncs.
+ * A36: 36 doubles row-major with both triangles filled, b6: 6 doubles (host). Synchronous. */
+int rgbid_build_system(rgbid_ctx* ctx, const float* W0, const float* I0, const float* gradW0_x,
+                       const float* gradW0_y, const float* gradI0_x, const float* gradI0_y, const float* W1,
+                       const float* I1, size_t pitch, int rows, int cols, const rgbid_system_params* params,
+                       double* A36_host, double* b6_host);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* Fused, device-resident coarse-to-fine alignment of `batch` independent frame pairs               */
+/* (the Gauss-Newton loops of VisodoTracker::estimateVisualOdometry, src/visodo.cpp:944-1479, and   */
+/*  KeyframeAlign::alignKeyframes, src/keyframe_align.cpp:115-357)                                  */
+/* ---------------------------------------------------------------------------------------------- */
+
+typedef struct {
+  int rows, cols;   /* level-0 size; must be divisible by 2^(levels-1) */
+  int levels;       /* VisodoTracker::LEVELS = 3 (include/visodo.h:52), KeyframeAlign::LEVELS = 4 */
+  int finest_level;
+  int iterations[RGBID_MAX_LEVELS]; /* per level; {10,5,3} tracker, {5,5,3,0} align */
+  int batch;        /* independent frame pairs processed per call */
+  int mode;         /* RGBID_MODE_TRACKER | RGBID_MODE_ALIGN */
+  int mestimator;   /* tracker: Mestimator_ */
+  int weighting;
+  int sigma_estimator; /* tracker only: RGBID_SIGMA_PDF | RGBID_SIGMA_CONS */
+  int nsamples;     /* residual sub-sampling target: 10000 tracker, 19200 align */
+  float fx, fy, cx, cy; /* level-0 intrinsics */
+  float factor_depth;
+  int with_fusion;  /* tracker: allocate integration-keyframe buffers */
+} rgbid_align_config;
+
+typedef struct {
+  int level, iter;
+  double sums27[27];
+  float sigma_int, sigma_depthinv, bias_int, bias_depthinv, nu_int, nu_depthinv;
+  int irls_iters_int, irls_iters_depthinv;
+  double x[6];
+  double R[9], t[3];
+} rgbid_iter_trace;
+
+int rgbid_aligner_create(rgbid_ctx* ctx, const rgbid_align_config* cfg, rgbid_aligner** out);
+int rgbid_aligner_destroy(rgbid_aligner* al);
+/* Total Gauss-Newton iterations per pair (sum of cfg.iterations over the active levels). */
+int rgbid_aligner_num_iterations(const rgbid_aligner* al);
+
+/* Load level-0 float maps (inverse depth, intensity) of the keyframe ("ini") of pair `index` and build
+ * its pyramid, Sobel gradients and -- in tracker mode -- the bilateral-filtered covariance-only
+ * gradients (saveCurrentImagesAsOdoKeyframes, src/visodo.cpp:826-878; keyframe_align.cpp:157-176).
+ * from_host != 0: pointers are host memory (uploaded through the context's pinned staging). */
+int rgbid_aligner_set_keyframe(rgbid_aligner* al, int index, const float* depthinv, size_t dpitch,
+                               const float* intensity, size_t ipitch, int from_host);
+/* Same for the current frame ("end" keyframe): pyramid only (prepareImages, src/visodo.cpp:760-773). */
+int rgbid_aligner_set_current(rgbid_aligner* al, int index, const float* depthinv, size_t dpitch,
+                              const float* intensity, size_t ipitch, int from_host);
+/* Ingest raw sensor data (uint16 depth in mm, RGB8) as the current frame of pair `index`:
+ * convertDepth2InvDepth + computeIntensity + pyramid fused (prepareImages). */
+int rgbid_aligner_set_current_rgbd(rgbid_aligner* al, int index, const uint16_t* depth, size_t dpitch,
+                                   const uint8_t* rgb, size_t cpitch, int from_host);
+/* Promote the current frame of pair `index` to keyframe (copy + gradients (+ filtered gradients)). */
+int rgbid_aligner_current_to_keyframe(rgbid_aligner* al, int index);
+
+/* Run the whole coarse-to-fine schedule for all `batch` pairs on the device.
+ * R_inout: batch x 9 doubles (row-major rotation _{KF}R^{cur}), t_inout: batch x 3 doubles: initial guess
+ * in, estimate out.  cov_out: batch x 36 doubles (may be NULL).  status_out: batch ints (RGBID_OK or
+ * RGBID_ERR_NAN).  trace_out (may be NULL): batch x num_iterations entries.  Synchronous. */
+int rgbid_aligner_run(rgbid_aligner* al, double* R_inout, double* t_inout, double* cov_out, int* status_out,
+                      rgbid_iter_trace* trace_out);
+/* Asynchronous variant: enqueue only; results are fetched with rgbid_aligner_fetch (which synchronises). */
+int rgbid_aligner_enqueue(rgbid_aligner* al, const double* R_init, const double* t_init);
+int rgbid_aligner_fetch(rgbid_aligner* al, double* R_out, double* t_out, double* cov_out, int* status_out,
+                        rgbid_iter_trace* trace_out);
+/* Frame statistics of the last tracker-mode run: chi_square / chi_test / ndof of the end-of-frame test
+ * (src/visodo.cpp:1411-1415), 3 floats per pair. */
+int rgbid_aligner_frame_stats(rgbid_aligner* al, float* stats_out);
+/* Device pointer + pitch of an internal pyramid map, for tests and for callers that fill maps in place.
+ * which: 0 W_kf, 1 I_kf, 2 gWx, 3 gWy, 4 gIx, 5 gIy, 6 W_cur, 7 I_cur, 8..11 covariance-only gradients */
+int rgbid_aligner_map(rgbid_aligner* al, int which, int level, int index, float** ptr, size_t* pitch);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* Tracker: per-frame state machine of VisodoTracker::trackNewFrame (src/visodo.cpp:1967-2247) for  */
+/* `batch` independent RGB-D streams: ingest, pyramid, Gauss-Newton, covariance, covisibility,      */
+/* keyframe switching, inverse-depth fusion.                                                        */
+/* ---------------------------------------------------------------------------------------------- */
+
+typedef struct {
+  rgbid_align_config align;  /* mode is forced to RGBID_MODE_TRACKER */
+  int motion_model;          /* RGBID_NO_MM | RGBID_CONSTANT_VELOCITY (src/visodo.cpp:1016-1032) */
+  float visratio_odo;        /* 0.9, src/internal.h:110 */
+  float visratio_integr;     /* 0.7, src/internal.h:111 */
+  int max_odo_kf_count;      /* 9999999 */
+  int max_integr_kf_count;   /* 9999999 */
+  int image_filtering;       /* RGBID_NO_FILTERS | RGBID_FILTER_GRADS */
+  float delta_t;             /* 0.03333 s in eval mode (src/visodo.cpp:1932) */
+} rgbid_tracker_config;
+
+typedef struct {
+  double R[9], t[3];          /* global pose (camera-to-world) after this frame */
+  double dR[9], dt[3];        /* pose relative to the odometry keyframe, _{KF}T^{cur} */
+  double cov[36];             /* covariance of the keyframe-relative estimate */
+  float visibility_odo, visibility_integr;
+  float chi_square, chi_test, ndof;
+  int status;                 /* RGBID_OK or RGBID_ERR_NAN (lost) */
+  int new_odo_keyframe, new_integr_keyframe;
+  int frame_index;
+} rgbid_frame_result;
+
+int rgbid_tracker_create(rgbid_ctx* ctx, const rgbid_tracker_config* cfg, rgbid_tracker** out);
+int rgbid_tracker_destroy(rgbid_tracker* trk);
+int rgbid_tracker_reset(rgbid_tracker* trk);
+/* Track one frame per stream.  depth: batch x rows x cols uint16 (dense), rgb: batch x rows x cols x 3
+ * uint8 (dense).  from_host != 0: host pointers (pinned or pageable; copied inside the call).
+ * results_host: batch entries.  Synchronous (the reference's trackNewFrame is). */
+int rgbid_tracker_track(rgbid_tracker* trk, const uint16_t* depth, const uint8_t* rgb, int from_host,
+                        rgbid_frame_result* results_host);
+/* Integration-keyframe maps of stream `index` (device pointers; pitch in bytes):
+ * which: 0 fused inverse depth, 1 fusion weight, 2 raw inverse depth, 3 vertex map (3*rows), 4 normal map
+ * (3*rows) */
+int rgbid_tracker_keyframe_map(rgbid_tracker* trk, int which, int index, float** ptr, size_t* pitch);
+int rgbid_tracker_overlap_mask(rgbid_tracker* trk, int index, uint8_t** ptr, size_t* pitch);
+rgbid_aligner* rgbid_tracker_aligner(rgbid_tracker* trk);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGBID_B200_H_ */

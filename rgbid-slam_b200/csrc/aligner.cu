@@ -1,0 +1,393 @@
+// aligner.cu -- host orchestration of the fused, device-resident coarse-to-fine alignment.
+//
+// The reference's drivers (VisodoTracker::estimateVisualOdometry, src/visodo.cpp:944-1479;
+// KeyframeAlign::alignKeyframes, src/keyframe_align.cpp:115-357) cross the host/device boundary ~40 times
+// per Gauss-Newton iteration.  Here the complete schedule -- every (level, iteration), scale estimation,
+// normal equations, solve, pose update and the covariance pass -- is recorded once as a CUDA graph and
+// replayed per call; the host only writes the initial guess and reads the final state.
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "aligner.hpp"
+
+using namespace rgbid;
+
+namespace rgbid {
+
+static ImgB sub(const ImgB& m, int first)
+{
+  ImgB v = m;
+  v.p = (float*)((char*)m.p + (size_t)first * m.sstride);
+  return v;
+}
+
+void aligner_current_pyramid(rgbid_aligner* al, int first, int batch)
+{
+  LaunchCtx L = al->ctx->L();
+  for (int l = 1; l < al->cfg.levels; ++l)  // prepareImages, src/visodo.cpp:768-772
+    launch_pyr_down2(L, sub(al->maps[MAP_I_CUR][l - 1], first), sub(al->maps[MAP_I_CUR][l], first),
+                     sub(al->maps[MAP_W_CUR][l - 1], first), sub(al->maps[MAP_W_CUR][l], first), batch);
+}
+
+void aligner_copy_current_to_keyframe(rgbid_aligner* al, int first, int batch, const int* active)
+{
+  LaunchCtx L = al->ctx->L();
+  for (int l = 0; l < al->cfg.levels; ++l)  // copyImages per level, src/visodo.cpp:837-840
+    launch_copy2(L, sub(al->maps[MAP_W_CUR][l], first), sub(al->maps[MAP_W_KF][l], first),
+                 sub(al->maps[MAP_I_CUR][l], first), sub(al->maps[MAP_I_KF][l], first), batch, active);
+}
+
+void aligner_keyframe_derivatives(rgbid_aligner* al, int first, int batch, const int* active, bool pyramid_from_l0)
+{
+  LaunchCtx L = al->ctx->L();
+  const int levels = al->cfg.levels;
+  auto M = [&](int which, int l) { return sub(al->maps[which][l], first); };
+  if (pyramid_from_l0)  // keyframe_align.cpp:157-164
+    for (int l = 1; l < levels; ++l)
+      launch_pyr_down2(L, M(MAP_W_KF, l - 1), M(MAP_W_KF, l), M(MAP_I_KF, l - 1), M(MAP_I_KF, l), batch, active);
+  const bool tracker = (al->cfg.mode == RGBID_MODE_TRACKER);
+  if (tracker) {
+    // saveCurrentImagesAsOdoKeyframes, src/visodo.cpp:842-857: bilateral filter (range sigma 2*0.0025 for the
+    // inverse depth, 3 for the intensity), pyramid of the filtered maps, Sobel -> covariance-only gradients
+    launch_bilateral2(L, M(MAP_W_KF, 0), M(MAP_WF, 0), 2.f * 0.0025f, M(MAP_I_KF, 0), M(MAP_IF, 0), 3.f, batch, active);
+    for (int l = 1; l < levels; ++l)
+      launch_pyr_down2(L, M(MAP_WF, l - 1), M(MAP_WF, l), M(MAP_IF, l - 1), M(MAP_IF, l), batch, active);
+    for (int l = 0; l < levels; ++l)
+      launch_gradient2(L, M(MAP_IF, l), M(MAP_CGIX, l), M(MAP_CGIY, l), M(MAP_WF, l), M(MAP_CGWX, l), M(MAP_CGWY, l),
+                       batch, active);
+  }
+  if (tracker && al->image_filtering == RGBID_FILTER_GRADS) {
+    for (int l = 0; l < levels; ++l) {  // src/visodo.cpp:859-866
+      launch_copy2(L, M(MAP_CGIX, l), M(MAP_GIX, l), M(MAP_CGIY, l), M(MAP_GIY, l), batch, active);
+      launch_copy2(L, M(MAP_CGWX, l), M(MAP_GWX, l), M(MAP_CGWY, l), M(MAP_GWY, l), batch, active);
+    }
+  } else {
+    for (int l = 0; l < levels; ++l)  // src/visodo.cpp:869-877, keyframe_align.cpp:168-176
+      launch_gradient2(L, M(MAP_I_KF, l), M(MAP_GIX, l), M(MAP_GIY, l), M(MAP_W_KF, l), M(MAP_GWX, l), M(MAP_GWY, l),
+                       batch, active);
+  }
+}
+
+static GnParams base_params(const rgbid_aligner* al, int level)
+{
+  const rgbid_align_config& c = al->cfg;
+  GnParams P;
+  memset(&P, 0, sizeof(P));
+  P.batch = c.batch; P.level = level;
+  P.rows = al->geom[level].rows; P.cols = al->geom[level].cols;
+  float div = (float)(1 << level);  // Intr::operator()(level), src/internal.h:128-132
+  P.fx = c.fx / div; P.fy = c.fy / div; P.cx = c.cx / div; P.cy = c.cy / div;
+  P.fx0 = c.fx; P.fy0 = c.fy; P.cx0 = c.cx; P.cy0 = c.cy;
+  P.levels = c.levels; P.mode = c.mode;
+  P.mestimator = c.mestimator; P.weighting = c.weighting;
+  P.student_nu = 1; P.use_scale = 1; P.update_pose = 1; P.compute_cov = 0; P.chi_mestimator = -1;
+  P.trace_stride = al->trace_stride;
+  P.kept_rows = al->geom[level].kept_rows; P.kept_cols = al->geom[level].kept_cols;
+  P.sample_stride = al->geom[level].sample_stride;
+  P.sigma_op = (c.mode == RGBID_MODE_TRACKER) ? SCALE_SIGMA_NU : SCALE_NU_ONLY;
+  return P;
+}
+
+static GnLevelMaps level_maps(const rgbid_aligner* al, int level, bool cov_gradients)
+{
+  GnLevelMaps M;
+  M.W0 = al->maps[MAP_W_KF][level]; M.I0 = al->maps[MAP_I_KF][level];
+  M.gWx = al->maps[cov_gradients ? MAP_CGWX : MAP_GWX][level];
+  M.gWy = al->maps[cov_gradients ? MAP_CGWY : MAP_GWY][level];
+  M.gIx = al->maps[cov_gradients ? MAP_CGIX : MAP_GIX][level];
+  M.gIy = al->maps[cov_gradients ? MAP_CGIY : MAP_GIY][level];
+  M.Wc = al->maps[MAP_W_CUR][level]; M.Ic = al->maps[MAP_I_CUR][level];
+  return M;
+}
+
+// Issues the launches of one complete alignment on the context's stream (captured into a graph when enabled).
+void aligner_record_schedule(rgbid_aligner* al)
+{
+  const rgbid_align_config& c = al->cfg;
+  LaunchCtx L = al->ctx->L();
+  launch_gn_init(L, al->d_states, al->d_init, al->d_init + 9 * c.batch, c.batch, c.levels, c.fx, c.fy, c.cx, c.cy);
+  const bool tracker = (c.mode == RGBID_MODE_TRACKER);
+  const bool estimate_scale = tracker ? (c.sigma_estimator == RGBID_SIGMA_PDF) : true;
+  int done = 0;
+  for (int level = c.levels - 1; level >= c.finest_level; --level) {
+    for (int it = 0; it < c.iterations[level]; ++it) {
+      GnParams P = base_params(al, level);
+      P.iter_index = done;
+      P.use_scale = estimate_scale ? 1 : 0;
+      ++done;
+      // KeyframeAlign: covariance = inverse of the LAST iteration's A (keyframe_align.cpp:339-350)
+      P.compute_cov = (!tracker && done == al->niters) ? 1 : 0;
+      GnLevelMaps M = level_maps(al, level, false);
+      if (estimate_scale) launch_gn_scale(L, M, P, al->d_states, al->d_scales);
+      launch_gn_build(L, M, P, al->d_states, al->d_scales, al->d_partials, 32, al->d_counters, al->d_trace);
+    }
+  }
+  if (tracker) {
+    // covariance pass at the finest level on the bilateral-filtered gradients with fixed scales and
+    // Student(5) weights, no pose update (src/visodo.cpp:1283-1409) + end-of-frame chi^2 (:1411-1415)
+    GnParams P = base_params(al, c.finest_level);
+    P.iter_index = al->niters;
+    P.use_scale = 0; P.student_nu = 0; P.mestimator = RGBID_STUDENT;
+    P.update_pose = 0; P.compute_cov = 1; P.chi_mestimator = c.mestimator;
+    GnLevelMaps M = level_maps(al, c.finest_level, true);
+    launch_gn_build(L, M, P, al->d_states, nullptr, al->d_partials, 32, al->d_counters, al->d_trace);
+  }
+}
+
+}  // namespace rgbid
+
+static int copy_in(rgbid_aligner* al, const void* src, size_t spitch, ImgB dst, size_t width_bytes, int from_host)
+{
+  RGBID_CUDA_TRY(cudaMemcpy2DAsync(dst.p, dst.pitch, src, spitch, width_bytes, dst.rows,
+                                   from_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, al->ctx->stream));
+  return RGBID_OK;
+}
+
+extern "C" {
+
+int rgbid_aligner_create(rgbid_ctx* ctx, const rgbid_align_config* cfg, rgbid_aligner** out)
+{
+  if (!ctx || !cfg || !out) return RGBID_ERR_ARG;
+  *out = nullptr;
+  if (cfg->levels < 1 || cfg->levels > RGBID_MAX_LEVELS || cfg->batch < 1 || cfg->rows <= 0 || cfg->cols <= 0)
+    return RGBID_ERR_ARG;
+  if (cfg->finest_level < 0 || cfg->finest_level >= cfg->levels) return RGBID_ERR_ARG;
+  if ((cfg->rows % (1 << (cfg->levels - 1))) || (cfg->cols % (1 << (cfg->levels - 1)))) return RGBID_ERR_ARG;
+  if (!(cfg->fx > 0.f) || !(cfg->fy > 0.f)) return RGBID_ERR_ARG;
+  RGBID_CUDA_TRY(cudaSetDevice(ctx->device));
+  rgbid_aligner* al = new (std::nothrow) rgbid_aligner();
+  if (!al) return RGBID_ERR_NOMEM;
+  memset(al, 0, sizeof(*al));
+  al->ctx = ctx;
+  al->cfg = *cfg;
+  if (al->cfg.factor_depth <= 0.f) al->cfg.factor_depth = 1.f;
+  if (al->cfg.nsamples <= 0) al->cfg.nsamples = (cfg->mode == RGBID_MODE_TRACKER) ? 10000 : 19200;
+  al->niters = 0;
+  for (int l = cfg->finest_level; l < cfg->levels; ++l) al->niters += cfg->iterations[l] > 0 ? cfg->iterations[l] : 0;
+  al->trace_stride = al->niters + 1;
+  const bool tracker = (cfg->mode == RGBID_MODE_TRACKER);
+  const int B = cfg->batch;
+
+  size_t total = 0;
+  for (int l = 0; l < cfg->levels; ++l) {
+    LevelGeom& g = al->geom[l];
+    g.rows = cfg->rows >> l; g.cols = cfg->cols >> l;
+    g.pitch = align_up((size_t)g.cols * sizeof(float), 128);
+    g.sstride = align_up(g.pitch * g.rows, 256);
+    rgbid_error_geometry(g.rows, g.cols, al->cfg.nsamples, &g.kept_rows, &g.kept_cols, &g.sample_stride);
+    int nmaps = tracker ? (int)MAP_COUNT : 8;
+    total += (size_t)nmaps * g.sstride * B;
+  }
+  size_t raw_depth = align_up((size_t)cfg->rows * cfg->cols * 2, 256), raw_rgb = align_up((size_t)cfg->rows * cfg->cols * 3, 256);
+  size_t off_depth = total; total += raw_depth * B;
+  size_t off_rgb = total; total += raw_rgb * B;
+  al->arena_bytes = total;
+  cudaError_t e = cudaMalloc(&al->d_arena, total);
+  if (e != cudaSuccess) { delete al; return e == cudaErrorMemoryAllocation ? RGBID_ERR_NOMEM : RGBID_ERR_CUDA_BASE + (int)e; }
+  size_t off = 0;
+  for (int l = 0; l < cfg->levels; ++l) {
+    const LevelGeom& g = al->geom[l];
+    int nmaps = tracker ? (int)MAP_COUNT : 8;
+    for (int m = 0; m < nmaps; ++m) {
+      al->maps[m][l] = make_img((float*)(al->d_arena + off), g.pitch, g.rows, g.cols, g.sstride);
+      off += g.sstride * B;
+    }
+  }
+  al->d_depth_raw = (uint16_t*)(al->d_arena + off_depth);
+  al->d_rgb_raw = (uint8_t*)(al->d_arena + off_rgb);
+
+  al->partial_blocks = ctx->num_sms;
+  e = cudaSuccess;
+  if (e == cudaSuccess) e = cudaMalloc(&al->d_states, sizeof(GnState) * B);
+  if (e == cudaSuccess) e = cudaMalloc(&al->d_scales, sizeof(ScaleState) * B);
+  if (e == cudaSuccess) e = cudaMalloc(&al->d_partials, sizeof(double) * 32 * (size_t)al->partial_blocks * B);
+  if (e == cudaSuccess) e = cudaMalloc(&al->d_counters, sizeof(unsigned int) * B);
+  if (e == cudaSuccess) e = cudaMalloc(&al->d_trace, sizeof(rgbid_iter_trace) * (size_t)al->trace_stride * B);
+  if (e == cudaSuccess) e = cudaMalloc(&al->d_init, sizeof(double) * 12 * B);
+  if (e == cudaSuccess) e = cudaMalloc(&al->d_active, sizeof(int) * 4 * B);
+  if (e == cudaSuccess) e = cudaMallocHost(&al->h_states, sizeof(GnState) * B);
+  if (e == cudaSuccess) e = cudaMallocHost(&al->h_trace, sizeof(rgbid_iter_trace) * (size_t)al->trace_stride * B);
+  if (e == cudaSuccess) e = cudaMallocHost(&al->h_init, sizeof(double) * 12 * B);
+  if (e == cudaSuccess) e = cudaMallocHost(&al->h_active, sizeof(int) * 4 * B);
+  if (e == cudaSuccess) e = cudaMemsetAsync(al->d_counters, 0, sizeof(unsigned int) * B, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(al->d_states, 0, sizeof(GnState) * B, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(al->d_trace, 0, sizeof(rgbid_iter_trace) * (size_t)al->trace_stride * B, ctx->stream);
+  // NaN-fill every map: an unset map then behaves as "all pixels invalid" instead of reading garbage
+  if (e == cudaSuccess) e = cudaMemsetAsync(al->d_arena, 0xff, off_depth, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { rgbid_aligner_destroy(al); return RGBID_ERR_CUDA_BASE + (int)e; }
+  const char* no_graph = getenv("RGBID_NO_GRAPH");
+  al->use_graph = !(no_graph && no_graph[0] == '1') && (ctx->stream != (cudaStream_t)0);
+  al->image_filtering = RGBID_NO_FILTERS;
+  *out = al;
+  return RGBID_OK;
+}
+
+int rgbid_aligner_destroy(rgbid_aligner* al)
+{
+  if (!al) return RGBID_OK;
+  cudaStreamSynchronize(al->ctx->stream);
+  if (al->gn_exec) cudaGraphExecDestroy(al->gn_exec);
+  cudaFree(al->d_arena); cudaFree(al->d_states); cudaFree(al->d_scales); cudaFree(al->d_partials);
+  cudaFree(al->d_counters); cudaFree(al->d_trace); cudaFree(al->d_init); cudaFree(al->d_active);
+  if (al->h_states) cudaFreeHost(al->h_states);
+  if (al->h_trace) cudaFreeHost(al->h_trace);
+  if (al->h_init) cudaFreeHost(al->h_init);
+  if (al->h_active) cudaFreeHost(al->h_active);
+  delete al;
+  return RGBID_OK;
+}
+
+int rgbid_aligner_num_iterations(const rgbid_aligner* al) { return al ? al->niters : 0; }
+
+int rgbid_aligner_set_keyframe(rgbid_aligner* al, int index, const float* depthinv, size_t dpitch,
+                               const float* intensity, size_t ipitch, int from_host)
+{
+  if (!al || index < 0 || index >= al->cfg.batch || !depthinv || !intensity) return RGBID_ERR_ARG;
+  int rc;
+  size_t wb = (size_t)al->cfg.cols * sizeof(float);
+  if ((rc = copy_in(al, depthinv, dpitch, al->view(MAP_W_KF, 0, index), wb, from_host)) != RGBID_OK) return rc;
+  if ((rc = copy_in(al, intensity, ipitch, al->view(MAP_I_KF, 0, index), wb, from_host)) != RGBID_OK) return rc;
+  aligner_keyframe_derivatives(al, index, 1, nullptr, true);
+  return check_last(al->ctx);
+}
+
+int rgbid_aligner_set_current(rgbid_aligner* al, int index, const float* depthinv, size_t dpitch,
+                              const float* intensity, size_t ipitch, int from_host)
+{
+  if (!al || index < 0 || index >= al->cfg.batch || !depthinv || !intensity) return RGBID_ERR_ARG;
+  int rc;
+  size_t wb = (size_t)al->cfg.cols * sizeof(float);
+  if ((rc = copy_in(al, depthinv, dpitch, al->view(MAP_W_CUR, 0, index), wb, from_host)) != RGBID_OK) return rc;
+  if ((rc = copy_in(al, intensity, ipitch, al->view(MAP_I_CUR, 0, index), wb, from_host)) != RGBID_OK) return rc;
+  aligner_current_pyramid(al, index, 1);
+  return check_last(al->ctx);
+}
+
+int rgbid_aligner_set_current_rgbd(rgbid_aligner* al, int index, const uint16_t* depth, size_t dpitch,
+                                   const uint8_t* rgb, size_t cpitch, int from_host)
+{
+  if (!al || index < 0 || index >= al->cfg.batch || !depth || !rgb) return RGBID_ERR_ARG;
+  const int rows = al->cfg.rows, cols = al->cfg.cols;
+  const uint16_t* d = depth;
+  const uint8_t* c = rgb;
+  size_t dp = dpitch, cp = cpitch;
+  if (from_host) {
+    size_t raw_depth = align_up((size_t)rows * cols * 2, 256), raw_rgb = align_up((size_t)rows * cols * 3, 256);
+    uint16_t* dd = (uint16_t*)((char*)al->d_depth_raw + raw_depth * index);
+    uint8_t* dc = al->d_rgb_raw + raw_rgb * index;
+    RGBID_CUDA_TRY(cudaMemcpy2DAsync(dd, (size_t)cols * 2, depth, dpitch, (size_t)cols * 2, rows, cudaMemcpyHostToDevice, al->ctx->stream));
+    RGBID_CUDA_TRY(cudaMemcpy2DAsync(dc, (size_t)cols * 3, rgb, cpitch, (size_t)cols * 3, rows, cudaMemcpyHostToDevice, al->ctx->stream));
+    d = dd; c = dc; dp = (size_t)cols * 2; cp = (size_t)cols * 3;
+  }
+  launch_ingest(al->ctx->L(), d, dp, 0, c, cp, 0, al->view(MAP_W_CUR, 0, index), al->view(MAP_I_CUR, 0, index), 1,
+                al->cfg.factor_depth);
+  aligner_current_pyramid(al, index, 1);
+  return check_last(al->ctx);
+}
+
+int rgbid_aligner_current_to_keyframe(rgbid_aligner* al, int index)
+{
+  if (!al || index < 0 || index >= al->cfg.batch) return RGBID_ERR_ARG;
+  aligner_copy_current_to_keyframe(al, index, 1, nullptr);
+  aligner_keyframe_derivatives(al, index, 1, nullptr, false);
+  return check_last(al->ctx);
+}
+
+int rgbid_aligner_enqueue(rgbid_aligner* al, const double* R_init, const double* t_init)
+{
+  if (!al || !R_init || !t_init) return RGBID_ERR_ARG;
+  const int B = al->cfg.batch;
+  cudaStream_t s = al->ctx->stream;
+  memcpy(al->h_init, R_init, sizeof(double) * 9 * B);
+  memcpy(al->h_init + 9 * B, t_init, sizeof(double) * 3 * B);
+  RGBID_CUDA_TRY(cudaMemcpyAsync(al->d_init, al->h_init, sizeof(double) * 12 * B, cudaMemcpyHostToDevice, s));
+  return aligner_enqueue_device_init(al);
+}
+
+int rgbid_aligner_fetch(rgbid_aligner* al, double* R_out, double* t_out, double* cov_out, int* status_out,
+                        rgbid_iter_trace* trace_out)
+{
+  if (!al) return RGBID_ERR_ARG;
+  const int B = al->cfg.batch;
+  cudaStream_t s = al->ctx->stream;
+  RGBID_CUDA_TRY(cudaMemcpyAsync(al->h_states, al->d_states, sizeof(GnState) * B, cudaMemcpyDeviceToHost, s));
+  if (trace_out)
+    RGBID_CUDA_TRY(cudaMemcpyAsync(al->h_trace, al->d_trace, sizeof(rgbid_iter_trace) * (size_t)al->trace_stride * B,
+                                   cudaMemcpyDeviceToHost, s));
+  RGBID_CUDA_TRY(cudaStreamSynchronize(s));
+  int rc = check_last(al->ctx);
+  if (rc != RGBID_OK) return rc;
+  for (int b = 0; b < B; ++b) {
+    const GnState& st = al->h_states[b];
+    if (R_out) memcpy(R_out + 9 * b, st.R, sizeof(double) * 9);
+    if (t_out) memcpy(t_out + 3 * b, st.t, sizeof(double) * 3);
+    if (cov_out) memcpy(cov_out + 36 * b, st.cov, sizeof(double) * 36);
+    if (status_out) status_out[b] = st.status;
+  }
+  if (trace_out) memcpy(trace_out, al->h_trace, sizeof(rgbid_iter_trace) * (size_t)al->trace_stride * B);
+  return RGBID_OK;
+}
+
+int rgbid_aligner_run(rgbid_aligner* al, double* R_inout, double* t_inout, double* cov_out, int* status_out,
+                      rgbid_iter_trace* trace_out)
+{
+  int rc = rgbid_aligner_enqueue(al, R_inout, t_inout);
+  if (rc != RGBID_OK) return rc;
+  return rgbid_aligner_fetch(al, R_inout, t_inout, cov_out, status_out, trace_out);
+}
+
+int rgbid_aligner_frame_stats(rgbid_aligner* al, float* stats_out)
+{
+  if (!al || !stats_out) return RGBID_ERR_ARG;
+  for (int b = 0; b < al->cfg.batch; ++b) {
+    stats_out[3 * b + 0] = al->h_states[b].chi_square;
+    stats_out[3 * b + 1] = al->h_states[b].chi_test;
+    stats_out[3 * b + 2] = al->h_states[b].ndof;
+  }
+  return RGBID_OK;
+}
+
+int rgbid_aligner_map(rgbid_aligner* al, int which, int level, int index, float** ptr, size_t* pitch)
+{
+  if (!al || which < 0 || which >= MAP_COUNT || level < 0 || level >= al->cfg.levels || index < 0 ||
+      index >= al->cfg.batch || !ptr || !pitch)
+    return RGBID_ERR_ARG;
+  if (al->maps[which][level].p == nullptr) return RGBID_ERR_STATE;
+  ImgB v = al->view(which, level, index);
+  *ptr = v.p; *pitch = v.pitch;
+  return RGBID_OK;
+}
+
+}  // extern "C"
+
+namespace rgbid {
+
+// Launch (or replay) the schedule; d_init must already hold the initial guesses.
+int aligner_enqueue_device_init(rgbid_aligner* al)
+{
+  cudaStream_t s = al->ctx->stream;
+  if (!al->use_graph) {
+    aligner_record_schedule(al);
+    return check_last(al->ctx);
+  }
+  if (!al->gn_exec) {
+    long long before = al->ctx->launches;
+    cudaGraph_t graph = nullptr;
+    RGBID_CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    aligner_record_schedule(al);
+    cudaError_t e = cudaStreamEndCapture(s, &graph);
+    if (e != cudaSuccess) return RGBID_ERR_CUDA_BASE + (int)e;
+    al->gn_graph_launches = al->ctx->launches - before;
+    al->ctx->launches = before;
+    e = cudaGraphInstantiate(&al->gn_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { al->gn_exec = nullptr; return RGBID_ERR_CUDA_BASE + (int)e; }
+  }
+  RGBID_CUDA_TRY(cudaGraphLaunch(al->gn_exec, s));
+  al->ctx->launches += al->gn_graph_launches;
+  return RGBID_OK;
+}
+
+}  // namespace rgbid

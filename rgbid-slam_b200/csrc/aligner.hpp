@@ -1,0 +1,71 @@
+// aligner.hpp -- device-resident coarse-to-fine aligner for `batch` independent frame pairs.
+#pragma once
+#include <vector>
+#include "ctx.hpp"
+
+namespace rgbid {
+
+enum MapId {
+  MAP_W_KF = 0, MAP_I_KF, MAP_GWX, MAP_GWY, MAP_GIX, MAP_GIY, MAP_W_CUR, MAP_I_CUR,
+  MAP_CGWX, MAP_CGWY, MAP_CGIX, MAP_CGIY,  // covariance-only (bilateral-filtered) gradients, tracker mode
+  MAP_WF, MAP_IF,                          // bilateral-filtered keyframe pyramid (scratch), tracker mode
+  MAP_COUNT
+};
+
+struct LevelGeom {
+  int rows, cols;
+  size_t pitch, sstride;
+  int kept_rows, kept_cols, sample_stride;
+};
+
+}  // namespace rgbid
+
+struct rgbid_aligner {
+  rgbid_ctx* ctx;
+  rgbid_align_config cfg;
+  int niters;        // Gauss-Newton iterations per pair
+  int trace_stride;  // niters + 1 (covariance pass)
+  rgbid::LevelGeom geom[RGBID_MAX_LEVELS];
+  char* d_arena;
+  size_t arena_bytes;
+  rgbid::ImgB maps[rgbid::MAP_COUNT][RGBID_MAX_LEVELS];
+  rgbid::GnState* d_states;
+  rgbid::ScaleState* d_scales;
+  double* d_partials;
+  int partial_blocks;
+  unsigned int* d_counters;
+  rgbid_iter_trace* d_trace;
+  double* d_init;  // batch x (9 + 3)
+  uint16_t* d_depth_raw;
+  uint8_t* d_rgb_raw;
+  int* d_active;   // per-stream predicate for keyframe updates (tracker)
+  // pinned host mirrors
+  rgbid::GnState* h_states;
+  rgbid_iter_trace* h_trace;
+  double* h_init;
+  int* h_active;
+  // CUDA graph of the whole schedule
+  bool use_graph;
+  cudaGraphExec_t gn_exec;
+  long long gn_graph_launches;
+  int image_filtering;
+
+  rgbid::ImgB view(int which, int level, int index) const
+  {
+    rgbid::ImgB m = maps[which][level];
+    m.p = (float*)((char*)m.p + (size_t)index * m.sstride);
+    return m;
+  }
+};
+
+namespace rgbid {
+
+// Build pyramid + gradients (+ filtered gradients in tracker mode) of the keyframe maps of `batch` streams
+// starting at `first`; active (device, may be null) predicates streams.
+void aligner_keyframe_derivatives(rgbid_aligner* al, int first, int batch, const int* active, bool pyramid_from_l0);
+void aligner_current_pyramid(rgbid_aligner* al, int first, int batch);
+void aligner_copy_current_to_keyframe(rgbid_aligner* al, int first, int batch, const int* active);
+void aligner_record_schedule(rgbid_aligner* al);
+int aligner_enqueue_device_init(rgbid_aligner* al);
+
+}  // namespace rgbid

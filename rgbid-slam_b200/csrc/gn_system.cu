@@ -1,0 +1,522 @@
+// gn_system.cu -- the Gauss-Newton iteration kernels (the hot path).
+//
+// One reference iteration = warp inverse depth (K4) + warp intensity (K5) + two residual samplers (K11) +
+// up to 34 tiny scale-estimation launches with host round trips (K12/K13) + partial sums (K1) + final
+// reduction (K3) + device->host copy + host LLT / exp-map / pose update.  Here it is two launches and no
+// host involvement:
+//
+//   gn_scale_kernel : 8-CTA cluster per frame pair.  Warps + samples the sub-sampled residuals straight into
+//                     shared memory and runs the IRLS sigma / nu bisection rounds over DSMEM (scale_core.cuh).
+//   gn_build_kernel : fused warp + bilinear sample + residual + 2x6 Jacobian rows + Student/M-estimator weights
+//                     + the 27 upper-triangular J^T J | J^T r sums.  float4-vectorised coalesced reads of the 6
+//                     keyframe maps, gathers of the 2 current-frame maps through the read-only path, per-thread
+//                     FP32 accumulators, FP64 from the warp level up, deterministic per-CTA partials, and a
+//                     last-block-done tail that sums the partials in fixed order, solves the 6x6 system
+//                     (Cholesky), applies the SE(3) update and refreshes the pixel-space transforms of every
+//                     pyramid level -- or inverts A for the covariance.
+//
+// Algorithmic HBM bytes: 32 B per keyframe pixel per iteration (6 keyframe maps + 2 current-frame maps,
+// fp32); this kernel is bandwidth bound (about 5 flop/B), tensor cores do not apply.
+#include "scale_core.cuh"
+
+namespace rgbid {
+
+namespace {
+
+constexpr int kBuildThreads = 256;
+constexpr int kBuildWarps = kBuildThreads / 32;
+constexpr int kAcc = 27;
+constexpr int kAccChi = 31;  // + [rho_int, n_int, rho_depthinv, n_depthinv]
+
+struct PixelParams {
+  float fx, fy, cx, cy;
+  float inv_sigma_int, inv_sigma_depthinv;
+  float bias_over_sigma_int, bias_over_sigma_depthinv;
+  float nu_int, nu_depthinv;
+  int mestimator, weighting, student_nu;
+  int chi_mestimator;
+};
+
+__device__ __forceinline__ float chi_rho_dev(float e, int mest)
+{
+  float rho = (e * e) / 2.f;
+  if (mest == RGBID_HUBER) { if (fabsf(e) > 1.345f) rho = 1.345f * (fabsf(e) - 1.345f / 2.f); }
+  else if (mest == RGBID_TUKEY) {
+    if (fabsf(e) < 4.685f) {
+      float a1 = (e / 4.685f) * (e / 4.685f);
+      float a2 = (1.f - a1) * (1.f - a1) * (1.f - a1);
+      rho = ((4.685f * 4.685f) / 6.f) * (1.f - a2);
+    } else rho = (4.685f * 4.685f) / 6.f;
+  } else if (mest == RGBID_STUDENT) rho = ((5.f + 1.f) / 2.f) * logf(1.f + (e * e) / 5.f);
+  return rho;
+}
+
+// One keyframe pixel of computeSystemGridStride / computeStudentNuSystemGridStride
+// (src/cuda/estimate_VO.cu:176-262 constraints, :295-329 / :384-418 weights + accumulation).
+template <bool CHI>
+__device__ __forceinline__ void accumulate_pixel(float* __restrict__ acc, int x, int y, float w0, float i0, float gwx,
+                                                 float gwy, float gix, float giy, float w1, float i1,
+                                                 const PixelParams& pp)
+{
+  float px = (__int2float_rn(x) - pp.cx) / pp.fx;
+  float py = (__int2float_rn(y) - pp.cy) / pp.fy;
+
+  float rd[6], ri[6];
+  float err_d = 0.f, err_i = 0.f, wgt_d = 0.f, wgt_i = 0.f, n_factor = 1.f;
+  bool any = false;
+
+  // invDepthConstraint (estimate_VO.cu:214-262)
+  if (!(isnan(w0) || isnan(w1) || isnan(gwx) || isnan(gwy))) {
+    float g0 = gwx * pp.fx, g1 = gwy * pp.fy;
+    float g2 = -(g0 * px + g1 * py);
+    float inv_w0 = 1.f / w0;
+    float n0 = g0 * inv_w0, n1 = g1 * inv_w0, n2 = g2 * inv_w0 + 1.f;
+    float rn = rsqrtf(n0 * n0 + n1 * n1 + n2 * n2);
+    float rp = rsqrtf(px * px + py * py + 1.f);
+    n_factor = fabsf((n0 * rn) * (px * rp) + (n1 * rn) * (py * rp) + (n2 * rn) * rp);
+    float wgt = pp.inv_sigma_depthinv;
+    float t0 = g0 * w0, t1 = g1 * w0, t2 = g2 * w0 + w0 * w1;
+    float h2 = g2 + w1;
+    // row_rot = -(g x p), p = (px, py, 1)
+    float r0 = -(g1 - h2 * py), r1 = -(h2 * px - g0), r2 = -(g0 * py - g1 * px);
+    rd[0] = t0 * wgt; rd[1] = t1 * wgt; rd[2] = t2 * wgt; rd[3] = r0 * wgt; rd[4] = r1 * wgt; rd[5] = r2 * wgt;
+    float b = w1 - w0;
+    err_d = -b * wgt;
+    float eu = err_d - pp.bias_over_sigma_depthinv;
+    float wv = pp.student_nu ? (pp.nu_depthinv + 1.f) / (pp.nu_depthinv + eu * eu) : mest_weight(eu, pp.mestimator);
+    wgt_d = (pp.weighting == RGBID_PHOT_ONLY) ? 0.f : wv;
+    any = true;
+  }
+  // intensityConstraint (estimate_VO.cu:176-212)
+  if (!(isnan(w0) || isnan(i0) || isnan(i1) || isnan(gix) || isnan(giy))) {
+    float g0 = gix * pp.fx, g1 = giy * pp.fy;
+    float g2 = -(g0 * px + g1 * py);
+    float wgt = pp.inv_sigma_int;
+    float r0 = -(g1 - g2 * py), r1 = -(g2 * px - g0), r2 = -(g0 * py - g1 * px);
+    ri[0] = (g0 * w0) * wgt; ri[1] = (g1 * w0) * wgt; ri[2] = (g2 * w0) * wgt;
+    ri[3] = r0 * wgt; ri[4] = r1 * wgt; ri[5] = r2 * wgt;
+    float b = i1 - i0;
+    err_i = -b * wgt;
+    float eu = err_i - pp.bias_over_sigma_int;
+    float wv = pp.student_nu ? (pp.nu_int + 1.f) / (pp.nu_int + eu * eu) : mest_weight(eu, pp.mestimator);
+    wgt_i = (pp.weighting == RGBID_GEOM_ONLY) ? 0.f : wv;
+    any = true;
+  }
+  if (CHI) {
+    // end-of-frame chi^2 on all finite full-resolution residuals (src/visodo.cpp:1411-1414,
+    // sigmaFuncs.cu:137-150, 541-611) with the reference scales 5 / 0.0025
+    if (pp.chi_mestimator >= 0) {
+      float ei = (i1 - i0) / 5.f, ed = (w1 - w0) / 0.0025f;
+      if (!(isnan(ei) || isinf(ei))) { acc[27] += chi_rho_dev(ei, pp.chi_mestimator); acc[28] += 1.f; }
+      if (!(isnan(ed) || isinf(ed))) { acc[29] += chi_rho_dev(ed, pp.chi_mestimator); acc[30] += 1.f; }
+    }
+  }
+  if (!any) return;
+  if (pp.weighting == RGBID_MIN_WEIGHT) wgt_i = fminf(wgt_d, wgt_i);
+  // an invalid constraint contributes weight 0 (the reference multiplies stale rows by a zero weight)
+  if (wgt_i == 0.f) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) ri[k] = 0.f;
+    err_i = 0.f;
+  }
+  float wd = n_factor * wgt_d;
+  if (wgt_d == 0.f) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) rd[k] = 0.f;
+    err_d = 0.f; wd = 0.f;
+  }
+  int shift = 0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    float si = wgt_i * ri[i], sd = wd * rd[i];
+#pragma unroll
+    for (int j = i; j < 6; ++j) acc[shift++] += si * ri[j] + sd * rd[j];
+    acc[shift++] += si * err_i + sd * err_d;
+  }
+}
+
+struct BuildShared {
+  double warp_part[kBuildWarps][kAccChi];
+  double total[kAccChi];
+  double fin[8][kAccChi];
+  Proj proj;
+  int is_last;
+};
+
+// Block reduce + publish the per-CTA partial + elect the last CTA of this pair + fixed-order final sum.
+// Returns true in every thread of the last CTA, with sh.total[0..NACC) holding the pair's sums.
+template <int NACC>
+__device__ __forceinline__ bool reduce_and_elect(BuildShared& sh, const float* acc, double* __restrict__ partials,
+                                                 int partial_stride, unsigned int* __restrict__ counter, int nblk,
+                                                 int blk)
+{
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) {
+    double v = warp_sum((double)acc[k]);
+    if (lane == 0) sh.warp_part[wid][k] = v;
+  }
+  __syncthreads();
+  if (tid < NACC) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kBuildWarps; ++w) v += sh.warp_part[w][tid];
+    partials[(size_t)blk * partial_stride + tid] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    unsigned ticket = atomicAdd(counter, 1u);
+    sh.is_last = (ticket == (unsigned)(nblk - 1));
+  }
+  __syncthreads();
+  if (!sh.is_last) return false;
+  __threadfence();
+  // fixed-order final sum: value k is summed by 8 threads over interleaved CTAs, then combined in order
+  const int k = tid % 32, part = tid / 32;  // NACC <= 32, 8 parts
+  if (k < NACC) {
+    double v = 0.0;
+    for (int c = part; c < nblk; c += 8) v += __ldcg(&partials[(size_t)c * partial_stride + k]);
+    sh.fin[part][k] = v;
+  }
+  __syncthreads();
+  if (tid < NACC) {
+    double v = 0.0;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) v += sh.fin[p][tid];
+    sh.total[tid] = v;
+  }
+  __syncthreads();
+  if (tid == 0) *counter = 0u;  // ready for the next launch
+  return true;
+}
+
+__device__ __forceinline__ void refresh_proj(GnState& st, int levels, float fx0, float fy0, float cx0, float cy0)
+{
+  double Ri[9], ti[3];
+  mat3_inverse(st.R, Ri);
+  mat3_vec(Ri, st.t, ti);
+  ti[0] = -ti[0]; ti[1] = -ti[1]; ti[2] = -ti[2];
+  for (int l = 0; l < levels; ++l) {
+    float div = (float)(1 << l);  // Intr::operator()(level), src/internal.h:128-132
+    projective_pose(Ri, ti, fx0 / div, fy0 / div, cx0 / div, cy0 / div, st.proj[l].r, st.proj[l].t);
+  }
+}
+
+// Tail executed by one thread of the last CTA: the host part of one reference iteration
+// (src/visodo.cpp:1242-1274 / src/keyframe_align.cpp:312-350) or of the covariance pass (:1382-1415).
+__device__ __noinline__ void gn_tail(GnState& st, const double* tot, const GnParams& P, const ScaleState* sc,
+                        rgbid_iter_trace* __restrict__ trace, int b, bool chi)
+{
+  double A[36], bv[6], x[6] = {0, 0, 0, 0, 0, 0};
+  unpack_system(tot, A, bv);
+  if (P.compute_cov) {
+    for (int i = 0; i < 36; ++i) st.lastA[i] = A[i];
+    inverse6(A, st.cov);
+  }
+  if (chi && P.chi_mestimator >= 0) {
+    // computeChiSquare host part, sigmaFuncs.cu:1286-1287
+    float n = (float)(tot[28] + tot[30]);
+    float chi2 = (float)(tot[27] + tot[29]) / n;
+    float z = (chi2 - n) / sqrtf(2.f * n);
+    st.chi_square = chi2; st.ndof = n; st.chi_test = 0.5f * (1.f + erff(z / sqrtf(2.f)));
+  }
+  if (P.update_pose) {
+    llt_solve6(A, bv, x);
+    bool bad = gn_update(x, st.R, st.t);
+    if (bad) {
+      // lost: keep the previous pose, covariance 100 I (src/visodo.cpp:1265-1274)
+      st.status = RGBID_ERR_NAN;
+      for (int i = 0; i < 9; ++i) st.R[i] = st.R0[i];
+      for (int i = 0; i < 3; ++i) st.t[i] = st.t0[i];
+      for (int i = 0; i < 36; ++i) st.cov[i] = (i % 7 == 0) ? 100.0 : 0.0;
+    }
+    refresh_proj(st, P.levels, P.fx0, P.fy0, P.cx0, P.cy0);
+  }
+  if (trace != nullptr && P.trace_stride > 0 && P.iter_index >= 0 && P.iter_index < P.trace_stride) {
+    rgbid_iter_trace& T = trace[(size_t)b * P.trace_stride + P.iter_index];
+    T.level = P.level; T.iter = P.iter_index;
+    for (int i = 0; i < 27; ++i) T.sums27[i] = tot[i];
+    if (sc != nullptr && P.use_scale) {
+      T.sigma_int = sc->sigma_int; T.sigma_depthinv = sc->sigma_depthinv; T.bias_int = sc->bias_int;
+      T.bias_depthinv = sc->bias_depthinv; T.nu_int = sc->nu_int; T.nu_depthinv = sc->nu_depthinv;
+      T.irls_iters_int = sc->irls_iters_int; T.irls_iters_depthinv = sc->irls_iters_depthinv;
+    } else {
+      T.sigma_int = 5.f; T.sigma_depthinv = 0.0025f; T.bias_int = 0.f; T.bias_depthinv = 0.f;
+      T.nu_int = 5.f; T.nu_depthinv = 5.f; T.irls_iters_int = 0; T.irls_iters_depthinv = 0;
+    }
+    for (int i = 0; i < 6; ++i) T.x[i] = x[i];
+    for (int i = 0; i < 9; ++i) T.R[i] = st.R[i];
+    for (int i = 0; i < 3; ++i) T.t[i] = st.t[i];
+  }
+}
+
+__device__ __forceinline__ PixelParams make_pixel_params(const GnParams& P, const ScaleState* sc)
+{
+  PixelParams pp;
+  pp.fx = P.fx; pp.fy = P.fy; pp.cx = P.cx; pp.cy = P.cy;
+  float sigma_int = 5.f, sigma_d = 0.0025f, bias_int = 0.f, bias_d = 0.f, nu_int = 5.f, nu_d = 5.f;
+  if (P.use_scale && sc != nullptr) {
+    sigma_int = sc->sigma_int; sigma_d = sc->sigma_depthinv; bias_int = sc->bias_int; bias_d = sc->bias_depthinv;
+    nu_int = sc->nu_int; nu_d = sc->nu_depthinv;
+  }
+  pp.inv_sigma_int = 1.f / sigma_int; pp.inv_sigma_depthinv = 1.f / sigma_d;
+  pp.bias_over_sigma_int = bias_int / sigma_int; pp.bias_over_sigma_depthinv = bias_d / sigma_d;
+  pp.nu_int = nu_int; pp.nu_depthinv = nu_d;
+  pp.mestimator = P.mestimator; pp.weighting = P.weighting; pp.student_nu = P.student_nu;
+  pp.chi_mestimator = P.chi_mestimator;
+  return pp;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// gn_build_kernel.  grid = (ctas_per_pair, batch); VEC = pixels per thread step (4: float4 path, 1: scalar).
+// ------------------------------------------------------------------------------------------------------------
+template <int VEC, bool CHI>
+__global__ void __launch_bounds__(kBuildThreads, 2)
+    gn_build_kernel(const GnLevelMaps M, const GnParams P, GnState* __restrict__ states,
+                    const ScaleState* __restrict__ scales, double* __restrict__ partials, int partial_stride,
+                    unsigned int* __restrict__ counters, rgbid_iter_trace* __restrict__ trace)
+{
+  constexpr int NACC = CHI ? kAccChi : kAcc;
+  const int b = blockIdx.y;
+  GnState& st = states[b];
+  if (st.status != RGBID_OK) return;  // lost pairs are skipped consistently by every CTA
+  __shared__ BuildShared sh;
+  if (threadIdx.x < 12) {
+    const float* src = (const float*)&st.proj[P.level];
+    ((float*)&sh.proj)[threadIdx.x] = src[threadIdx.x];
+  }
+  __syncthreads();
+  const Proj proj = sh.proj;
+  const ScaleState* sc = scales ? &scales[b] : nullptr;
+  const PixelParams pp = make_pixel_params(P, sc);
+  const bool geom_is_warped = (P.mode == RGBID_MODE_TRACKER);
+
+  float acc[NACC];
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+
+  const float* Wc = M.Wc.row(b, 0);
+  const float* Ic = M.Ic.row(b, 0);
+  const int cols = P.cols, rows = P.rows;
+  const int upr = cols / VEC;  // units per row
+  const int total = upr * rows;
+  for (int u = blockIdx.x * kBuildThreads + threadIdx.x; u < total; u += gridDim.x * kBuildThreads) {
+    const int y = u / upr, x0 = (u - y * upr) * VEC;
+    float w0[VEC], i0[VEC], gwx[VEC], gwy[VEC], gix[VEC], giy[VEC];
+    if (VEC == 4) {
+      *(float4*)w0 = __ldg((const float4*)(M.W0.row(b, y) + x0));
+      *(float4*)i0 = __ldg((const float4*)(M.I0.row(b, y) + x0));
+      *(float4*)gwx = __ldg((const float4*)(M.gWx.row(b, y) + x0));
+      *(float4*)gwy = __ldg((const float4*)(M.gWy.row(b, y) + x0));
+      *(float4*)gix = __ldg((const float4*)(M.gIx.row(b, y) + x0));
+      *(float4*)giy = __ldg((const float4*)(M.gIy.row(b, y) + x0));
+    } else {
+      w0[0] = __ldg(M.W0.row(b, y) + x0); i0[0] = __ldg(M.I0.row(b, y) + x0);
+      gwx[0] = __ldg(M.gWx.row(b, y) + x0); gwy[0] = __ldg(M.gWy.row(b, y) + x0);
+      gix[0] = __ldg(M.gIx.row(b, y) + x0); giy[0] = __ldg(M.gIy.row(b, y) + x0);
+    }
+    float w1[VEC], i1[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k)
+      warp_pixel(proj, x0 + k, y, w0[k], Wc, M.Wc.pitch, Ic, M.Ic.pitch, cols, rows, geom_is_warped, w1[k], i1[k]);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k)
+      accumulate_pixel<CHI>(acc, x0 + k, y, w0[k], i0[k], gwx[k], gwy[k], gix[k], giy[k], w1[k], i1[k], pp);
+  }
+
+  if (!reduce_and_elect<NACC>(sh, acc, partials + (size_t)b * gridDim.x * partial_stride, partial_stride,
+                              &counters[b], gridDim.x, blockIdx.x))
+    return;
+  if (threadIdx.x == 0) gn_tail(st, sh.total, P, sc, trace, b, CHI);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Un-fused drop-in for buildSystem(StudentNu)GridStride on pre-warped maps (one pair)
+// ------------------------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(kBuildThreads, 2)
+    build_system_kernel(ImgB W0, ImgB I0, ImgB gWx, ImgB gWy, ImgB gIx, ImgB gIy, ImgB W1, ImgB I1, PixelParams pp,
+                        double* __restrict__ partials, unsigned int* __restrict__ counter, double* __restrict__ out27)
+{
+  __shared__ BuildShared sh;
+  float acc[kAcc];
+#pragma unroll
+  for (int k = 0; k < kAcc; ++k) acc[k] = 0.f;
+  const int upr = W0.cols / VEC, total = upr * W0.rows;
+  for (int u = blockIdx.x * kBuildThreads + threadIdx.x; u < total; u += gridDim.x * kBuildThreads) {
+    const int y = u / upr, x0 = (u - y * upr) * VEC;
+    float w0[VEC], i0[VEC], gwx[VEC], gwy[VEC], gix[VEC], giy[VEC], w1[VEC], i1[VEC];
+    if (VEC == 4) {
+      *(float4*)w0 = __ldg((const float4*)(W0.row(0, y) + x0));
+      *(float4*)i0 = __ldg((const float4*)(I0.row(0, y) + x0));
+      *(float4*)gwx = __ldg((const float4*)(gWx.row(0, y) + x0));
+      *(float4*)gwy = __ldg((const float4*)(gWy.row(0, y) + x0));
+      *(float4*)gix = __ldg((const float4*)(gIx.row(0, y) + x0));
+      *(float4*)giy = __ldg((const float4*)(gIy.row(0, y) + x0));
+      *(float4*)w1 = __ldg((const float4*)(W1.row(0, y) + x0));
+      *(float4*)i1 = __ldg((const float4*)(I1.row(0, y) + x0));
+    } else {
+      w0[0] = W0.row(0, y)[x0]; i0[0] = I0.row(0, y)[x0]; gwx[0] = gWx.row(0, y)[x0]; gwy[0] = gWy.row(0, y)[x0];
+      gix[0] = gIx.row(0, y)[x0]; giy[0] = gIy.row(0, y)[x0]; w1[0] = W1.row(0, y)[x0]; i1[0] = I1.row(0, y)[x0];
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k)
+      accumulate_pixel<false>(acc, x0 + k, y, w0[k], i0[k], gwx[k], gwy[k], gix[k], giy[k], w1[k], i1[k], pp);
+  }
+  if (!reduce_and_elect<kAcc>(sh, acc, partials, kAccChi, counter, gridDim.x, blockIdx.x)) return;
+  if (threadIdx.x < kAcc) out27[threadIdx.x] = sh.total[threadIdx.x];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// gn_scale_kernel: fused warp + residual sampling + scale estimation; one 8-CTA cluster per pair.
+// Sampling geometry of computeErrorGridStride (sigmaFuncs.cu:711-747): sample (s y, s x) -> index y*kept_cols+x.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(kScaleCluster, 1, 1) __launch_bounds__(kScaleThreads)
+    gn_scale_kernel(const GnLevelMaps M, const GnParams P, const GnState* __restrict__ states,
+                    ScaleState* __restrict__ scales)
+{
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ float smem_samples[];
+  __shared__ ScaleShared sh;
+  __shared__ Proj s_proj;
+  const int b = blockIdx.x / kScaleCluster;
+  const int rank = (int)cluster.block_rank();
+  const GnState& st = states[b];
+  if (st.status != RGBID_OK) return;  // uniform over the whole cluster
+  if (threadIdx.x < 12) ((float*)&s_proj)[threadIdx.x] = ((const float*)&st.proj[P.level])[threadIdx.x];
+  __syncthreads();
+  const Proj proj = s_proj;
+
+  const int n = P.kept_rows * P.kept_cols;
+  const int chunk = (n + kScaleCluster - 1) / kScaleCluster;
+  const int begin = min(rank * chunk, n);
+  const int n_local = min(chunk, n - begin);
+  float* samp_int = smem_samples;
+  float* samp_dep = smem_samples + chunk;
+  const bool geom_is_warped = (P.mode == RGBID_MODE_TRACKER);
+  const float* Wc = M.Wc.row(b, 0);
+  const float* Ic = M.Ic.row(b, 0);
+  const int s = P.sample_stride;
+  for (int il = threadIdx.x; il < n_local; il += kScaleThreads) {
+    const int i = begin + il;
+    const int ys = i / P.kept_cols, xs = i - ys * P.kept_cols;
+    const int x = s * xs, y = s * ys;
+    float w0 = __ldg(M.W0.row(b, y) + x), i0 = __ldg(M.I0.row(b, y) + x);
+    float w1, i1;
+    warp_pixel(proj, x, y, w0, Wc, M.Wc.pitch, Ic, M.Ic.pitch, P.cols, P.rows, geom_is_warped, w1, i1);
+    samp_int[il] = i1 - i0;
+    samp_dep[il] = w1 - w0;
+  }
+  __syncthreads();
+
+  ScaleSlot s_int, s_dep;
+  slot_init(s_int, P.sigma_op, P.mestimator, 0.f, 5.f, true);      // seeds: src/visodo.cpp:1168-1173
+  slot_init(s_dep, P.sigma_op, P.mestimator, 0.f, 0.0025f, true);  //        src/keyframe_align.cpp:284-289
+  scale_rounds(cluster, sh, s_int, s_dep, samp_int, samp_dep, n_local);
+
+  if (rank == 0 && threadIdx.x == 0) {
+    ScaleState out;
+    out.bias_int = s_int.out_bias; out.sigma_int = s_int.out_sigma;
+    out.bias_depthinv = s_dep.out_bias; out.sigma_depthinv = s_dep.out_sigma;
+    out.nu_depthinv = s_dep.nu;
+    // tracker: nu_int = max(nu_int, nu_depthinv) (src/visodo.cpp:1186);
+    // KeyframeAlign passes nu_depthinv for both residuals (src/keyframe_align.cpp:308)
+    out.nu_int = (P.mode == RGBID_MODE_TRACKER) ? fmaxf(s_int.nu, s_dep.nu) : s_dep.nu;
+    out.irls_iters_int = s_int.irls_iters; out.irls_iters_depthinv = s_dep.irls_iters;
+    scales[b] = out;
+  }
+}
+
+__global__ void gn_init_kernel(GnState* __restrict__ states, const double* __restrict__ R_init,
+                               const double* __restrict__ t_init, int batch, int levels, float fx0, float fy0,
+                               float cx0, float cy0)
+{
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  GnState& st = states[b];
+  for (int i = 0; i < 9; ++i) { st.R[i] = R_init[9 * b + i]; st.R0[i] = st.R[i]; }
+  for (int i = 0; i < 3; ++i) { st.t[i] = t_init[3 * b + i]; st.t0[i] = st.t[i]; }
+  for (int i = 0; i < 36; ++i) { st.cov[i] = 0.0; st.lastA[i] = 0.0; }
+  st.status = RGBID_OK; st.iter_count = 0;
+  st.chi_square = 0.f; st.chi_test = 0.f; st.ndof = 0.f;
+  refresh_proj(st, levels, fx0, fy0, cx0, cy0);
+}
+
+inline bool aligned16(const ImgB& m) { return ((uintptr_t)m.p % 16 == 0) && (m.pitch % 16 == 0) && (m.sstride % 16 == 0); }
+
+}  // namespace
+
+int gn_build_grid_x(int rows, int cols, int batch, int num_sms)
+{
+  // Enough CTAs for one balanced wave at 2 CTAs / SM across the batch, never more than one quad per thread
+  // would need, and at most num_sms per pair so the last-block final sum stays short.
+  int units = (cols % 4 == 0) ? (cols / 4) * rows : cols * rows;
+  int need = (units + kBuildThreads - 1) / kBuildThreads;
+  int target = (2 * num_sms + batch - 1) / batch;
+  if (target < 4) target = 4;
+  if (target > num_sms) target = num_sms;
+  int g = need < target ? need : target;
+  return g < 1 ? 1 : g;
+}
+
+void launch_gn_init(const LaunchCtx& L, GnState* states, const double* R_init, const double* t_init, int batch,
+                    int levels, float fx0, float fy0, float cx0, float cy0)
+{
+  gn_init_kernel<<<(batch + 63) / 64, 64, 0, L.stream>>>(states, R_init, t_init, batch, levels, fx0, fy0, cx0, cy0);
+  ++*L.launches;
+}
+
+void launch_gn_scale(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P, GnState* states, ScaleState* scales)
+{
+  const int n = P.kept_rows * P.kept_cols;
+  const int chunk = (n + kScaleCluster - 1) / kScaleCluster;
+  size_t smem = (size_t)2 * chunk * sizeof(float);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(gn_scale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  gn_scale_kernel<<<kScaleCluster * P.batch, kScaleThreads, smem, L.stream>>>(M, P, states, scales);
+  ++*L.launches;
+}
+
+void launch_gn_build(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P, GnState* states,
+                     const ScaleState* scales, double* partials, int partial_stride, unsigned int* counters,
+                     rgbid_iter_trace* trace)
+{
+  bool vec = (P.cols % 4 == 0) && aligned16(M.W0) && aligned16(M.I0) && aligned16(M.gWx) && aligned16(M.gWy) &&
+             aligned16(M.gIx) && aligned16(M.gIy);
+  dim3 grid(gn_build_grid_x(P.rows, P.cols, P.batch, L.num_sms), P.batch);
+  const bool chi = (P.chi_mestimator >= 0);
+  if (vec) {
+    if (chi) gn_build_kernel<4, true><<<grid, kBuildThreads, 0, L.stream>>>(M, P, states, scales, partials, partial_stride, counters, trace);
+    else gn_build_kernel<4, false><<<grid, kBuildThreads, 0, L.stream>>>(M, P, states, scales, partials, partial_stride, counters, trace);
+  } else {
+    if (chi) gn_build_kernel<1, true><<<grid, kBuildThreads, 0, L.stream>>>(M, P, states, scales, partials, partial_stride, counters, trace);
+    else gn_build_kernel<1, false><<<grid, kBuildThreads, 0, L.stream>>>(M, P, states, scales, partials, partial_stride, counters, trace);
+  }
+  ++*L.launches;
+}
+
+void launch_build_system(const LaunchCtx& L, ImgB W0, ImgB I0, ImgB gWx, ImgB gWy, ImgB gIx, ImgB gIy, ImgB W1,
+                         ImgB I1, const rgbid_system_params& sp, double* partials, unsigned int* counter,
+                         double* out27)
+{
+  PixelParams pp;
+  pp.fx = sp.fx; pp.fy = sp.fy; pp.cx = sp.cx; pp.cy = sp.cy;
+  pp.inv_sigma_int = 1.f / sp.sigma_int; pp.inv_sigma_depthinv = 1.f / sp.sigma_depthinv;
+  pp.bias_over_sigma_int = sp.bias_int / sp.sigma_int;
+  pp.bias_over_sigma_depthinv = sp.bias_depthinv / sp.sigma_depthinv;
+  pp.nu_int = sp.nu_int; pp.nu_depthinv = sp.nu_depthinv;
+  pp.mestimator = sp.mestimator; pp.weighting = sp.weighting; pp.student_nu = sp.student_nu;
+  pp.chi_mestimator = -1;
+  bool vec = (W0.cols % 4 == 0) && aligned16(W0) && aligned16(I0) && aligned16(gWx) && aligned16(gWy) &&
+             aligned16(gIx) && aligned16(gIy) && aligned16(W1) && aligned16(I1);
+  int grid = gn_build_grid_x(W0.rows, W0.cols, 1, L.num_sms);
+  if (vec) build_system_kernel<4><<<grid, kBuildThreads, 0, L.stream>>>(W0, I0, gWx, gWy, gIx, gIy, W1, I1, pp, partials, counter, out27);
+  else build_system_kernel<1><<<grid, kBuildThreads, 0, L.stream>>>(W0, I0, gWx, gWy, gIx, gIy, W1, I1, pp, partials, counter, out27);
+  ++*L.launches;
+}
+
+}  // namespace rgbid

@@ -1,0 +1,375 @@
+// image_ops.cu -- frame ingest, pyramid, gradients, bilateral filter, vertex / normal maps.
+//
+// B200 notes: all of these are streaming / small-stencil kernels bound by HBM (or L2 once a frame pair is
+// resident).  Each launch covers every stream of the batch (blockIdx.z) and, where the reference issues
+// one launch per map (intensity and inverse depth separately), both maps at once.  Loads are coalesced
+// along rows; the ingest kernel moves 4 pixels per thread with 32/64/128-bit accesses.
+#include "kernels.cuh"
+
+namespace rgbid {
+
+namespace {
+
+constexpr int BX = 32, BY = 8;
+
+inline dim3 grid2d(int cols, int rows, int z) { return dim3((cols + BX - 1) / BX, (rows + BY - 1) / BY, z); }
+
+#define RGBID_ACTIVE_GUARD(b) \
+  if (active != nullptr && active[b] == 0) return
+
+// ---- ingest: K18 + K19 fused (src/cuda/misc.cu:105-147) ------------------------------------------
+__device__ __forceinline__ float depth_to_invdepth(int value, float inv_factor_1000)
+{
+  // (1/factor_depth)*1000 / clamp(d_mm, 0, 10000); 0 -> NaN   (misc.cu:116-121)
+  return value > 0 ? inv_factor_1000 / __int2float_rn(min(value, 10000)) : qnanf();
+}
+
+__device__ __forceinline__ float luma(unsigned r, unsigned g, unsigned b)
+{
+  float v = 0.2126f * __uint2float_rn(r) + 0.7152f * __uint2float_rn(g) + 0.0722f * __uint2float_rn(b);
+  return fmaxf(0.f, fminf(v, 255.f));
+}
+
+// 4 pixels per thread: 12 B of RGB (3 x 32-bit), 8 B of depth (1 x 64-bit), two float4 stores.
+__global__ void __launch_bounds__(256) ingest_vec4_kernel(const uint16_t* __restrict__ depth, size_t dpitch,
+                                                          size_t dstride, const uint8_t* __restrict__ rgb,
+                                                          size_t cpitch, size_t cstride, ImgB W, ImgB I,
+                                                          float inv_factor_1000)
+{
+  const int b = blockIdx.y;
+  const int qpr = W.cols >> 2;
+  const int total = qpr * W.rows;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+    int y = q / qpr, xq = q - y * qpr;
+    if (depth != nullptr) {
+      const uint2 d = *(const uint2*)((const char*)depth + (size_t)b * dstride + (size_t)y * dpitch + (size_t)xq * 8);
+      float4 w;
+      w.x = depth_to_invdepth(d.x & 0xffff, inv_factor_1000);
+      w.y = depth_to_invdepth(d.x >> 16, inv_factor_1000);
+      w.z = depth_to_invdepth(d.y & 0xffff, inv_factor_1000);
+      w.w = depth_to_invdepth(d.y >> 16, inv_factor_1000);
+      *(float4*)(W.row(b, y) + 4 * xq) = w;
+    }
+    if (rgb != nullptr) {
+      const uint32_t* c = (const uint32_t*)((const char*)rgb + (size_t)b * cstride + (size_t)y * cpitch + (size_t)xq * 12);
+      uint32_t c0 = c[0], c1 = c[1], c2 = c[2];
+      float4 i;
+      i.x = luma(c0 & 0xff, (c0 >> 8) & 0xff, (c0 >> 16) & 0xff);
+      i.y = luma(c0 >> 24, c1 & 0xff, (c1 >> 8) & 0xff);
+      i.z = luma((c1 >> 16) & 0xff, c1 >> 24, c2 & 0xff);
+      i.w = luma((c2 >> 8) & 0xff, (c2 >> 16) & 0xff, c2 >> 24);
+      *(float4*)(I.row(b, y) + 4 * xq) = i;
+    }
+  }
+}
+
+__global__ void ingest_scalar_kernel(const uint16_t* __restrict__ depth, size_t dpitch, size_t dstride,
+                                     const uint8_t* __restrict__ rgb, size_t cpitch, size_t cstride, ImgB W,
+                                     ImgB I, float inv_factor_1000)
+{
+  const int b = blockIdx.z;
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  int cols = depth ? W.cols : I.cols, rows = depth ? W.rows : I.rows;
+  if (x >= cols || y >= rows) return;
+  if (depth != nullptr) {
+    const uint16_t* d = (const uint16_t*)((const char*)depth + (size_t)b * dstride + (size_t)y * dpitch);
+    W.row(b, y)[x] = depth_to_invdepth(d[x], inv_factor_1000);
+  }
+  if (rgb != nullptr) {
+    const uint8_t* c = rgb + (size_t)b * cstride + (size_t)y * cpitch + (size_t)x * 3;
+    I.row(b, y)[x] = luma(c[0], c[1], c[2]);
+  }
+}
+
+__global__ void decompose_rgb_kernel(const uint8_t* __restrict__ rgb, size_t spitch, ImgB r, ImgB g, ImgB bch)
+{
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= r.cols || y >= r.rows) return;
+  const uint8_t* c = rgb + (size_t)y * spitch + (size_t)x * 3;
+  r.row(0, y)[x] = __uint2float_rn(c[0]);
+  g.row(0, y)[x] = __uint2float_rn(c[1]);
+  bch.row(0, y)[x] = __uint2float_rn(c[2]);
+}
+
+// ---- pyramid: K16 (src/cuda/pyrdown.cu:84-132) --------------------------------------------------
+__global__ void __launch_bounds__(BX* BY) pyr_down2_kernel(ImgB srcA, ImgB dstA, ImgB srcB, ImgB dstB, int batch,
+                                                            const int* __restrict__ active)
+{
+  const int z = blockIdx.z;
+  const int b = z % batch;
+  RGBID_ACTIVE_GUARD(b);
+  const ImgB& src = (z < batch) ? srcA : srcB;
+  const ImgB& dst = (z < batch) ? dstA : dstB;
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= dst.cols || y >= dst.rows) return;
+  const int R = 2;
+  int tx = min(2 * x + R + 1, src.cols), ty = min(2 * y + R + 1, src.rows);
+  float sum1 = 0.f, sum2 = 0.f;
+  int count = 0;
+  for (int cy = max(0, 2 * y - R); cy < ty; ++cy) {
+    const float* srow = src.row(b, cy);
+    for (int cx = max(0, 2 * x - R); cx < tx; ++cx) {
+      float val = __ldg(srow + cx);
+      if (!isnan(val)) {
+        float space2 = __int2float_rn((2 * x - cx) * (2 * x - cx) + (2 * y - cy) * (2 * y - cy));
+        float weight = __expf(-(space2 * 0.5f));
+        sum1 += val * weight;
+        sum2 += weight;
+        ++count;
+      }
+    }
+  }
+  dst.row(b, y)[x] = (count > 12) ? sum1 / sum2 : qnanf();
+}
+
+// ---- gradients: K21 (src/cuda/misc.cu:176-220) ----------------------------------------------------
+__global__ void __launch_bounds__(BX* BY) gradient2_kernel(ImgB srcA, ImgB gxA, ImgB gyA, ImgB srcB, ImgB gxB,
+                                                            ImgB gyB, int batch, const int* __restrict__ active)
+{
+  const int z = blockIdx.z;
+  const int b = z % batch;
+  RGBID_ACTIVE_GUARD(b);
+  const ImgB& src = (z < batch) ? srcA : srcB;
+  const ImgB& gx = (z < batch) ? gxA : gxB;
+  const ImgB& gy = (z < batch) ? gyA : gyB;
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= src.cols || y >= src.rows) return;
+  float rh = 0.f, rv = 0.f;
+#pragma unroll
+  for (int dx = -1; dx < 2; ++dx) {
+#pragma unroll
+    for (int dy = -1; dy < 2; ++dy) {
+      int cx = min(max(0, x + dx), src.cols - 1);
+      int cy = min(max(0, y + dy), src.rows - 1);
+      float t = __ldg(src.row(b, cy) + cx);
+      // zero weights are kept on purpose: 0 * NaN = NaN invalidates the pixel as in the reference
+      rh += t * (float)(dx * (2 - dy * dy));
+      rv += t * (float)(dy * (2 - dx * dx));
+    }
+  }
+  gx.row(b, y)[x] = rh / 8.f;
+  gy.row(b, y)[x] = rv / 8.f;
+}
+
+// ---- bilateral: K23 (src/cuda/filters.cu:86-135) ----------------------------------------------------
+__global__ void __launch_bounds__(BX* BY) bilateral2_kernel(ImgB srcA, ImgB dstA, float sigmaA, ImgB srcB,
+                                                             ImgB dstB, float sigmaB, int batch,
+                                                             const int* __restrict__ active)
+{
+  const int z = blockIdx.z;
+  const int b = z % batch;
+  RGBID_ACTIVE_GUARD(b);
+  const ImgB& src = (z < batch) ? srcA : srcB;
+  const ImgB& dst = (z < batch) ? dstA : dstB;
+  const float sigma_floatmap = (z < batch) ? sigmaA : sigmaB;
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= src.cols || y >= src.rows) return;
+  const int R = 2;
+  float value = __ldg(src.row(b, y) + x);
+  if (isnan(value)) { dst.row(b, y)[x] = qnanf(); return; }
+  int tx = min(x + R + 1, src.cols), ty = min(y + R + 1, src.rows);
+  const float s2ih = 0.5f / (5.f * 5.f);  // sigma_space = 5 (filters.cu:83)
+  float sum1 = 0.f, sum2 = 0.f;
+  for (int cy = max(y - R, 0); cy < ty; ++cy) {
+    const float* srow = src.row(b, cy);
+    for (int cx = max(x - R, 0); cx < tx; ++cx) {
+      float tmp = __ldg(srow + cx);
+      if (!isnan(tmp)) {
+        float space2 = __int2float_rn((x - cx) * (x - cx) + (y - cy) * (y - cy));
+        float fn = (value - tmp) / sigma_floatmap;
+        float weight = __expf(-(s2ih * space2 + 0.5f * fn * fn));
+        sum1 += tmp * weight;
+        sum2 += weight;
+      }
+    }
+  }
+  dst.row(b, y)[x] = sum1 / sum2;
+}
+
+// ---- copies / fills: K22 --------------------------------------------------------------------------
+__global__ void copy2_kernel(ImgB srcA, ImgB dstA, ImgB srcB, ImgB dstB, int batch, const int* __restrict__ active)
+{
+  const int z = blockIdx.z;
+  const int b = z % batch;
+  RGBID_ACTIVE_GUARD(b);
+  const ImgB& src = (z < batch) ? srcA : srcB;
+  const ImgB& dst = (z < batch) ? dstA : dstB;
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= src.cols || y >= src.rows) return;
+  dst.row(b, y)[x] = src.row(b, y)[x];
+}
+
+__global__ void fill_kernel(ImgB dst, float value, const int* __restrict__ active)
+{
+  const int b = blockIdx.z;
+  RGBID_ACTIVE_GUARD(b);
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= dst.cols || y >= dst.rows) return;
+  dst.row(b, y)[x] = value;
+}
+
+__global__ void fill_u8_kernel(uint8_t* dst, size_t pitch, size_t sstride, int rows, int cols, uint8_t value,
+                               const int* __restrict__ active)
+{
+  const int b = blockIdx.z;
+  RGBID_ACTIVE_GUARD(b);
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= cols || y >= rows) return;
+  dst[(size_t)b * sstride + (size_t)y * pitch + x] = value;
+}
+
+// ---- vertex / normal maps: K24 (src/cuda/maps.cu:63-90, 134-179) ------------------------------------
+__global__ void vmap_kernel(ImgB depth_inv, ImgB vmap, float fx_inv, float fy_inv, float cx, float cy,
+                            const int* __restrict__ active)
+{
+  const int b = blockIdx.z;
+  RGBID_ACTIVE_GUARD(b);
+  int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y * blockDim.y + threadIdx.y;
+  const int rows = depth_inv.rows;
+  if (u >= depth_inv.cols || v >= rows) return;
+  float z = 1.f / depth_inv.row(b, v)[u];
+  if (!isnan(z)) {
+    vmap.row(b, v)[u] = z * (__int2float_rn(u) - cx) * fx_inv;
+    vmap.row(b, v + rows)[u] = z * (__int2float_rn(v) - cy) * fy_inv;
+    vmap.row(b, v + 2 * rows)[u] = z;
+  } else {
+    vmap.row(b, v)[u] = qnanf();  // only the x plane is invalidated, as in the reference
+  }
+}
+
+__global__ void nmap_gradients_kernel(ImgB depth_inv, ImgB gx_, ImgB gy_, ImgB nmap, float fx, float fy, float cx,
+                                      float cy, const int* __restrict__ active)
+{
+  const int b = blockIdx.z;
+  RGBID_ACTIVE_GUARD(b);
+  int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y * blockDim.y + threadIdx.y;
+  const int rows = depth_inv.rows;
+  if (u >= depth_inv.cols || v >= rows) return;
+  float nx_out = qnanf();
+  float w = depth_inv.row(b, v)[u], gx = gx_.row(b, v)[u], gy = gy_.row(b, v)[u];
+  if (!(isnan(w) || isnan(gx) || isnan(gy))) {
+    float nx = gx * fx, ny = gy * fy;
+    float nz = gx * (cx - __int2float_rn(u)) + gy * (cy - __int2float_rn(v)) + w;
+    float rn = rsqrtf(nx * nx + ny * ny + nz * nz);
+    nx *= rn; ny *= rn; nz *= rn;
+    float z = 1.f / w;
+    float vx = z * (__int2float_rn(u) - cx) * (1.f / fx);
+    float vy = z * (__int2float_rn(v) - cy) * (1.f / fy);
+    float rv = rsqrtf(vx * vx + vy * vy + z * z);
+    float d = (vx * rv) * nx + (vy * rv) * ny + (z * rv) * nz;
+    if (d > 0.1f) {  // grazing-angle cut (maps.cu:170)
+      nx_out = nx;
+      nmap.row(b, v + rows)[u] = ny;
+      nmap.row(b, v + 2 * rows)[u] = nz;
+    }
+  }
+  nmap.row(b, v)[u] = nx_out;
+}
+
+inline bool aligned(const void* p, size_t a) { return ((uintptr_t)p % a) == 0; }
+
+}  // namespace
+
+// --------------------------------------------------------------------------------------------------
+void launch_ingest(const LaunchCtx& L, const uint16_t* depth, size_t dpitch, size_t dstride, const uint8_t* rgb,
+                   size_t cpitch, size_t cstride, ImgB W, ImgB I, int batch, float factor_depth)
+{
+  const ImgB& ref = depth ? W : I;
+  float inv_factor_1000 = (1.f / factor_depth) * 1000.f;
+  bool vec = (ref.cols % 4 == 0);
+  if (depth) vec = vec && aligned(depth, 8) && dpitch % 8 == 0 && dstride % 8 == 0 && aligned(W.p, 16) && W.pitch % 16 == 0 && W.sstride % 16 == 0;
+  if (rgb) vec = vec && aligned(rgb, 4) && cpitch % 4 == 0 && cstride % 4 == 0 && aligned(I.p, 16) && I.pitch % 16 == 0 && I.sstride % 16 == 0;
+  if (vec) {
+    int total = (ref.cols / 4) * ref.rows;
+    int gx = (total + 255) / 256;
+    ingest_vec4_kernel<<<dim3(gx, batch), 256, 0, L.stream>>>(depth, dpitch, dstride, rgb, cpitch, cstride, W, I,
+                                                             inv_factor_1000);
+  } else {
+    ingest_scalar_kernel<<<grid2d(ref.cols, ref.rows, batch), dim3(BX, BY), 0, L.stream>>>(
+        depth, dpitch, dstride, rgb, cpitch, cstride, W, I, inv_factor_1000);
+  }
+  ++*L.launches;
+}
+
+void launch_depth_to_invdepth(const LaunchCtx& L, const uint16_t* src, size_t spitch, size_t sstride, ImgB dst,
+                              int batch, float factor_depth)
+{
+  launch_ingest(L, src, spitch, sstride, nullptr, 0, 0, dst, dst, batch, factor_depth);
+}
+
+void launch_intensity(const LaunchCtx& L, const uint8_t* rgb, size_t spitch, size_t sstride, ImgB dst, int batch)
+{
+  launch_ingest(L, nullptr, 0, 0, rgb, spitch, sstride, dst, dst, batch, 1.f);
+}
+
+void launch_decompose_rgb(const LaunchCtx& L, const uint8_t* rgb, size_t spitch, ImgB r, ImgB g, ImgB b)
+{
+  decompose_rgb_kernel<<<grid2d(r.cols, r.rows, 1), dim3(BX, BY), 0, L.stream>>>(rgb, spitch, r, g, b);
+  ++*L.launches;
+}
+
+void launch_pyr_down2(const LaunchCtx& L, ImgB srcA, ImgB dstA, ImgB srcB, ImgB dstB, int batch, const int* active)
+{
+  int nm = srcB.p ? 2 : 1;
+  pyr_down2_kernel<<<grid2d(dstA.cols, dstA.rows, batch * nm), dim3(BX, BY), 0, L.stream>>>(srcA, dstA, srcB, dstB,
+                                                                                            batch, active);
+  ++*L.launches;
+}
+
+void launch_gradient2(const LaunchCtx& L, ImgB srcA, ImgB gxA, ImgB gyA, ImgB srcB, ImgB gxB, ImgB gyB, int batch,
+                      const int* active)
+{
+  int nm = srcB.p ? 2 : 1;
+  gradient2_kernel<<<grid2d(srcA.cols, srcA.rows, batch * nm), dim3(BX, BY), 0, L.stream>>>(srcA, gxA, gyA, srcB, gxB,
+                                                                                            gyB, batch, active);
+  ++*L.launches;
+}
+
+void launch_bilateral2(const LaunchCtx& L, ImgB srcA, ImgB dstA, float sigmaA, ImgB srcB, ImgB dstB, float sigmaB,
+                       int batch, const int* active)
+{
+  int nm = srcB.p ? 2 : 1;
+  bilateral2_kernel<<<grid2d(srcA.cols, srcA.rows, batch * nm), dim3(BX, BY), 0, L.stream>>>(
+      srcA, dstA, sigmaA, srcB, dstB, sigmaB, batch, active);
+  ++*L.launches;
+}
+
+void launch_copy2(const LaunchCtx& L, ImgB srcA, ImgB dstA, ImgB srcB, ImgB dstB, int batch, const int* active)
+{
+  int nm = srcB.p ? 2 : 1;
+  copy2_kernel<<<grid2d(srcA.cols, srcA.rows, batch * nm), dim3(BX, BY), 0, L.stream>>>(srcA, dstA, srcB, dstB, batch,
+                                                                                        active);
+  ++*L.launches;
+}
+
+void launch_fill(const LaunchCtx& L, ImgB dst, float value, int batch, const int* active)
+{
+  fill_kernel<<<grid2d(dst.cols, dst.rows, batch), dim3(BX, BY), 0, L.stream>>>(dst, value, active);
+  ++*L.launches;
+}
+
+void launch_fill_u8(const LaunchCtx& L, uint8_t* dst, size_t pitch, size_t sstride, int rows, int cols,
+                    uint8_t value, int batch, const int* active)
+{
+  fill_u8_kernel<<<grid2d(cols, rows, batch), dim3(BX, BY), 0, L.stream>>>(dst, pitch, sstride, rows, cols, value,
+                                                                          active);
+  ++*L.launches;
+}
+
+void launch_vmap(const LaunchCtx& L, ImgB depth_inv, ImgB vmap, float fx, float fy, float cx, float cy, int batch,
+                 const int* active)
+{
+  vmap_kernel<<<grid2d(depth_inv.cols, depth_inv.rows, batch), dim3(BX, BY), 0, L.stream>>>(
+      depth_inv, vmap, 1.f / fx, 1.f / fy, cx, cy, active);
+  ++*L.launches;
+}
+
+void launch_nmap_gradients(const LaunchCtx& L, ImgB depth_inv, ImgB gx, ImgB gy, ImgB nmap, float fx, float fy,
+                           float cx, float cy, int batch, const int* active)
+{
+  nmap_gradients_kernel<<<grid2d(depth_inv.cols, depth_inv.rows, batch), dim3(BX, BY), 0, L.stream>>>(
+      depth_inv, gx, gy, nmap, fx, fy, cx, cy, active);
+  ++*L.launches;
+}
+
+}  // namespace rgbid

@@ -1,0 +1,128 @@
+// kernels.cuh -- internal launchers (C++ linkage) shared by the C-ABI layer.
+#pragma once
+#include "common.cuh"
+
+namespace rgbid {
+
+// Launch bookkeeping: every launcher bumps *launches (bench.py's gpu_launches).
+struct LaunchCtx {
+  cudaStream_t stream;
+  long long* launches;
+  int num_sms;
+};
+
+// ---- image_ops.cu ---------------------------------------------------------------------------------
+void launch_depth_to_invdepth(const LaunchCtx& L, const uint16_t* src, size_t spitch, size_t sstride, ImgB dst,
+                              int batch, float factor_depth);
+void launch_intensity(const LaunchCtx& L, const uint8_t* rgb, size_t spitch, size_t sstride, ImgB dst, int batch);
+void launch_ingest(const LaunchCtx& L, const uint16_t* depth, size_t dpitch, size_t dstride, const uint8_t* rgb,
+                   size_t cpitch, size_t cstride, ImgB W, ImgB I, int batch, float factor_depth);
+void launch_decompose_rgb(const LaunchCtx& L, const uint8_t* rgb, size_t spitch, ImgB r, ImgB g, ImgB b);
+// two maps (A, B) down-sampled in one launch; B may have p == nullptr
+void launch_pyr_down2(const LaunchCtx& L, ImgB srcA, ImgB dstA, ImgB srcB, ImgB dstB, int batch,
+                      const int* active = nullptr);
+void launch_gradient2(const LaunchCtx& L, ImgB srcA, ImgB gxA, ImgB gyA, ImgB srcB, ImgB gxB, ImgB gyB, int batch,
+                      const int* active = nullptr);
+void launch_bilateral2(const LaunchCtx& L, ImgB srcA, ImgB dstA, float sigmaA, ImgB srcB, ImgB dstB, float sigmaB,
+                       int batch, const int* active = nullptr);
+void launch_copy2(const LaunchCtx& L, ImgB srcA, ImgB dstA, ImgB srcB, ImgB dstB, int batch,
+                  const int* active = nullptr);
+void launch_fill(const LaunchCtx& L, ImgB dst, float value, int batch, const int* active = nullptr);
+void launch_fill_u8(const LaunchCtx& L, uint8_t* dst, size_t pitch, size_t sstride, int rows, int cols,
+                    uint8_t value, int batch, const int* active = nullptr);
+void launch_vmap(const LaunchCtx& L, ImgB depth_inv, ImgB vmap, float fx, float fy, float cx, float cy, int batch,
+                 const int* active = nullptr);
+void launch_nmap_gradients(const LaunchCtx& L, ImgB depth_inv, ImgB gx, ImgB gy, ImgB nmap, float fx, float fy,
+                           float cx, float cy, int batch, const int* active = nullptr);
+
+// ---- warp_ops.cu ----------------------------------------------------------------------------------
+void launch_warp_invdepth(const LaunchCtx& L, ImgB src, ImgB prev, ImgB dst, const Proj& P);
+void launch_warp_intensity(const LaunchCtx& L, ImgB src, ImgB prev, ImgB dst, const Proj& P);
+// batched weighted warp (+ optional fused integration): per-stream Proj read from device memory
+void launch_warp_invdepth_weighted(const LaunchCtx& L, ImgB src, ImgB prev, ImgB dst, ImgB weight, const Proj* P_dev,
+                                   Proj P_host, int batch, const int* active = nullptr);
+void launch_integrate(const LaunchCtx& L, ImgB wsrc, ImgB wweight, ImgB dst, ImgB dweight, int batch,
+                      const int* active = nullptr);
+// fused K6 + K7: warp current inverse depth into the keyframe and fuse it in the same pass
+void launch_warp_integrate(const LaunchCtx& L, ImgB cur, ImgB kf, ImgB kf_weight, ImgB warped_weight_state,
+                           const Proj* P_dev, int batch, const int* active);
+// visibility: counts[b*4 + {0 visible,1 valid}] (+2,+3 for the second direction) are accumulated with
+// integer atomics; mask may be null.  P_dev holds one Proj per stream (per direction).
+void launch_visibility(const LaunchCtx& L, ImgB src, ImgB dst, const Proj* P_dev, Proj P_host,
+                       unsigned int* counts, int count_offset, int count_stride, uint8_t* mask, size_t mpitch,
+                       size_t mstride, int batch, const int* active = nullptr);
+
+// ---- scale_est.cu ---------------------------------------------------------------------------------
+void launch_compute_error(const LaunchCtx& L, ImgB im1, ImgB im0, float* error, int kept_rows, int kept_cols,
+                          int stride);
+
+enum ScaleOp { SCALE_SIGMA_NU = 0, SCALE_NU_ONLY = 1, SCALE_SIGMA_PDF = 2 };
+
+// Result of the scale estimation for one frame pair (device resident)
+struct ScaleState {
+  float bias_int, sigma_int, nu_int;
+  float bias_depthinv, sigma_depthinv, nu_depthinv;
+  int irls_iters_int, irls_iters_depthinv;
+};
+
+// Scale estimation on explicit error vectors (bridge API); slot 1 may be disabled with err1 == nullptr.
+void launch_scale_from_errors(const LaunchCtx& L, const float* err0, const float* err1, int n, int op, int mest,
+                              float bias0, float sigma0, float bias1, float sigma1, ScaleState* out);
+void launch_chi_square(const LaunchCtx& L, const float* err_int, const float* err_depth, int n, float sigma_int,
+                       float sigma_depth, int mest, double* out2 /* [sum_rho, n_valid] */);
+
+// ---- gn_system.cu ---------------------------------------------------------------------------------
+struct GnLevelMaps {
+  ImgB W0, I0, gWx, gWy, gIx, gIy;  // keyframe maps of this level
+  ImgB Wc, Ic;                      // current-frame maps of this level
+};
+
+// Device-resident state of one frame pair's Gauss-Newton problem
+struct GnState {
+  double R[9], t[3];         // current estimate _{KF}T^{cur}
+  double R0[9], t0[3];       // initial guess (restored if the pose goes NaN)
+  double cov[36];
+  double lastA[36];
+  Proj proj[RGBID_MAX_LEVELS];  // K_l R^-1 K_l^-1, -K_l R^-1 t for every level, refreshed after each update
+  int status;                // RGBID_OK | RGBID_ERR_NAN
+  int iter_count;            // trace cursor
+  float chi_square, chi_test, ndof;
+  int pad;
+};
+
+struct GnParams {
+  int batch, level, rows, cols;
+  float fx, fy, cx, cy;         // level intrinsics
+  float fx0, fy0, cx0, cy0;     // level-0 intrinsics (to refresh proj[] for all levels)
+  int levels;
+  int mode;                     // RGBID_MODE_*
+  int mestimator, weighting;
+  int student_nu;               // 1: Student weights with estimated nu; 0: computeWeight(mestimator)
+  int use_scale;                // 1: read ScaleState; 0: sigma 5 / 0.0025, nu 5, bias 0
+  int update_pose;              // 1: solve + update pose in the last block; 0: covariance pass
+  int compute_cov;              // 1: cov = A^-1 in the last block
+  int chi_mestimator;           // covariance pass: M-estimator of the end-of-frame chi^2 (-1: skip)
+  int iter_index;               // for the trace
+  int trace_stride;             // entries per pair (0: no trace)
+  int kept_rows, kept_cols, sample_stride;  // residual sampling geometry of this level
+  int sigma_op;                 // ScaleOp used by the sampling kernel
+};
+
+// fused warp + sample + residual -> IRLS sigma / nu (8-CTA cluster per pair)
+void launch_gn_scale(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P, GnState* states,
+                     ScaleState* scales);
+// fused warp + bilinear sample + residual + Jacobian + weights + 27-sum reduction (+ solve / covariance in
+// the last block of each pair)
+void launch_gn_build(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P, GnState* states,
+                     const ScaleState* scales, double* partials, int partial_stride, unsigned int* counters,
+                     rgbid_iter_trace* trace);
+void launch_gn_init(const LaunchCtx& L, GnState* states, const double* R_init, const double* t_init, int batch,
+                    int levels, float fx0, float fy0, float cx0, float cy0);
+int gn_build_grid_x(int rows, int cols, int batch, int num_sms);
+
+// un-fused drop-in (pre-warped W1 / I1), one pair
+void launch_build_system(const LaunchCtx& L, ImgB W0, ImgB I0, ImgB gWx, ImgB gWy, ImgB gIx, ImgB gIy, ImgB W1,
+                         ImgB I1, const rgbid_system_params& sp, double* partials, unsigned int* counter,
+                         double* out27);
+
+}  // namespace rgbid

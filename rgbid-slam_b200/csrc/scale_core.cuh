@@ -1,0 +1,206 @@
+// scale_core.cuh -- robust scale (bias, sigma) and Student-t nu estimation inside one thread-block cluster.
+//
+// Reference behaviour (src/cuda/sigmaFuncs.cu:858-1222): up to 10 IRLS iterations for (bias, sigma) and up
+// to 6 evaluations of the nu likelihood equation, each a pair of tiny kernels + cudaStreamSynchronize +
+// device->host copy, with host-side control flow (bisection, float digamma).  Here the whole procedure
+// runs inside ONE kernel: an 8-CTA cluster owns the residual samples of one frame pair (both residual
+// types), keeps them in shared memory, and performs one cluster-wide reduction per round through
+// distributed shared memory; the control flow (convergence test, bisection) is evaluated redundantly and
+// identically by every thread, so no host round trip is needed.
+#pragma once
+#include <cooperative_groups.h>
+#include "kernels.cuh"
+
+namespace rgbid {
+
+namespace cg = cooperative_groups;
+
+constexpr int kScaleCluster = 8;    // CTAs per frame pair (portable cluster size limit)
+constexpr int kScaleThreads = 512;  // threads per CTA
+constexpr int kScaleVals = 12;      // reduced values per round (6 per residual slot)
+
+// digamma(float): the reference uses boost::math::digamma on a float argument (src/cuda/device.hpp:76-80),
+// which evaluates in double and rounds to float.  Recurrence to x >= 10, then the asymptotic series.
+__device__ __forceinline__ float digamma_float(float xf)
+{
+  double x = (double)xf, r = 0.0;
+  while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
+  double f = 1.0 / (x * x);
+  double t = f * (-1.0 / 12.0 + f * (1.0 / 120.0 + f * (-1.0 / 252.0 + f * (1.0 / 240.0 +
+             f * (-1.0 / 132.0 + f * (691.0 / 32760.0 + f * (-1.0 / 12.0)))))));
+  return (float)(r + log(x) - 0.5 / x + t);
+}
+
+// C(nu) of sigmaFuncs.cu:966, float arithmetic evaluated left to right (no re-association, no FMA)
+__device__ __forceinline__ float c_nu_float(float nu, float fw)
+{
+  float a = __fadd_rn(-digamma_float(nu / 2.f), logf(nu / 2.f));
+  a = __fadd_rn(a, fw);
+  a = __fadd_rn(a, 1.f);
+  a = __fadd_rn(a, digamma_float((nu + 1.f) / 2.f));
+  return __fsub_rn(a, logf((nu + 1.f) / 2.f));
+}
+
+enum ScalePhase { PH_IRLS = 0, PH_NU_INIT = 1, PH_NU_BISECT = 2, PH_DONE = 3 };
+
+struct ScaleSlot {
+  int phase, op, mest;
+  int it, j, lsq, irls_iters;
+  float bias, sigma;          // sh.bias / sh.sigma of the reference's handler
+  float out_bias, out_sigma;  // values returned to the caller
+  float nu, nu_up, nu_down, nu_new, C_up, C_down;
+};
+
+__device__ __forceinline__ void slot_init(ScaleSlot& s, int op, int mest, float bias, float sigma, bool enabled)
+{
+  s.op = op; s.mest = mest;
+  s.it = 0; s.j = 0; s.lsq = 1; s.irls_iters = 0;
+  s.bias = bias; s.sigma = sigma; s.out_bias = bias; s.out_sigma = sigma;
+  s.nu = 5.f; s.nu_up = 10.f; s.nu_down = 2.f; s.nu_new = 0.f; s.C_up = 0.f; s.C_down = 0.f;
+  s.phase = !enabled ? PH_DONE : (op == SCALE_NU_ONLY ? PH_NU_INIT : PH_IRLS);
+}
+
+// Per-sample contribution of one round.  acc[0..5]:
+//   IRLS     : sum w r^2, sum w r, sum w, N
+//   NU_INIT  : sum ln w(nu=2), sum w(2), sum ln w(10), sum w(10), N
+//   NU_BISECT: sum ln w(nu_new), sum w(nu_new), -, -, N
+__device__ __forceinline__ void slot_accumulate(const ScaleSlot& s, float e, float* acc)
+{
+  if (isinf(e) || isnan(e)) return;  // sigmaFuncs.cu:206,308,436
+  if (s.phase == PH_IRLS) {
+    float weight = 1.f, valid = 1.f;
+    if (s.op == SCALE_SIGMA_NU) {
+      // partialBiasAndSigmaStudent, sigmaFuncs.cu:281-360 (nu fixed at 5 during IRLS, :907)
+      if (!s.lsq) {
+        float en = (e - s.bias) / s.sigma;
+        weight = (5.f + 1.f) / (5.f + en * en);
+      }
+    } else {
+      // partialBiasAndSigma, sigmaFuncs.cu:179-278 (first iteration runs with Mestimator = LSQ, :813)
+      float en = (e - s.bias) / s.sigma;
+      int m = s.lsq ? RGBID_LSQ : s.mest;
+      if (m == RGBID_HUBER) { if (fabsf(en) > 1.345f) weight = 1.345f / fabsf(en); }
+      else if (m == RGBID_TUKEY) {
+        if (fabsf(en) < 4.685f) { float a = (en / 4.685f) * (en / 4.685f); weight = (1.f - a) * (1.f - a); }
+        else { weight = 0.f; valid = 0.f; }
+      } else if (m == RGBID_STUDENT) weight = (5.f + 1.f) / (5.f + en * en);
+    }
+    float wr = e * weight;
+    acc[0] += wr * e; acc[1] += wr; acc[2] += weight; acc[5] += valid;
+  } else {
+    // partialFuncWeightsNu, sigmaFuncs.cu:412-475
+    float en = (e - s.bias) / s.sigma;
+    float e2 = en * en;
+    if (s.phase == PH_NU_INIT) {
+      float w2 = (2.f + 1.f) / (2.f + e2), w10 = (10.f + 1.f) / (10.f + e2);
+      acc[0] += logf(w2); acc[1] += w2; acc[2] += logf(w10); acc[3] += w10;
+    } else {
+      float w = (s.nu_new + 1.f) / (s.nu_new + e2);
+      acc[0] += logf(w); acc[1] += w;
+    }
+    acc[5] += 1.f;
+  }
+}
+
+// Host-side control flow of computeSigmaAndNuStudent / computeSigmaPdf / computeNuStudent, advanced by
+// one round given the cluster-wide totals tot[0..5] of this slot.
+__device__ __forceinline__ void slot_advance(ScaleSlot& s, const double* tot)
+{
+  if (s.phase == PH_IRLS) {
+    // finalReductionBiasAndSigma, sigmaFuncs.cu:362-409 (float arithmetic on the reduced sums)
+    float fwr2 = (float)tot[0], fwr = (float)tot[1], fw = (float)tot[2], fn = (float)tot[5];
+    float m0 = fwr / fw;
+    float m1 = sqrtf((fwr2 - 2.f * m0 * fwr + m0 * m0 * fw) / fn);
+    s.out_bias = m0; s.out_sigma = m1;
+    float sigma_prev = s.sigma;
+    s.bias = m0; s.sigma = m1;
+    s.lsq = (s.op == SCALE_SIGMA_NU) ? (s.mest == RGBID_LSQ) : 0;
+    ++s.irls_iters;
+    bool conv = (s.it > 0) && ((fabsf(m1 - sigma_prev) / sigma_prev) < 0.1f);
+    ++s.it;
+    if (conv || s.it >= 10) s.phase = (s.op == SCALE_SIGMA_NU) ? PH_NU_INIT : PH_DONE;
+  } else if (s.phase == PH_NU_INIT) {
+    float fn = (float)tot[5];
+    float f_down = ((float)tot[0] - (float)tot[1]) / fn;  // finalReductionFuncWeightsNu, :478-516
+    float f_up = ((float)tot[2] - (float)tot[3]) / fn;
+    s.C_down = c_nu_float(2.f, f_down);
+    s.C_up = c_nu_float(10.f, f_up);
+    if (s.C_up * s.C_down > 0.f) {
+      s.nu = (s.C_down <= 0.f) ? 2.f : 10.f;
+      s.phase = PH_DONE;
+    } else {
+      s.j = 0;
+      s.nu_new = (s.nu_up + s.nu_down) / 2.f;
+      if ((s.nu_up - s.nu_down) < 1.f) { s.nu = s.nu_new; s.phase = PH_DONE; }
+      else s.phase = PH_NU_BISECT;
+    }
+  } else if (s.phase == PH_NU_BISECT) {
+    float fn = (float)tot[5];
+    float f_new = ((float)tot[0] - (float)tot[1]) / fn;
+    float C_new = c_nu_float(s.nu_new, f_new);
+    if (C_new * s.C_up > 0.f) { s.C_up = C_new; s.nu_up = s.nu_new; }
+    else { s.C_down = C_new; s.nu_down = s.nu_new; }
+    ++s.j;
+    if (s.j >= 5) { s.nu = s.nu_new; s.phase = PH_DONE; }
+    else {
+      s.nu_new = (s.nu_up + s.nu_down) / 2.f;
+      if ((s.nu_up - s.nu_down) < 1.f) { s.nu = s.nu_new; s.phase = PH_DONE; }
+    }
+  }
+}
+
+struct ScaleShared {
+  double warp_part[kScaleThreads / 32][kScaleVals];
+  double xchg[2][kScaleVals];  // this CTA's totals, double-buffered across rounds (read by peers via DSMEM)
+  double total[kScaleVals];
+};
+
+// Runs all rounds for the two slots.  samples0/1: this CTA's slice of each residual vector (shared or global
+// memory), n_local entries each.  Every thread of every CTA of the cluster must call this.
+__device__ __forceinline__ void scale_rounds(cg::cluster_group& cluster, ScaleShared& sh, ScaleSlot& s0, ScaleSlot& s1,
+                                             const float* samples0, const float* samples1, int n_local)
+{
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int parity = 0;
+  // bounded: <= 10 IRLS + 1 + 5 bisection rounds per slot (they advance concurrently)
+  for (int round = 0; round < 20; ++round) {
+    if (s0.phase == PH_DONE && s1.phase == PH_DONE) break;
+    float acc[kScaleVals];
+#pragma unroll
+    for (int k = 0; k < kScaleVals; ++k) acc[k] = 0.f;
+    if (s0.phase != PH_DONE)
+      for (int i = tid; i < n_local; i += kScaleThreads) slot_accumulate(s0, samples0[i], acc);
+    if (s1.phase != PH_DONE)
+      for (int i = tid; i < n_local; i += kScaleThreads) slot_accumulate(s1, samples1[i], acc + 6);
+#pragma unroll
+    for (int k = 0; k < kScaleVals; ++k) {
+      double v = warp_sum((double)acc[k]);
+      if (lane == 0) sh.warp_part[wid][k] = v;
+    }
+    __syncthreads();
+    if (tid < kScaleVals) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < kScaleThreads / 32; ++w) v += sh.warp_part[w][tid];
+      sh.xchg[parity][tid] = v;
+    }
+    cluster.sync();
+    if (tid < kScaleVals) {
+      double v = 0.0;
+      for (unsigned r = 0; r < cluster.num_blocks(); ++r) {
+        const double* remote = cluster.map_shared_rank(&sh.xchg[parity][0], r);
+        v += remote[tid];
+      }
+      sh.total[tid] = v;
+    }
+    __syncthreads();
+    slot_advance(s0, &sh.total[0]);
+    slot_advance(s1, &sh.total[6]);
+    parity ^= 1;
+    __syncthreads();  // total[] / warp_part[] are rewritten next round
+  }
+  // peers may still be reading this CTA's xchg through DSMEM: do not exit before they are done
+  cluster.sync();
+}
+
+}  // namespace rgbid

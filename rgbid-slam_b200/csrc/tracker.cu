@@ -1,0 +1,412 @@
+// tracker.cu -- per-frame state machine of VisodoTracker::trackNewFrame (src/visodo.cpp:1967-2247) for
+// `batch` independent RGB-D streams advancing in lock step.
+//
+// Per frame and per stream the reference performs ~700 kernel launches / stream synchronisations; here one
+// frame of ALL streams is: 1 ingest launch + (levels-1) pyramid launches, one graph replay for the whole
+// Gauss-Newton schedule + covariance pass, 4 covisibility launches, and 4-5 launches of fusion / map
+// maintenance (keyframe refresh launches are predicated per stream on the device).  The host synchronises
+// twice per frame (pose read-back, covisibility read-back) to take the keyframe decisions in double
+// precision exactly like the reference's host code.
+#include <cstring>
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "aligner.hpp"
+
+using namespace rgbid;
+
+namespace {
+
+struct StreamState {
+  double R_odoKF[9], t_odoKF[3];  // last_odoKF_global_{rotation,translation}_
+  double R_est[9], t_est[3];      // last_estimated_{rotation,translation}_
+  double dR[9], dt[3], dcov[36];  // delta_{rotation,translation,covariance}_ : _{odoKF}T^{cur}
+  double R_intKF[9], t_intKF[3];  // last_integrKF_global_*
+  double vel[3], omega[3];        // constant-velocity model state
+  bool lost;
+  int global_time, odoKF_count, integrKF_count;
+};
+
+void set_identity(double* R, double* t)
+{
+  for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  t[0] = t[1] = t[2] = 0.0;
+}
+
+}  // namespace
+
+struct rgbid_tracker {
+  rgbid_ctx* ctx;
+  rgbid_tracker_config cfg;
+  rgbid_aligner* al;
+  std::vector<StreamState> st;
+  int frame_index;
+  // integration keyframe (level 0), batched
+  char* d_arena;
+  ImgB intW, intWraw, intWeight, wstate, vmap, nmap, intGx, intGy;
+  uint8_t* d_mask; size_t mask_pitch, mask_sstride;
+  uint8_t* d_colors; size_t colors_sstride;
+  Proj* d_proj; Proj* h_proj;              // [4][batch]: odo cur->KF, odo KF->cur, integr cur->KF, integr KF->cur
+  unsigned int* d_counts; unsigned int* h_counts;  // [batch][8]
+  int* d_flags; int* h_flags;              // [3][batch]: new odo KF, new integration KF, fuse
+};
+
+namespace {
+
+void save_integration_keyframes(rgbid_tracker* t, const int* active)
+{
+  // saveCurrentImagesAsIntegrationKeyframes, src/visodo.cpp:880-893
+  rgbid_aligner* al = t->al;
+  LaunchCtx L = t->ctx->L();
+  const rgbid_align_config& c = al->cfg;
+  const int B = c.batch;
+  launch_copy2(L, al->maps[MAP_W_CUR][0], t->intW, al->maps[MAP_W_CUR][0], t->intWraw, B, active);
+  launch_fill(L, t->intWeight, 1.f, B, active);  // initialiseWeightKernel: 1 everywhere (misc.cu:272-287)
+}
+
+void refresh_integration_maps(rgbid_tracker* t)
+{
+  // createVMap + computeGradientDepth + createNMapGradients (src/visodo.cpp:889-892, 1753-1758)
+  rgbid_aligner* al = t->al;
+  LaunchCtx L = t->ctx->L();
+  const rgbid_align_config& c = al->cfg;
+  ImgB none = make_img(nullptr, 0, 0, 0);
+  launch_vmap(L, t->intW, t->vmap, c.fx, c.fy, c.cx, c.cy, c.batch);
+  launch_gradient2(L, t->intW, t->intGx, t->intGy, none, none, none, c.batch);
+  launch_nmap_gradients(L, t->intW, t->intGx, t->intGy, t->nmap, c.fx, c.fy, c.cx, c.cy, c.batch);
+}
+
+void to_proj(const double* R, const double* tt, const rgbid_align_config& c, Proj* P)
+{
+  projective_pose(R, tt, c.fx, c.fy, c.cx, c.cy, P->r, P->t);
+}
+
+void to_proj_inverse(const double* R, const double* tt, const rgbid_align_config& c, Proj* P)
+{
+  projective_inverse_pose(R, tt, c.fx, c.fy, c.cx, c.cy, P->r, P->t);
+}
+
+}  // namespace
+
+extern "C" {
+
+int rgbid_tracker_create(rgbid_ctx* ctx, const rgbid_tracker_config* cfg, rgbid_tracker** out)
+{
+  if (!ctx || !cfg || !out) return RGBID_ERR_ARG;
+  *out = nullptr;
+  rgbid_tracker* t = new (std::nothrow) rgbid_tracker();
+  if (!t) return RGBID_ERR_NOMEM;
+  t->ctx = ctx;
+  t->cfg = *cfg;
+  t->cfg.align.mode = RGBID_MODE_TRACKER;
+  if (t->cfg.delta_t <= 0.f) t->cfg.delta_t = 0.03333f;
+  if (t->cfg.visratio_odo <= 0.f) t->cfg.visratio_odo = 0.9f;
+  if (t->cfg.visratio_integr <= 0.f) t->cfg.visratio_integr = 0.7f;
+  if (t->cfg.max_odo_kf_count <= 0) t->cfg.max_odo_kf_count = 9999999;
+  if (t->cfg.max_integr_kf_count <= 0) t->cfg.max_integr_kf_count = 9999999;
+  t->al = nullptr; t->d_arena = nullptr; t->d_proj = nullptr; t->h_proj = nullptr; t->d_counts = nullptr;
+  t->h_counts = nullptr; t->d_flags = nullptr; t->h_flags = nullptr;
+  int rc = rgbid_aligner_create(ctx, &t->cfg.align, &t->al);
+  if (rc != RGBID_OK) { delete t; return rc; }
+  t->al->image_filtering = t->cfg.image_filtering;
+  const rgbid_align_config& c = t->al->cfg;
+  const int B = c.batch, rows = c.rows, cols = c.cols;
+  const LevelGeom& g = t->al->geom[0];
+  size_t map1 = g.sstride, map3 = align_up(g.pitch * rows * 3, 256);
+  t->mask_pitch = align_up((size_t)cols, 128);
+  t->mask_sstride = align_up(t->mask_pitch * rows, 256);
+  t->colors_sstride = align_up((size_t)rows * cols * 3, 256);
+  size_t total = (6 * map1 + 2 * map3 + t->mask_sstride + t->colors_sstride) * B;
+  cudaError_t e = cudaMalloc(&t->d_arena, total);
+  if (e != cudaSuccess) { rgbid_tracker_destroy(t); return e == cudaErrorMemoryAllocation ? RGBID_ERR_NOMEM : RGBID_ERR_CUDA_BASE + (int)e; }
+  size_t off = 0;
+  auto carve1 = [&](ImgB& m) { m = make_img((float*)(t->d_arena + off), g.pitch, rows, cols, map1); off += map1 * B; };
+  auto carve3 = [&](ImgB& m) { m = make_img((float*)(t->d_arena + off), g.pitch, 3 * rows, cols, map3); off += map3 * B; };
+  carve1(t->intW); carve1(t->intWraw); carve1(t->intWeight); carve1(t->wstate); carve1(t->intGx); carve1(t->intGy);
+  carve3(t->vmap); carve3(t->nmap);
+  t->d_mask = (uint8_t*)(t->d_arena + off); off += t->mask_sstride * B;
+  t->d_colors = (uint8_t*)(t->d_arena + off); off += t->colors_sstride * B;
+  if (e == cudaSuccess) e = cudaMalloc(&t->d_proj, sizeof(Proj) * 4 * B);
+  if (e == cudaSuccess) e = cudaMallocHost(&t->h_proj, sizeof(Proj) * 4 * B);
+  if (e == cudaSuccess) e = cudaMalloc(&t->d_counts, sizeof(unsigned int) * 8 * B);
+  if (e == cudaSuccess) e = cudaMallocHost(&t->h_counts, sizeof(unsigned int) * 8 * B);
+  if (e == cudaSuccess) e = cudaMalloc(&t->d_flags, sizeof(int) * 3 * B);
+  if (e == cudaSuccess) e = cudaMallocHost(&t->h_flags, sizeof(int) * 3 * B);
+  if (e != cudaSuccess) { rgbid_tracker_destroy(t); return RGBID_ERR_CUDA_BASE + (int)e; }
+  t->st.resize(B);
+  rc = rgbid_tracker_reset(t);
+  if (rc != RGBID_OK) { rgbid_tracker_destroy(t); return rc; }
+  *out = t;
+  return RGBID_OK;
+}
+
+int rgbid_tracker_destroy(rgbid_tracker* t)
+{
+  if (!t) return RGBID_OK;
+  cudaStreamSynchronize(t->ctx->stream);
+  if (t->al) rgbid_aligner_destroy(t->al);
+  cudaFree(t->d_arena); cudaFree(t->d_proj); cudaFree(t->d_counts); cudaFree(t->d_flags);
+  if (t->h_proj) cudaFreeHost(t->h_proj);
+  if (t->h_counts) cudaFreeHost(t->h_counts);
+  if (t->h_flags) cudaFreeHost(t->h_flags);
+  delete t;
+  return RGBID_OK;
+}
+
+int rgbid_tracker_reset(rgbid_tracker* t)
+{
+  if (!t) return RGBID_ERR_ARG;
+  t->frame_index = 0;
+  for (auto& s : t->st) {
+    memset(&s, 0, sizeof(s));
+    set_identity(s.R_odoKF, s.t_odoKF); set_identity(s.R_est, s.t_est); set_identity(s.dR, s.dt);
+    set_identity(s.R_intKF, s.t_intKF);
+    s.lost = false; s.global_time = 0;
+  }
+  const rgbid_align_config& c = t->al->cfg;
+  cudaStream_t s = t->ctx->stream;
+  size_t fl = (size_t)(t->d_mask - (uint8_t*)t->d_arena);
+  RGBID_CUDA_TRY(cudaMemsetAsync(t->d_arena, 0xff, fl, s));  // NaN-fill float maps
+  // warped_weight_curr_ is never cleared by the reference (fresh cudaMalloc memory): start from zero weights
+  RGBID_CUDA_TRY(cudaMemsetAsync(t->wstate.p, 0, t->wstate.sstride * c.batch, s));
+  RGBID_CUDA_TRY(cudaMemsetAsync(t->d_mask, 0, (t->mask_sstride + t->colors_sstride) * c.batch, s));
+  return RGBID_OK;
+}
+
+rgbid_aligner* rgbid_tracker_aligner(rgbid_tracker* t) { return t ? t->al : nullptr; }
+
+int rgbid_tracker_keyframe_map(rgbid_tracker* t, int which, int index, float** ptr, size_t* pitch)
+{
+  if (!t || !ptr || !pitch || index < 0 || index >= t->al->cfg.batch) return RGBID_ERR_ARG;
+  const ImgB* m = nullptr;
+  switch (which) {
+    case 0: m = &t->intW; break;
+    case 1: m = &t->intWeight; break;
+    case 2: m = &t->intWraw; break;
+    case 3: m = &t->vmap; break;
+    case 4: m = &t->nmap; break;
+    case 5: m = &t->intGx; break;
+    case 6: m = &t->intGy; break;
+    default: return RGBID_ERR_ARG;
+  }
+  *ptr = (float*)((char*)m->p + (size_t)index * m->sstride);
+  *pitch = m->pitch;
+  return RGBID_OK;
+}
+
+int rgbid_tracker_overlap_mask(rgbid_tracker* t, int index, uint8_t** ptr, size_t* pitch)
+{
+  if (!t || !ptr || !pitch || index < 0 || index >= t->al->cfg.batch) return RGBID_ERR_ARG;
+  *ptr = t->d_mask + (size_t)index * t->mask_sstride;
+  *pitch = t->mask_pitch;
+  return RGBID_OK;
+}
+
+int rgbid_tracker_track(rgbid_tracker* t, const uint16_t* depth, const uint8_t* rgb, int from_host,
+                        rgbid_frame_result* results)
+{
+  if (!t || !depth || !rgb || !results) return RGBID_ERR_ARG;
+  rgbid_aligner* al = t->al;
+  rgbid_ctx* ctx = t->ctx;
+  const rgbid_align_config& c = al->cfg;
+  const int B = c.batch, rows = c.rows, cols = c.cols;
+  cudaStream_t s = ctx->stream;
+  LaunchCtx L = ctx->L();
+  const float dt_frame = t->cfg.delta_t;
+  const size_t dsz = (size_t)rows * cols * 2, csz = (size_t)rows * cols * 3;
+
+  // ---- prepareImages (src/visodo.cpp:760-773): ingest + pyramid for all streams --------------------------
+  const uint16_t* d_depth = depth;
+  const uint8_t* d_rgb = rgb;
+  size_t dstride = dsz, cstride = csz;
+  if (from_host) {
+    size_t raw_depth = align_up(dsz, 256), raw_rgb = align_up(csz, 256);
+    if (raw_depth == dsz && raw_rgb == csz) {
+      RGBID_CUDA_TRY(cudaMemcpyAsync(al->d_depth_raw, depth, dsz * B, cudaMemcpyHostToDevice, s));
+      RGBID_CUDA_TRY(cudaMemcpyAsync(al->d_rgb_raw, rgb, csz * B, cudaMemcpyHostToDevice, s));
+    } else {
+      for (int b = 0; b < B; ++b) {
+        RGBID_CUDA_TRY(cudaMemcpyAsync((char*)al->d_depth_raw + raw_depth * b, (const char*)depth + dsz * b, dsz, cudaMemcpyHostToDevice, s));
+        RGBID_CUDA_TRY(cudaMemcpyAsync(al->d_rgb_raw + raw_rgb * b, rgb + csz * b, csz, cudaMemcpyHostToDevice, s));
+      }
+    }
+    d_depth = al->d_depth_raw; d_rgb = al->d_rgb_raw; dstride = raw_depth; cstride = raw_rgb;
+  }
+  launch_ingest(L, d_depth, (size_t)cols * 2, dstride, d_rgb, (size_t)cols * 3, cstride, al->maps[MAP_W_CUR][0],
+                al->maps[MAP_I_CUR][0], B, c.factor_depth);
+  aligner_current_pyramid(al, 0, B);
+
+  // ---- first frame: everything becomes a keyframe (src/visodo.cpp:1994-2045) ---------------------------------
+  if (t->frame_index == 0) {
+    aligner_copy_current_to_keyframe(al, 0, B, nullptr);
+    aligner_keyframe_derivatives(al, 0, B, nullptr, false);
+    save_integration_keyframes(t, nullptr);
+    for (int b = 0; b < B; ++b)
+      RGBID_CUDA_TRY(cudaMemcpyAsync(t->d_colors + t->colors_sstride * b, (const char*)d_rgb + cstride * b, csz, cudaMemcpyDeviceToDevice, s));
+    refresh_integration_maps(t);
+    launch_fill_u8(L, t->d_mask, t->mask_pitch, t->mask_sstride, rows, cols, 0, B);
+    RGBID_CUDA_TRY(cudaStreamSynchronize(s));
+    for (int b = 0; b < B; ++b) {
+      StreamState& S = t->st[b];
+      S.global_time = 1;
+      rgbid_frame_result& r = results[b];
+      memset(&r, 0, sizeof(r));
+      set_identity(r.R, r.t); set_identity(r.dR, r.dt);
+      r.visibility_odo = 1.f; r.visibility_integr = 1.f;
+      r.new_odo_keyframe = 1; r.new_integr_keyframe = 1; r.frame_index = 0; r.status = RGBID_OK;
+    }
+    t->frame_index = 1;
+    return check_last(ctx);
+  }
+
+  // ---- estimateVisualOdometry (src/visodo.cpp:944-1479) -------------------------------------------------------
+  std::vector<double> prevR(9 * B), prevt(3 * B);
+  for (int b = 0; b < B; ++b) {
+    StreamState& S = t->st[b];
+    memcpy(&prevR[9 * b], S.dR, sizeof(double) * 9);
+    memcpy(&prevt[3 * b], S.dt, sizeof(double) * 3);
+    double* Ri = al->h_init + 9 * b;
+    double* ti = al->h_init + 9 * B + 3 * b;
+    if (S.global_time > 1 && t->cfg.motion_model == RGBID_CONSTANT_VELOCITY && !S.lost) {
+      // constant-velocity prediction (:1016-1027)
+      double vt[3] = {S.vel[0] * dt_frame, S.vel[1] * dt_frame, S.vel[2] * dt_frame};
+      double wt[3] = {S.omega[0] * dt_frame, S.omega[1] * dt_frame, S.omega[2] * dt_frame};
+      double dRp[9], dtp[3], tmp[3];
+      exp_map(wt, vt, dRp, dtp);
+      mat3_vec(S.dR, dtp, tmp);
+      for (int k = 0; k < 3; ++k) ti[k] = tmp[k] + S.dt[k];
+      mat3_mul(S.dR, dRp, Ri);
+    } else {
+      memcpy(Ri, S.dR, sizeof(double) * 9);
+      memcpy(ti, S.dt, sizeof(double) * 3);
+    }
+  }
+  RGBID_CUDA_TRY(cudaMemcpyAsync(al->d_init, al->h_init, sizeof(double) * 12 * B, cudaMemcpyHostToDevice, s));
+  int rc = aligner_enqueue_device_init(al);
+  if (rc != RGBID_OK) return rc;
+  RGBID_CUDA_TRY(cudaMemcpyAsync(al->h_states, al->d_states, sizeof(GnState) * B, cudaMemcpyDeviceToHost, s));
+  RGBID_CUDA_TRY(cudaStreamSynchronize(s));
+  if ((rc = check_last(ctx)) != RGBID_OK) return rc;
+
+  // ---- pose bookkeeping (:1463-1468, :2059-2117) + covisibility transforms (:1481-1514, :2172-2186) ----------
+  for (int b = 0; b < B; ++b) {
+    StreamState& S = t->st[b];
+    const GnState& g = al->h_states[b];
+    rgbid_frame_result& r = results[b];
+    memset(&r, 0, sizeof(r));
+    r.frame_index = t->frame_index;
+    r.status = g.status;
+    r.chi_square = g.chi_square; r.chi_test = g.chi_test; r.ndof = g.ndof;
+    const bool ok = (g.status == RGBID_OK);
+    if (ok) {
+      memcpy(S.dR, g.R, sizeof(double) * 9);
+      memcpy(S.dt, g.t, sizeof(double) * 3);
+      memcpy(S.dcov, g.cov, sizeof(double) * 36);
+      double Rt[9], dRc[9], dtc[3], diff[3], twist[6];
+      mat3_transpose(&prevR[9 * b], Rt);
+      mat3_mul(Rt, S.dR, dRc);
+      for (int k = 0; k < 3; ++k) diff[k] = S.dt[k] - prevt[3 * b + k];
+      mat3_vec(Rt, diff, dtc);
+      log_map(dRc, dtc, twist);
+      const double inv_dt = (double)(1.f / dt_frame);  // velocity_ = twist * (1.f / delta_t_), :1467-1468
+      for (int k = 0; k < 3; ++k) { S.vel[k] = twist[k] * inv_dt; S.omega[k] = twist[3 + k] * inv_dt; }
+      S.lost = false;
+    } else {
+      for (int i = 0; i < 36; ++i) S.dcov[i] = (i % 7 == 0) ? 100.0 : 0.0;
+    }
+    // last_estimated = last_odoKF_global * delta (:2061-2062)
+    double tmp[3];
+    mat3_vec(S.R_odoKF, S.dt, tmp);
+    for (int k = 0; k < 3; ++k) S.t_est[k] = S.t_odoKF[k] + tmp[k];
+    mat3_mul(S.R_odoKF, S.dR, S.R_est);
+    // covisibility transforms: [0] cur->odoKF (K R K^-1), [1] odoKF->cur, [2] cur->integrKF, [3] integrKF->cur
+    to_proj(S.dR, S.dt, c, &t->h_proj[0 * B + b]);
+    to_proj_inverse(S.dR, S.dt, c, &t->h_proj[1 * B + b]);
+    double Rki[9], dRi[9], dti[3], d2[3];
+    mat3_inverse(S.R_intKF, Rki);
+    mat3_mul(Rki, S.R_est, dRi);
+    for (int k = 0; k < 3; ++k) d2[k] = S.t_est[k] - S.t_intKF[k];
+    mat3_vec(Rki, d2, dti);
+    to_proj(dRi, dti, c, &t->h_proj[2 * B + b]);
+    to_proj_inverse(dRi, dti, c, &t->h_proj[3 * B + b]);
+  }
+  RGBID_CUDA_TRY(cudaMemcpyAsync(t->d_proj, t->h_proj, sizeof(Proj) * 4 * B, cudaMemcpyHostToDevice, s));
+  RGBID_CUDA_TRY(cudaMemsetAsync(t->d_counts, 0, sizeof(unsigned int) * 8 * B, s));
+  Proj dummy;
+  memset(&dummy, 0, sizeof(dummy));
+  const ImgB& Wcur = al->maps[MAP_W_CUR][0];
+  const ImgB& Wkf = al->maps[MAP_W_KF][0];
+  launch_visibility(L, Wcur, Wkf, t->d_proj + 0 * B, dummy, t->d_counts, 0, 8, nullptr, 0, 0, B);
+  launch_visibility(L, Wkf, Wcur, t->d_proj + 1 * B, dummy, t->d_counts, 2, 8, nullptr, 0, 0, B);
+  launch_visibility(L, Wcur, t->intWraw, t->d_proj + 2 * B, dummy, t->d_counts, 4, 8, nullptr, 0, 0, B);
+  launch_visibility(L, t->intWraw, Wcur, t->d_proj + 3 * B, dummy, t->d_counts, 6, 8, nullptr, 0, 0, B);
+  RGBID_CUDA_TRY(cudaMemcpyAsync(t->h_counts, t->d_counts, sizeof(unsigned int) * 8 * B, cudaMemcpyDeviceToHost, s));
+  RGBID_CUDA_TRY(cudaStreamSynchronize(s));
+
+  // ---- keyframe decisions (:2175-2215) ----------------------------------------------------------------------------
+  bool any_odo = false, any_int = false, any_fuse = false;
+  for (int b = 0; b < B; ++b) {
+    StreamState& S = t->st[b];
+    rgbid_frame_result& r = results[b];
+    const unsigned int* cnt = t->h_counts + 8 * b;
+    auto ratio = [](unsigned vis, unsigned val) { return ((float)val < 1.f) ? 0.f : (float)vis / (float)val; };
+    float vis_odo = fminf(ratio(cnt[2], cnt[3]), ratio(cnt[0], cnt[1]));
+    float vis_int = fminf(ratio(cnt[6], cnt[7]), ratio(cnt[4], cnt[5]));
+    r.visibility_odo = vis_odo; r.visibility_integr = vis_int;
+    int new_odo = 0, new_int = 0, fuse = 0;
+    if (r.status != RGBID_OK) {
+      // lost: both keyframes are re-initialised from the current frame (:2066-2097, :2111-2116)
+      S.lost = true;
+      new_odo = 1; new_int = 1;
+    } else {
+      S.odoKF_count++; S.integrKF_count++;
+      new_odo = (S.odoKF_count >= t->cfg.max_odo_kf_count) || (vis_odo < t->cfg.visratio_odo);
+      new_int = (S.integrKF_count >= t->cfg.max_integr_kf_count) || (vis_int < t->cfg.visratio_integr);
+      fuse = !new_int;
+    }
+    memcpy(r.R, S.R_est, sizeof(double) * 9); memcpy(r.t, S.t_est, sizeof(double) * 3);
+    memcpy(r.dR, S.dR, sizeof(double) * 9); memcpy(r.dt, S.dt, sizeof(double) * 3);
+    memcpy(r.cov, S.dcov, sizeof(double) * 36);
+    r.new_odo_keyframe = new_odo; r.new_integr_keyframe = new_int;
+    if (new_odo) {
+      // resetOdometryKeyframe (:1541-1575)
+      S.odoKF_count = 0;
+      memcpy(S.R_odoKF, S.R_est, sizeof(double) * 9); memcpy(S.t_odoKF, S.t_est, sizeof(double) * 3);
+      set_identity(S.dR, S.dt);
+      memset(S.dcov, 0, sizeof(S.dcov));
+    }
+    if (new_int) {
+      // resetIntegrationKeyframe (:1577-1672): switch to the new keyframe
+      S.integrKF_count = 0;
+      memcpy(S.R_intKF, S.R_est, sizeof(double) * 9); memcpy(S.t_intKF, S.t_est, sizeof(double) * 3);
+    }
+    t->h_flags[0 * B + b] = new_odo; t->h_flags[1 * B + b] = new_int; t->h_flags[2 * B + b] = fuse;
+    any_odo |= (new_odo != 0); any_int |= (new_int != 0); any_fuse |= (fuse != 0);
+    S.global_time++;
+  }
+  RGBID_CUDA_TRY(cudaMemcpyAsync(t->d_flags, t->h_flags, sizeof(int) * 3 * B, cudaMemcpyHostToDevice, s));
+  if (any_odo) {
+    // saveCurrentImagesAsOdoKeyframes (:826-878), predicated per stream
+    aligner_copy_current_to_keyframe(al, 0, B, t->d_flags + 0 * B);
+    aligner_keyframe_derivatives(al, 0, B, t->d_flags + 0 * B, false);
+  }
+  if (any_int) {
+    // computeOverlapping (:1517-1539): mask of the new keyframe (current frame) against the old raw keyframe
+    launch_visibility(L, Wcur, t->intWraw, t->d_proj + 2 * B, dummy, t->d_counts, 4, 8, t->d_mask, t->mask_pitch,
+                      t->mask_sstride, B, t->d_flags + 1 * B);
+    save_integration_keyframes(t, t->d_flags + 1 * B);
+    for (int b = 0; b < B; ++b)
+      if (t->h_flags[1 * B + b])
+        RGBID_CUDA_TRY(cudaMemcpyAsync(t->d_colors + t->colors_sstride * b, (const char*)d_rgb + cstride * b, csz, cudaMemcpyDeviceToDevice, s));
+  }
+  if (any_fuse) {
+    // integrateImagesIntoKeyframes (:1674-1764): K6 + K7 fused; transform = integrKF->cur (h_proj[3])
+    launch_warp_integrate(L, Wcur, t->intW, t->intWeight, t->wstate, t->d_proj + 3 * B, B, t->d_flags + 2 * B);
+  }
+  refresh_integration_maps(t);
+  t->frame_index++;
+  return check_last(ctx);
+}
+
+}  // extern "C"

@@ -1,0 +1,251 @@
+// warp_ops.cu -- SE(3) inverse warps, covisibility and keyframe inverse-depth fusion.
+//
+// Drop-in (un-fused) versions of the reference's warp kernels plus the batched/fused variants used by
+// the tracker.  The reference creates and destroys a texture object around every warp launch
+// (src/cuda/warping_registration.cu:926-964); here the gathers go through the read-only path with the
+// texture unit's addressing and 1/256 weight quantisation reproduced in software (common.cuh).
+#include "kernels.cuh"
+
+namespace rgbid {
+
+namespace {
+
+constexpr int BX = 32, BY = 8;
+inline dim3 grid2d(int cols, int rows, int z) { return dim3((cols + BX - 1) / BX, (rows + BY - 1) / BY, z); }
+
+// K4: trafo3DKernelInvDepthGridStride (warping_registration.cu:505-546)
+__global__ void __launch_bounds__(BX* BY) warp_invdepth_kernel(ImgB src, ImgB prev, ImgB dst, Proj P)
+{
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= dst.cols || y >= dst.rows) return;
+  float out = qnanf();
+  float w = prev.row(0, y)[x];
+  if (!isnan(w)) {
+    float xs, ys;
+    float w3 = project_pixel(P, x, y, w, xs, ys);
+    float xt = xs + 0.5f, yt = ys + 0.5f;
+    if (in_image(xt, yt, src.cols, src.rows)) {
+      float w2 = sample_nearest(src.p, src.pitch, xt, yt);
+      float tz = P.t[2];
+      float v1z = (1.f / w3 - tz) * w;
+      float res = (v1z / (1.f - w2 * tz)) * w2;
+      if (res > 0.f) out = res;
+    }
+  }
+  dst.row(0, y)[x] = out;
+}
+
+// K5: trafo3DKernelIntensityWithInvDepthGridStride (warping_registration.cu:465-501)
+__global__ void __launch_bounds__(BX* BY) warp_intensity_kernel(ImgB src, ImgB prev, ImgB dst, Proj P)
+{
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= dst.cols || y >= dst.rows) return;
+  float out = qnanf();
+  float w = prev.row(0, y)[x];
+  if (!isnan(w)) {
+    float xs, ys;
+    project_pixel(P, x, y, w, xs, ys);
+    float xt = xs + 0.5f, yt = ys + 0.5f;
+    if (in_image(xt, yt, src.cols, src.rows)) {
+      float r = sample_bilinear_q8(src.p, src.pitch, src.cols, src.rows, xt, yt);
+      out = fmaxf(0.f, fminf(r, 255.f));
+    }
+  }
+  dst.row(0, y)[x] = out;
+}
+
+// Shared body of K6 (trafo3DKernelInvDepthWeightedGridStride, warping_registration.cu:549-594):
+// returns the warped inverse depth (NaN if rejected) and, through weight / has_weight, the fusion weight
+// (1 - w2 tz)^4 / v1z^2 when it is positive.
+__device__ __forceinline__ float warp_weighted_pixel(const Proj& P, int x, int y, float w, const float* srcb,
+                                                     size_t spitch, int cols, int rows, float& weight,
+                                                     bool& has_weight)
+{
+  float out = qnanf();
+  has_weight = false;
+  if (!isnan(w)) {
+    float xs, ys;
+    float w3 = project_pixel(P, x, y, w, xs, ys);
+    float xt = xs + 0.5f, yt = ys + 0.5f;
+    if (in_image(xt, yt, cols, rows)) {
+      float w2 = sample_nearest(srcb, spitch, xt, yt);
+      float tz = P.t[2];
+      float v1z = (1.f / w3 - tz) * w;
+      float wf = 1.f - w2 * tz;
+      float wf2 = wf * wf;
+      float weight_res = (wf2 * wf2) / (v1z * v1z);
+      float res = (v1z / wf) * w2;
+      if (res > 0.f) out = res;
+      if (weight_res > 0.f) { weight = weight_res; has_weight = true; }
+    }
+  }
+  return out;
+}
+
+__global__ void __launch_bounds__(BX* BY) warp_invdepth_weighted_kernel(ImgB src, ImgB prev, ImgB dst, ImgB weight,
+                                                                         const Proj* __restrict__ P_dev, Proj P_host,
+                                                                         const int* __restrict__ active)
+{
+  const int b = blockIdx.z;
+  if (active != nullptr && active[b] == 0) return;
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= dst.cols || y >= dst.rows) return;
+  const Proj P = P_dev ? P_dev[b] : P_host;
+  float wgt;
+  bool has;
+  float out = warp_weighted_pixel(P, x, y, prev.row(b, y)[x], src.row(b, 0), src.pitch, src.cols, src.rows, wgt, has);
+  dst.row(b, y)[x] = out;
+  if (has) weight.row(b, y)[x] = wgt;  // stale weights survive elsewhere, as in the reference
+}
+
+// K7: integrateWarpedFrameKernel (warping_registration.cu:637-669); gate 3 * DEPTHINV_INTEGR_TH (:80,660)
+__device__ __forceinline__ void integrate_pixel(float w_sum, float w_src_weight, float& w_kf, float& kf_weight)
+{
+  if (isnan(w_sum)) return;
+  float dw = fabsf(w_sum - w_kf);
+  if (isnan(w_kf)) {
+    w_kf = w_sum;
+    kf_weight = w_src_weight;
+  } else if (dw < 3 * 0.0075f) {
+    float nw = kf_weight + w_src_weight;
+    w_kf = (w_kf * kf_weight + w_sum * w_src_weight) / nw;
+    kf_weight = nw;
+  }
+}
+
+__global__ void __launch_bounds__(BX* BY) integrate_kernel(ImgB wsrc, ImgB wweight, ImgB dst, ImgB dweight,
+                                                            const int* __restrict__ active)
+{
+  const int b = blockIdx.z;
+  if (active != nullptr && active[b] == 0) return;
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= dst.cols || y >= dst.rows) return;
+  float ws = wsrc.row(b, y)[x];
+  if (isnan(ws)) return;
+  float wk = dst.row(b, y)[x], kw = dweight.row(b, y)[x];
+  float wk0 = wk, kw0 = kw;
+  integrate_pixel(ws, wweight.row(b, y)[x], wk, kw);
+  if (!(wk == wk0) || !(kw == kw0)) {
+    dst.row(b, y)[x] = wk;
+    dweight.row(b, y)[x] = kw;
+  }
+}
+
+// K6 + K7 fused: the warped map never goes to memory.  `wstate` is the reference's warped_weight_curr_
+// buffer, which is NOT cleared between frames (src/visodo.cpp:1708-1717): a pixel whose weight is not
+// positive keeps the weight of an earlier frame, so that state has to be carried.
+__global__ void __launch_bounds__(BX* BY) warp_integrate_kernel(ImgB cur, ImgB kf, ImgB kf_weight, ImgB wstate,
+                                                                 const Proj* __restrict__ P_dev,
+                                                                 const int* __restrict__ active)
+{
+  const int b = blockIdx.z;
+  if (active != nullptr && active[b] == 0) return;
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= kf.cols || y >= kf.rows) return;
+  const Proj P = P_dev[b];
+  float wk = kf.row(b, y)[x];
+  float wgt;
+  bool has;
+  float ws = warp_weighted_pixel(P, x, y, wk, cur.row(b, 0), cur.pitch, cur.cols, cur.rows, wgt, has);
+  if (has) wstate.row(b, y)[x] = wgt;
+  if (isnan(ws)) return;
+  if (!has) wgt = wstate.row(b, y)[x];
+  float kw = kf_weight.row(b, y)[x];
+  float wk0 = wk, kw0 = kw;
+  integrate_pixel(ws, wgt, wk, kw);
+  if (!(wk == wk0) || !(kw == kw0)) {
+    kf.row(b, y)[x] = wk;
+    kf_weight.row(b, y)[x] = kw;
+  }
+}
+
+// K9 + K10: partialVisibility(WithOverlapMask)Kernel + finalVisibilityReductionKernel
+// (warping_registration.cu:297-461).  Counts are exact integers (the reference sums 1.f in float, which
+// is exact below 2^24), reduced with a warp ballot and one integer atomic per warp.
+__global__ void __launch_bounds__(BX* BY) visibility_kernel(ImgB src, ImgB dst, const Proj* __restrict__ P_dev,
+                                                             Proj P_host, unsigned int* __restrict__ counts,
+                                                             int count_offset, int count_stride, uint8_t* mask,
+                                                             size_t mpitch, size_t mstride,
+                                                             const int* __restrict__ active)
+{
+  const int b = blockIdx.z;
+  if (active != nullptr && active[b] == 0) return;
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  bool valid = false, visible = false;
+  if (x < src.cols && y < src.rows) {
+    const Proj P = P_dev ? P_dev[b] : P_host;
+    float w = src.row(b, y)[x];
+    if (!isnan(w)) {
+      valid = true;
+      float xd, yd;
+      float wd = project_pixel(P, x, y, w, xd, yd);
+      if (xd > 0.f && xd < __int2float_rn(src.cols - 1) && yd > 0.f && yd < __int2float_rn(src.rows - 1)) {
+        int xi = __float2int_rn(xd), yi = __float2int_rn(yd);
+        // geom_tol is ignored by the reference: 0.020 is hard-coded (:332, :405)
+        if (fabsf(wd - __ldg(dst.row(b, yi) + xi)) < 0.020f) visible = true;
+      }
+      if (mask != nullptr) mask[(size_t)b * mstride + (size_t)y * mpitch + x] = visible ? 1 : 0;
+    }
+  }
+  unsigned nval = __popc(__ballot_sync(0xffffffffu, valid));
+  unsigned nvis = __popc(__ballot_sync(0xffffffffu, visible));
+  __shared__ unsigned s_vis, s_val;
+  int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (tid == 0) { s_vis = 0; s_val = 0; }
+  __syncthreads();
+  if ((tid & 31) == 0 && nval) { atomicAdd(&s_val, nval); atomicAdd(&s_vis, nvis); }
+  __syncthreads();
+  if (tid == 0 && s_val) {
+    atomicAdd(&counts[b * count_stride + count_offset + 0], s_vis);
+    atomicAdd(&counts[b * count_stride + count_offset + 1], s_val);
+  }
+}
+
+}  // namespace
+
+void launch_warp_invdepth(const LaunchCtx& L, ImgB src, ImgB prev, ImgB dst, const Proj& P)
+{
+  warp_invdepth_kernel<<<grid2d(dst.cols, dst.rows, 1), dim3(BX, BY), 0, L.stream>>>(src, prev, dst, P);
+  ++*L.launches;
+}
+
+void launch_warp_intensity(const LaunchCtx& L, ImgB src, ImgB prev, ImgB dst, const Proj& P)
+{
+  warp_intensity_kernel<<<grid2d(dst.cols, dst.rows, 1), dim3(BX, BY), 0, L.stream>>>(src, prev, dst, P);
+  ++*L.launches;
+}
+
+void launch_warp_invdepth_weighted(const LaunchCtx& L, ImgB src, ImgB prev, ImgB dst, ImgB weight, const Proj* P_dev,
+                                   Proj P_host, int batch, const int* active)
+{
+  warp_invdepth_weighted_kernel<<<grid2d(dst.cols, dst.rows, batch), dim3(BX, BY), 0, L.stream>>>(
+      src, prev, dst, weight, P_dev, P_host, active);
+  ++*L.launches;
+}
+
+void launch_integrate(const LaunchCtx& L, ImgB wsrc, ImgB wweight, ImgB dst, ImgB dweight, int batch,
+                      const int* active)
+{
+  integrate_kernel<<<grid2d(dst.cols, dst.rows, batch), dim3(BX, BY), 0, L.stream>>>(wsrc, wweight, dst, dweight,
+                                                                                    active);
+  ++*L.launches;
+}
+
+void launch_warp_integrate(const LaunchCtx& L, ImgB cur, ImgB kf, ImgB kf_weight, ImgB wstate, const Proj* P_dev,
+                           int batch, const int* active)
+{
+  warp_integrate_kernel<<<grid2d(kf.cols, kf.rows, batch), dim3(BX, BY), 0, L.stream>>>(cur, kf, kf_weight, wstate,
+                                                                                       P_dev, active);
+  ++*L.launches;
+}
+
+void launch_visibility(const LaunchCtx& L, ImgB src, ImgB dst, const Proj* P_dev, Proj P_host, unsigned int* counts,
+                       int count_offset, int count_stride, uint8_t* mask, size_t mpitch, size_t mstride, int batch,
+                       const int* active)
+{
+  visibility_kernel<<<grid2d(src.cols, src.rows, batch), dim3(BX, BY), 0, L.stream>>>(
+      src, dst, P_dev, P_host, counts, count_offset, count_stride, mask, mpitch, mstride, active);
+  ++*L.launches;
+}
+
+}  // namespace rgbid
