@@ -79,9 +79,20 @@ def gradient(src):
 
 
 def bilateral(src, sigma):
+    """bilateralFilter of the reference.  NOTE (reference defect): bilateralKernel declares x, y as unsigned
+    (src/cuda/filters.cu:91-92), so `max(y - RADIUS, 0)` wraps for y < 2 (and x < 2) and the window starts at row /
+    column -2: the kernel reads out of bounds above the image and the tail of the previous row.  On this B200 pool
+    that is an illegal memory access when the image starts an allocation (cudaSafeCall then calls exit(0)).  The
+    input is therefore embedded in a NaN-filled buffer (4 rows above, 4 columns of row padding): the stray taps
+    hit NaN, which the kernel skips, i.e. exactly the clamped window the code intends and oracle.c restates."""
     rows, cols = src.shape
+    pad = torch.full((rows + 8, cols + 4), float("nan"), device=src.device)
+    pad[4:rows + 4, :cols] = src
+    view = pad[4:rows + 4, :cols]
     out = torch.empty_like(src)
-    lib().ref_bilateral(_dense(src), _sz(cols * 4), rows, cols, _dense(out), _sz(cols * 4), C.c_float(sigma))
+    torch.cuda.synchronize()
+    lib().ref_bilateral(C.c_void_p(view.data_ptr()), _sz((cols + 4) * 4), rows, cols, _dense(out), _sz(cols * 4),
+                        C.c_float(sigma))
     return out
 
 

@@ -74,15 +74,20 @@ __device__ __forceinline__ float sample_nearest(const float* __restrict__ base, 
 }
 
 // Bilinear fetch reproducing cudaFilterModeLinear with clamp addressing
-// (warping_registration.cu:943, fetch :493): xB = xt - 0.5, i = floor(xB), alpha = frac(xB) rounded to
-// 8 fractional bits (1.8 fixed point of the texture unit).
+// (warping_registration.cu:943, fetch :493): xB = xt - 0.5, i = floor(xB), alpha = frac(xB) in 1.8 fixed point.
+// The texture unit was characterised on B200 with tests/cuda/tex_probe2.cu: ka = round(alpha * 256),
+// kb = round(beta * 256), and the four weights are themselves 8-bit:
+//   w11 = (ka*kb + 128) >> 8, w10 = ka - w11, w01 = kb - w11, w00 = 256 - ka - kb + w11   (all / 256)
+// (zero mismatches over all 257 x 257 weight pairs).
 __device__ __forceinline__ float sample_bilinear_q8(const float* __restrict__ base, size_t pitch, int cols,
                                                     int rows, float xt, float yt)
 {
   float xB = xt - 0.5f, yB = yt - 0.5f;
   float fxf = floorf(xB), fyf = floorf(yB);
-  float a = floorf((xB - fxf) * 256.f + 0.5f) * (1.f / 256.f);
-  float b = floorf((yB - fyf) * 256.f + 0.5f) * (1.f / 256.f);
+  int ka = __float2int_rd((xB - fxf) * 256.f + 0.5f);
+  int kb = __float2int_rd((yB - fyf) * 256.f + 0.5f);
+  int w11 = (ka * kb + 128) >> 8;
+  int w10 = ka - w11, w01 = kb - w11, w00 = 256 - ka - kb + w11;
   int i0 = (int)fxf, j0 = (int)fyf;
   int i1 = min(max(i0 + 1, 0), cols - 1), j1 = min(max(j0 + 1, 0), rows - 1);
   i0 = min(max(i0, 0), cols - 1);
@@ -90,7 +95,8 @@ __device__ __forceinline__ float sample_bilinear_q8(const float* __restrict__ ba
   const float* r0 = (const float*)((const char*)base + (size_t)j0 * pitch);
   const float* r1 = (const float*)((const char*)base + (size_t)j1 * pitch);
   float t00 = __ldg(r0 + i0), t10 = __ldg(r0 + i1), t01 = __ldg(r1 + i0), t11 = __ldg(r1 + i1);
-  return (1.f - a) * (1.f - b) * t00 + a * (1.f - b) * t10 + (1.f - a) * b * t01 + a * b * t11;
+  return (__int2float_rn(w00) * t00 + __int2float_rn(w10) * t10 + __int2float_rn(w01) * t01 +
+          __int2float_rn(w11) * t11) * (1.f / 256.f);
 }
 
 // Warp of one keyframe pixel: the fused equivalent of trafo3DKernelInvDepthGridStride

@@ -42,9 +42,19 @@ class Context:
         h = C.c_void_p()
         capi.check(self.lib.rgbid_ctx_create(C.byref(h), device, C.c_void_p(self.stream.cuda_stream)), "ctx_create")
         self.h = h
+        self._children = []
+
+    def _register(self, child):
+        import weakref
+        self._children.append(weakref.ref(child))
 
     def close(self):
         if self.h is not None:
+            for ref in self._children:  # handles created on this context must go first
+                child = ref()
+                if child is not None:
+                    child.close()
+            self._children = []
             self.lib.rgbid_ctx_destroy(self.h)
             self.h = None
 
@@ -294,10 +304,12 @@ class Aligner:
         self.h = h
         self.batch = cfg.batch
         self.niters = self.lib.rgbid_aligner_num_iterations(h)
+        ctx._register(self)
 
     def close(self):
         if self.h is not None:
-            self.lib.rgbid_aligner_destroy(self.h)
+            if self.ctx.h is not None:
+                self.lib.rgbid_aligner_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -404,10 +416,12 @@ class Tracker:
         self.h = h
         self.batch = cfg.align.batch
         self.results = (capi.FrameResult * self.batch)()
+        ctx._register(self)
 
     def close(self):
         if self.h is not None:
-            self.lib.rgbid_tracker_destroy(self.h)
+            if self.ctx.h is not None:
+                self.lib.rgbid_tracker_destroy(self.h)
             self.h = None
 
     def __del__(self):

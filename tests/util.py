@@ -37,7 +37,7 @@ def rot_angle(Ra, Rb):
     return float(np.arccos(np.clip((np.trace(dR) - 1.0) / 2.0, -1.0, 1.0)))
 
 
-def sums_rel_err(a, b):
+def sums_rel_err(a, b, ignore_b=False):
     """Relative error of two 27-vectors [A00..A05,b0,A11..]: each entry is scaled by the geometric mean of the
     diagonal entries of its row/column (b entries by sqrt(A_ii) * ||b||-scale), i.e. by the magnitude the
     entry would have without cancellation."""
@@ -52,6 +52,8 @@ def sums_rel_err(a, b):
     bscale = max(abs(b[idx[(i, 6)]]) / np.sqrt(diag[i]) for i in range(6) if diag[i] > 0) if diag.max() > 0 else 1.0
     worst = 0.0
     for (i, j), k in idx.items():
+        if ignore_b and j == 6:
+            continue
         scale = np.sqrt(diag[i] * diag[j]) if j < 6 else np.sqrt(diag[i]) * max(bscale, 1e-30)
         if scale > 0:
             worst = max(worst, abs(a[k] - b[k]) / scale)
