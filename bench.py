@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- RGB-D frames/s of the dense frame-to-keyframe tracking path (640x480, 4-level pyramid).
+
+One "step" = one pass of the hot path over one batch of synthetic input: every one of the `streams_per_gpu`
+independent TUM-format synthetic RGB-D streams resident on a GPU advances by one frame, i.e. everything
+VisodoTracker::trackNewFrame does per frame: ingest (uint16 depth + RGB8), pyramid, the
+full coarse-to-fine Gauss-Newton schedule with sigma / nu estimation, the covariance pass with the
+end-of-frame chi^2, both covisibility tests, keyframe switching and inverse-depth fusion.
+
+  value   : frames/s with the frames already resident in HBM when the timed region starts
+  e2e     : the same through the C-ABI call with HOST buffers (H2D of every frame + D2H of the results inside
+            the timed region)
+  roofline: the fused warp+residual+J^T J kernel at level 0, algorithmic bytes = 32 B per keyframe pixel
+  cpu_baseline / --impl reference: see DESIGN.md ("Measurement")
+
+Multi-GPU: one process per GPU (torchrun), streams sharded across ranks (weak scaling, no data-path
+collective); the per-stream 6x6 systems / poses are all-gathered with NCCL once per step on a side stream.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "RGB-D frames/s (640x480, 4-level pyr)"
+UNIT = "frames/s"
+ALGO_BYTES_PER_PX = 32  # 6 keyframe maps + 2 current-frame maps, fp32
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("RGBID_BENCH_STREAMS", "32")),
+                    help="independent RGB-D streams per GPU (batch of one step)")
+    ap.add_argument("--rows", type=int, default=480)
+    ap.add_argument("--cols", type=int, default=640)
+    ap.add_argument("--levels", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-streams", type=int, default=2, help="streams per step for --impl reference")
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.samples, self.reasons, self.max_mhz = gpu_index, [], set(), None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def dist_setup(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return world, rank, local
+
+
+def shard_streams(total_streams, world, rank):
+    """Stream s lives on rank s mod world; returns the global ids owned by `rank`."""
+    return [s for s in range(total_streams) if s % world == rank]
+
+
+def make_frames(args, stream_ids, n_frames, device):
+    """[n_frames, S, rows, cols] uint16 depth and [n_frames, S, rows, cols, 3] uint8 RGB, rendered on `device`."""
+    from rgbid_slam_b200 import synth
+    intr = synth.intrinsics_for(args.rows, args.cols)
+    S = len(stream_ids)
+    depth = torch.empty(n_frames, S, args.rows, args.cols, dtype=torch.uint16, device=device)
+    rgb = torch.empty(n_frames, S, args.rows, args.cols, 3, dtype=torch.uint8, device=device)
+    for j, sid in enumerate(stream_ids):
+        scene = synth.Scene(20261017 + 1 + sid)            # seed = 20261017 + config index (+ stream)
+        poses = synth.trajectory(n_frames, seed=sid)
+        for k, (R, t) in enumerate(poses):
+            d, c, _, _ = scene.render(R, t, args.rows, args.cols, intr=intr, device=device, frame_id=k, noise=True)
+            depth[k, j], rgb[k, j] = d, c
+    return depth, rgb, intr
+
+
+def run_b200(args, world, rank, local):
+    from rgbid_slam_b200 import capi, host
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    S, K, W = args.streams, args.steps, args.warmup
+    stream_ids = shard_streams(S * world, world, rank)
+    n_frames = 1 + W + K
+    depth, rgb, intr = make_frames(args, stream_ids, n_frames, device)
+    ctx = host.Context(local)
+    its = host.default_iterations(args.levels, capi.MODE_TRACKER)
+    acfg = host.make_align_config(args.rows, args.cols, args.levels, capi.MODE_TRACKER, batch=S, iterations=its, **intr)
+    trk = host.Tracker(ctx, host.make_tracker_config(acfg))
+
+    gather = None
+    if world > 1:
+        import torch.distributed as dist
+        side = torch.cuda.Stream(device)
+        local_sys = torch.zeros(S, 48, dtype=torch.float64, device=device)  # 36 cov + 9 R + 3 t per stream
+        all_sys = torch.zeros(world * S, 48, dtype=torch.float64, device=device)
+
+        def gather(results):
+            arr = np.array([list(r.cov) + list(r.R) + list(r.t) for r in results], dtype=np.float64)
+            with torch.cuda.stream(side):
+                local_sys.copy_(torch.from_numpy(arr), non_blocking=True)
+                dist.all_gather_into_tensor(all_sys, local_sys)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    def timed(frames_d, frames_c, host_path):
+        """K steps bracketed by barrier + synchronize; device time from CUDA events on the context's stream."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        launches0 = ctx.launches
+        t0 = time.perf_counter()
+        with torch.cuda.stream(ctx.stream):
+            e0.record()
+            for k in range(K):
+                res = trk.track(frames_d[k], frames_c[k])
+                if gather:
+                    gather(res)
+            e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        dev_s = e0.elapsed_time(e1) / 1e3
+        lost = sum(1 for r in res if r.status != 0)
+        return dev_s, wall, ctx.launches - launches0, lost
+
+    # ---- device-resident arm ----------------------------------------------------------------------------
+    trk.track(depth[0], rgb[0])                      # frame 0: keyframe initialisation
+    for k in range(1, 1 + W):
+        trk.track(depth[k], rgb[k])
+    sampler = ClockSampler(local)
+    sampler.start()
+    dev_s, wall_s, launches, lost = timed(depth[1 + W:], rgb[1 + W:], False)
+    clocks = sampler.stop()
+    ms_build = trk.time_build(level=0, reps=20)
+
+    # ---- end-to-end arm: host buffers, H2D + D2H inside the timed region ----------------------------------
+    h_depth = depth.cpu().pin_memory()
+    h_rgb = rgb.cpu().pin_memory()
+    trk.reset()
+    trk.track(h_depth[0], h_rgb[0])
+    for k in range(1, 1 + W):
+        trk.track(h_depth[k], h_rgb[k])
+    e2e_dev_s, e2e_wall_s, _, _ = timed(h_depth[1 + W:], h_rgb[1 + W:], True)
+
+    def allmax(x):
+        if world == 1:
+            return x
+        import torch.distributed as dist
+        tns = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(tns, op=dist.ReduceOp.MAX)
+        return float(tns.item())
+
+    dev_s, e2e_s = allmax(dev_s), allmax(max(e2e_dev_s, e2e_wall_s))
+    total_frames = S * world * K
+    out = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        algo_bytes = ALGO_BYTES_PER_PX * args.rows * args.cols * S
+        achieved = algo_bytes / (ms_build * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        bytes_in = S * args.rows * args.cols * 5
+        out = {
+            "metric": METRIC, "value": total_frames / dev_s, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_s / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "tum_synth_640x480_4lvl_tracker" if (args.rows, args.cols, args.levels) == (480, 640, 4)
+                       else "tum_synth_%dx%d_%dlvl_tracker" % (args.cols, args.rows, args.levels),
+                       "streams_per_gpu": S, "frames_per_step": S * world, "iterations": its,
+                       "sigma_estimator": "sigmaML", "m_estimator": "Student", "warp_order": "pyrFirst",
+                       "l2_policy": "inputs larger than L2: %.0f MB of pyramids touched per step, new frames every step"
+                                    % (S * 39.0)},
+            "clocks": clocks,
+            "e2e": {"value": total_frames / e2e_s, "unit": UNIT, "h2d_bytes_per_step": bytes_in,
+                    "d2h_bytes_per_step": int(S * 1208)},  # per stream: solver state 1176 B + 8 covisibility counters
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "gn_build_kernel<4,false> level 0 (fused warp+residual+JtJ)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes,
+                         "ms_per_launch": ms_build, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback"},
+            "lost_streams": lost,
+        }
+        if not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args, depth[:, 0].cpu(), rgb[:, 0].cpu(), intr, its)
+    trk.close()
+    ctx.close()
+    return out
+
+
+def cpu_baseline(args, depth, rgb, intr, its, max_seconds=20.0):
+    """The CPU oracle port (oracle.c, OpenMP) tracking one stream of the same workload for a bounded sample."""
+    import oracle as orc  # the one place bench.py may execute the oracle: the reported CPU baseline
+    from oracle.tracker import OracleTracker
+    orc.lib()
+    levels = args.levels
+    ot = OracleTracker(args.rows, args.cols, intr, levels=levels, iterations=tuple(its), kind="cpu")
+    ot.track(depth[0].numpy().astype(np.uint16), rgb[0].numpy())
+    n, t0 = 0, time.perf_counter()
+    for k in range(1, depth.shape[0]):
+        ot.track(depth[k].numpy().astype(np.uint16), rgb[k].numpy())
+        n += 1
+        if time.perf_counter() - t0 > max_seconds:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1)),
+            "kind": "port", "sample": "%d frames of one stream of the same workload (oracle.c, OpenMP over rows)" % n}
+
+
+def run_reference(args, world, rank, local):
+    """Reference arm: the reference's OWN implementation of the path -- its CUDA kernels and bridge functions
+    compiled verbatim (oracle/_ref/libref_oracle.so) driven by the restated host loop -- on the same workload,
+    frame by frame and stream by stream as the reference processes them.  Falls back to the CPU port when the
+    reference library is not present."""
+    if rank != 0:
+        return None
+    import oracle as orc
+    from oracle import ref as refk
+    from oracle.tracker import OracleTracker
+    use_ref = refk.available()
+    device = torch.device("cuda", local) if use_ref else torch.device("cpu")
+    S, K, W = max(1, args.ref_streams), args.steps, args.warmup
+    n_frames = 1 + W + K
+    depth, rgb, intr = make_frames(args, list(range(S)), n_frames, "cuda" if torch.cuda.is_available() else "cpu")
+    from rgbid_slam_b200 import capi, host
+    its = host.default_iterations(args.levels, capi.MODE_TRACKER)
+    trackers = [OracleTracker(args.rows, args.cols, intr, levels=args.levels, iterations=tuple(its),
+                              kind="ref" if use_ref else "cpu") for _ in range(S)]
+    if use_ref:
+        feed = lambda k, j: (depth[k, j].contiguous(), rgb[k, j].contiguous())
+    else:
+        dn, cn = depth.cpu().numpy().astype(np.uint16), rgb.cpu().numpy()
+        feed = lambda k, j: (dn[k, j], cn[k, j])
+    for k in range(0, 1 + W):
+        for j in range(S):
+            trackers[j].track(*feed(k, j))
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(1 + W, n_frames):
+        for j in range(S):
+            trackers[j].track(*feed(k, j))
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    val = S * K / dt
+    kind = "reference" if use_ref else "port"
+    return {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "tum_synth_640x480_4lvl_tracker", "streams_per_gpu": S, "frames_per_step": S,
+                   "iterations": its,
+                   "note": ("the reference's own CUDA kernels + bridge functions (sm_100a build of src/cuda/*.cu) with the "
+                            "restated trackNewFrame host loop; the reference has no CPU implementation of this path and "
+                            "no batching, frames are processed one at a time") if use_ref else
+                           "CPU oracle port (reference library not present)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
+                         "sample": "%d frames x %d streams, one frame at a time" % (K, S)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+
+
+def main():
+    args = parse()
+    world, rank, local = dist_setup(args)
+    try:
+        if args.impl == "reference":
+            out = run_reference(args, world, rank, local)
+        else:
+            out = run_b200(args, world, rank, local)
+        if rank == 0 and out is not None:
+            print(json.dumps(out))
+            sys.stdout.flush()
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -245,6 +245,10 @@ int rgbid_aligner_fetch(rgbid_aligner* al, double* R_out, double* t_out, double*
 /* Frame statistics of the last tracker-mode run: chi_square / chi_test / ndof of the end-of-frame test
  * (src/visodo.cpp:1411-1415), 3 floats per pair. */
 int rgbid_aligner_frame_stats(rgbid_aligner* al, float* stats_out);
+/* Measurement hook for bench.py's roofline: launches the fused warp+residual+J^T J kernel of `level` `reps`
+ * times back to back on the aligner's current maps / poses / scales (no pose update), bracketed by CUDA
+ * events on the context's stream; returns the average launch duration in milliseconds.  Synchronous. */
+int rgbid_aligner_time_build(rgbid_aligner* al, int level, int reps, float* ms_per_launch_host);
 /* Device pointer + pitch of an internal pyramid map, for tests and for callers that fill maps in place.
  * which: 0 W_kf, 1 I_kf, 2 gWx, 3 gWy, 4 gIx, 5 gIy, 6 W_cur, 7 I_cur, 8..11 covariance-only gradients */
 int rgbid_aligner_map(rgbid_aligner* al, int which, int level, int index, float** ptr, size_t* pitch);

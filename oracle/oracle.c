@@ -214,7 +214,14 @@ static inline float tex_linear(const float* img, int rows, int cols, float x, fl
     int ka = (int)floorf(a * 256.f + 0.5f), kb = (int)floorf(b * 256.f + 0.5f);
     int w11 = (ka * kb + 128) >> 8;
     int w10 = ka - w11, w01 = kb - w11, w00 = 256 - ka - kb + w11;
-    return ((float)w00 * t00 + (float)w10 * t10 + (float)w01 * t01 + (float)w11 * t11) * (1.f / 256.f);
+    /* a tap with zero weight is not blended by the hardware: a NaN texel (the corner pixels of every
+     * pyramid level >= 1 are NaN, pyrdown.cu:124-127) only poisons the result if its weight is non-zero */
+    float acc = 0.f;
+    if (w00) acc += (float)w00 * t00;
+    if (w10) acc += (float)w10 * t10;
+    if (w01) acc += (float)w01 * t01;
+    if (w11) acc += (float)w11 * t11;
+    return acc * (1.f / 256.f);
   }
   if (g_tex_frac_mode == ORC_TEX_FRAC_TRUNC) {
     a = floorf(a * 256.f) * (1.f / 256.f);

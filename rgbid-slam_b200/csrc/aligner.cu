@@ -349,6 +349,32 @@ int rgbid_aligner_frame_stats(rgbid_aligner* al, float* stats_out)
   return RGBID_OK;
 }
 
+int rgbid_aligner_time_build(rgbid_aligner* al, int level, int reps, float* ms_per_launch)
+{
+  if (!al || level < 0 || level >= al->cfg.levels || reps < 1 || !ms_per_launch) return RGBID_ERR_ARG;
+  cudaStream_t s = al->ctx->stream;
+  cudaEvent_t e0, e1;
+  RGBID_CUDA_TRY(cudaEventCreate(&e0));
+  RGBID_CUDA_TRY(cudaEventCreate(&e1));
+  GnParams P = base_params(al, level);
+  P.iter_index = -1; P.update_pose = 0; P.compute_cov = 0;
+  const bool tracker = (al->cfg.mode == RGBID_MODE_TRACKER);
+  P.use_scale = (tracker && al->cfg.sigma_estimator != RGBID_SIGMA_PDF) ? 0 : 1;
+  GnLevelMaps M = level_maps(al, level, false);
+  LaunchCtx L = al->ctx->L();
+  launch_gn_build(L, M, P, al->d_states, al->d_scales, al->d_partials, 32, al->d_counters, nullptr);  // warm
+  RGBID_CUDA_TRY(cudaEventRecord(e0, s));
+  for (int r = 0; r < reps; ++r)
+    launch_gn_build(L, M, P, al->d_states, al->d_scales, al->d_partials, 32, al->d_counters, nullptr);
+  RGBID_CUDA_TRY(cudaEventRecord(e1, s));
+  RGBID_CUDA_TRY(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  RGBID_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *ms_per_launch = ms / reps;
+  return check_last(al->ctx);
+}
+
 int rgbid_aligner_map(rgbid_aligner* al, int which, int level, int index, float** ptr, size_t* pitch)
 {
   if (!al || which < 0 || which >= MAP_COUNT || level < 0 || level >= al->cfg.levels || index < 0 ||

@@ -95,8 +95,14 @@ __device__ __forceinline__ float sample_bilinear_q8(const float* __restrict__ ba
   const float* r0 = (const float*)((const char*)base + (size_t)j0 * pitch);
   const float* r1 = (const float*)((const char*)base + (size_t)j1 * pitch);
   float t00 = __ldg(r0 + i0), t10 = __ldg(r0 + i1), t01 = __ldg(r1 + i0), t11 = __ldg(r1 + i1);
-  return (__int2float_rn(w00) * t00 + __int2float_rn(w10) * t10 + __int2float_rn(w01) * t01 +
-          __int2float_rn(w11) * t11) * (1.f / 256.f);
+  // a tap with zero weight is not blended by the hardware: a NaN texel (the corner pixels of every pyramid
+  // level >= 1 are NaN, pyrdown.cu:124-127) only poisons the result when its weight is non-zero
+  float acc = 0.f;
+  if (w00) acc += __int2float_rn(w00) * t00;
+  if (w10) acc += __int2float_rn(w10) * t10;
+  if (w01) acc += __int2float_rn(w01) * t01;
+  if (w11) acc += __int2float_rn(w11) * t11;
+  return acc * (1.f / 256.f);
 }
 
 // Warp of one keyframe pixel: the fused equivalent of trafo3DKernelInvDepthGridStride

@@ -370,6 +370,11 @@ class Aligner:
         t = np.ascontiguousarray(t, dtype=np.float64)
         capi.check(self.lib.rgbid_aligner_enqueue(self.h, _dp(R), _dp(t)), "aligner_enqueue")
 
+    def time_build(self, level=0, reps=20):
+        ms = _F(0)
+        capi.check(self.lib.rgbid_aligner_time_build(self.h, level, reps, C.byref(ms)), "aligner_time_build")
+        return ms.value
+
     def map(self, name, level, index=0):
         """torch view (rows x cols, row-pitched) of an internal pyramid map."""
         p, pitch = C.c_void_p(), C.c_size_t()
@@ -445,6 +450,15 @@ class Tracker:
             pd, pc, host = depth.ctypes.data, rgb.ctypes.data, 1
         capi.check(self.lib.rgbid_tracker_track(self.h, pd, pc, host, self.results), "tracker_track")
         return self.results
+
+    @property
+    def aligner_handle(self):
+        return C.c_void_p(self.lib.rgbid_tracker_aligner(self.h))
+
+    def time_build(self, level=0, reps=20):
+        ms = _F(0)
+        capi.check(self.lib.rgbid_aligner_time_build(self.aligner_handle, level, reps, C.byref(ms)), "aligner_time_build")
+        return ms.value
 
     def keyframe_map(self, which, index=0):
         p, pitch = C.c_void_p(), C.c_size_t()
