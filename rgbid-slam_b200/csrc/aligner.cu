@@ -98,6 +98,9 @@ static GnLevelMaps level_maps(const rgbid_aligner* al, int level, bool cov_gradi
   M.gIx = al->maps[cov_gradients ? MAP_CGIX : MAP_GIX][level];
   M.gIy = al->maps[cov_gradients ? MAP_CGIY : MAP_GIY][level];
   M.Wc = al->maps[MAP_W_CUR][level]; M.Ic = al->maps[MAP_I_CUR][level];
+  const int B = al->cfg.batch;
+  M.texW = al->use_tex ? al->d_tex + (size_t)(level * 2 + 0) * B : nullptr;
+  M.texI = al->use_tex ? al->d_tex + (size_t)(level * 2 + 1) * B : nullptr;
   return M;
 }
 
@@ -174,7 +177,7 @@ int rgbid_aligner_create(rgbid_ctx* ctx, const rgbid_align_config* cfg, rgbid_al
     LevelGeom& g = al->geom[l];
     g.rows = cfg->rows >> l; g.cols = cfg->cols >> l;
     g.pitch = align_up((size_t)g.cols * sizeof(float), 128);
-    g.sstride = align_up(g.pitch * g.rows, 256);
+    g.sstride = align_up(g.pitch * g.rows, 512);  // texture base alignment
     rgbid_error_geometry(g.rows, g.cols, al->cfg.nsamples, &g.kept_rows, &g.kept_cols, &g.sample_stride);
     int nmaps = tracker ? (int)MAP_COUNT : 8;
     total += (size_t)nmaps * g.sstride * B;
@@ -217,6 +220,37 @@ int rgbid_aligner_create(rgbid_ctx* ctx, const rgbid_align_config* cfg, rgbid_al
   if (e == cudaSuccess) e = cudaMemsetAsync(al->d_arena, 0xff, off_depth, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) { rgbid_aligner_destroy(al); return RGBID_ERR_CUDA_BASE + (int)e; }
+  // Texture objects over the current-frame pyramid (created once; the reference creates and destroys one per
+  // warp call, warping_registration.cu:926-964).  RGBID_SAMPLER=soft selects the software sampler instead.
+  const char* sampler = getenv("RGBID_SAMPLER");
+  al->use_tex = !(sampler && sampler[0] == 's');
+  if (al->use_tex) {
+    const size_t ntex = (size_t)cfg->levels * 2 * B;
+    al->h_tex = new (std::nothrow) cudaTextureObject_t[ntex];
+    if (!al->h_tex) { rgbid_aligner_destroy(al); return RGBID_ERR_NOMEM; }
+    memset(al->h_tex, 0, sizeof(cudaTextureObject_t) * ntex);
+    for (int l = 0; l < cfg->levels && e == cudaSuccess; ++l)
+      for (int which = 0; which < 2 && e == cudaSuccess; ++which)
+        for (int b = 0; b < B && e == cudaSuccess; ++b) {
+          ImgB v = al->view(which == 0 ? MAP_W_CUR : MAP_I_CUR, l, b);
+          cudaResourceDesc rd;
+          memset(&rd, 0, sizeof(rd));
+          rd.resType = cudaResourceTypePitch2D;
+          rd.res.pitch2D.devPtr = v.p; rd.res.pitch2D.pitchInBytes = v.pitch;
+          rd.res.pitch2D.width = v.cols; rd.res.pitch2D.height = v.rows;
+          rd.res.pitch2D.desc = cudaCreateChannelDesc<float>();
+          cudaTextureDesc td;
+          memset(&td, 0, sizeof(td));
+          td.readMode = cudaReadModeElementType;
+          td.addressMode[0] = cudaAddressModeClamp; td.addressMode[1] = cudaAddressModeClamp;
+          td.filterMode = which == 0 ? cudaFilterModePoint : cudaFilterModeLinear;
+          td.normalizedCoords = 0;
+          e = cudaCreateTextureObject(&al->h_tex[(size_t)(l * 2 + which) * B + b], &rd, &td, nullptr);
+        }
+    if (e == cudaSuccess) e = cudaMalloc(&al->d_tex, sizeof(cudaTextureObject_t) * ntex);
+    if (e == cudaSuccess) e = cudaMemcpy(al->d_tex, al->h_tex, sizeof(cudaTextureObject_t) * ntex, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { rgbid_aligner_destroy(al); return RGBID_ERR_CUDA_BASE + (int)e; }
+  }
   const char* no_graph = getenv("RGBID_NO_GRAPH");
   al->use_graph = !(no_graph && no_graph[0] == '1') && (ctx->stream != (cudaStream_t)0);
   al->image_filtering = RGBID_NO_FILTERS;
@@ -229,6 +263,12 @@ int rgbid_aligner_destroy(rgbid_aligner* al)
   if (!al) return RGBID_OK;
   cudaStreamSynchronize(al->ctx->stream);
   if (al->gn_exec) cudaGraphExecDestroy(al->gn_exec);
+  if (al->h_tex) {
+    const size_t ntex = (size_t)al->cfg.levels * 2 * al->cfg.batch;
+    for (size_t i = 0; i < ntex; ++i) if (al->h_tex[i]) cudaDestroyTextureObject(al->h_tex[i]);
+    delete[] al->h_tex;
+  }
+  cudaFree(al->d_tex);
   cudaFree(al->d_arena); cudaFree(al->d_states); cudaFree(al->d_scales); cudaFree(al->d_partials);
   cudaFree(al->d_counters); cudaFree(al->d_trace); cudaFree(al->d_init); cudaFree(al->d_active);
   if (al->h_states) cudaFreeHost(al->h_states);

@@ -49,6 +49,10 @@ struct rgbid_aligner {
   cudaGraphExec_t gn_exec;
   long long gn_graph_launches;
   int image_filtering;
+  // texture objects over the current-frame pyramid: [level][0: W point | 1: I linear][batch]
+  bool use_tex;
+  cudaTextureObject_t* h_tex;
+  cudaTextureObject_t* d_tex;
 
   rgbid::ImgB view(int which, int level, int index) const
   {

@@ -105,13 +105,25 @@ __device__ __forceinline__ float sample_bilinear_q8(const float* __restrict__ ba
   return acc * (1.f / 256.f);
 }
 
+// Current-frame maps of one stream at one level: raw pointers for the software sampler and (optionally)
+// texture objects over the same memory: texW = point filter, texI = linear filter, both clamp / unnormalised,
+// i.e. exactly the objects the reference creates per call (warping_registration.cu:926-947, 977-998) but
+// created once per buffer.
+struct CurFrame {
+  const float* Wc;
+  const float* Ic;
+  size_t wpitch, ipitch;
+  cudaTextureObject_t texW, texI;
+};
+
 // Warp of one keyframe pixel: the fused equivalent of trafo3DKernelInvDepthGridStride
 // (warping_registration.cu:505-546) followed by trafo3DKernelIntensityWithInvDepthGridStride
 // (:465-501).  geom_is_warped selects the tracker's behaviour (intensity is warped with the
 // just-warped inverse depth as geometry, src/visodo.cpp:1121-1126) or KeyframeAlign's (keyframe inverse
-// depth as geometry, src/keyframe_align.cpp:239).
-__device__ __forceinline__ void warp_pixel(const Proj& P, int x, int y, float w0, const float* __restrict__ Wc,
-                                           size_t wpitch, const float* __restrict__ Ic, size_t ipitch, int cols,
+// depth as geometry, src/keyframe_align.cpp:239).  TEX: gather through the texture unit (1 instruction per
+// fetch, hardware bilinear) instead of the software sampler (same results, see tests).
+template <bool TEX>
+__device__ __forceinline__ void warp_pixel(const Proj& P, int x, int y, float w0, const CurFrame& C, int cols,
                                            int rows, bool geom_is_warped, float& w1, float& i1)
 {
   w1 = qnanf();
@@ -122,7 +134,7 @@ __device__ __forceinline__ void warp_pixel(const Proj& P, int x, int y, float w0
   float xt = xs + 0.5f, yt = ys + 0.5f;
   bool inside = in_image(xt, yt, cols, rows);
   if (inside) {
-    float w2 = sample_nearest(Wc, wpitch, xt, yt);
+    float w2 = TEX ? tex2D<float>(C.texW, xt, yt) : sample_nearest(C.Wc, C.wpitch, xt, yt);
     float tz = P.t[2];
     float v1z = (1.f / w3 - tz) * w0;
     float res = (v1z / (1.f - w2 * tz)) * w2;
@@ -135,7 +147,7 @@ __device__ __forceinline__ void warp_pixel(const Proj& P, int x, int y, float w0
     inside = in_image(xt, yt, cols, rows);
   }
   if (inside) {
-    float r = sample_bilinear_q8(Ic, ipitch, cols, rows, xt, yt);
+    float r = TEX ? tex2D<float>(C.texI, xt, yt) : sample_bilinear_q8(C.Ic, C.ipitch, cols, rows, xt, yt);
     i1 = fmaxf(0.f, fminf(r, 255.f));
   }
 }

@@ -31,6 +31,7 @@ constexpr int kAccChi = 31;  // + [rho_int, n_int, rho_depthinv, n_depthinv]
 struct PixelParams {
   float fx, fy, cx, cy;
   float inv_sigma_int, inv_sigma_depthinv;
+  float inv_sigma2_int, inv_sigma2_depthinv;
   float bias_over_sigma_int, bias_over_sigma_depthinv;
   float nu_int, nu_depthinv;
   int mestimator, weighting, student_nu;
@@ -53,54 +54,52 @@ __device__ __forceinline__ float chi_rho_dev(float e, int mest)
 
 // One keyframe pixel of computeSystemGridStride / computeStudentNuSystemGridStride
 // (src/cuda/estimate_VO.cu:176-262 constraints, :295-329 / :384-418 weights + accumulation).
+//
+// The reference scales each Jacobian row and residual by 1/sigma and accumulates w * row_i * row_j.  Here the
+// rows stay un-normalised and 1/sigma^2 is folded into the weight (s = w / sigma^2), which is the same sum with
+// 12 fewer multiplies per pixel; each of the 27 terms is two FMAs straight into the accumulator.
 template <bool CHI>
 __device__ __forceinline__ void accumulate_pixel(float* __restrict__ acc, int x, int y, float w0, float i0, float gwx,
                                                  float gwy, float gix, float giy, float w1, float i1,
                                                  const PixelParams& pp)
 {
-  float px = (__int2float_rn(x) - pp.cx) / pp.fx;
-  float py = (__int2float_rn(y) - pp.cy) / pp.fy;
+  const float px = (__int2float_rn(x) - pp.cx) / pp.fx;
+  const float py = (__int2float_rn(y) - pp.cy) / pp.fy;
 
   float rd[6], ri[6];
-  float err_d = 0.f, err_i = 0.f, wgt_d = 0.f, wgt_i = 0.f, n_factor = 1.f;
-  bool any = false;
+  float err_d = 0.f, err_i = 0.f, s_d = 0.f, s_i = 0.f, wgt_d = 0.f, wgt_i = 0.f;
+  const bool valid_d = !(isnan(w0) || isnan(w1) || isnan(gwx) || isnan(gwy));
+  const bool valid_i = !(isnan(w0) || isnan(i0) || isnan(i1) || isnan(gix) || isnan(giy));
 
   // invDepthConstraint (estimate_VO.cu:214-262)
-  if (!(isnan(w0) || isnan(w1) || isnan(gwx) || isnan(gwy))) {
+  if (valid_d) {
     float g0 = gwx * pp.fx, g1 = gwy * pp.fy;
     float g2 = -(g0 * px + g1 * py);
     float inv_w0 = 1.f / w0;
     float n0 = g0 * inv_w0, n1 = g1 * inv_w0, n2 = g2 * inv_w0 + 1.f;
-    float rn = rsqrtf(n0 * n0 + n1 * n1 + n2 * n2);
-    float rp = rsqrtf(px * px + py * py + 1.f);
-    n_factor = fabsf((n0 * rn) * (px * rp) + (n1 * rn) * (py * rp) + (n2 * rn) * rp);
-    float wgt = pp.inv_sigma_depthinv;
-    float t0 = g0 * w0, t1 = g1 * w0, t2 = g2 * w0 + w0 * w1;
+    // |n . p| / (|n| |p|) with p = (px, py, 1)
+    float n_factor = fabsf(n0 * px + n1 * py + n2) * rsqrtf((n0 * n0 + n1 * n1 + n2 * n2) * (px * px + py * py + 1.f));
     float h2 = g2 + w1;
-    // row_rot = -(g x p), p = (px, py, 1)
-    float r0 = -(g1 - h2 * py), r1 = -(h2 * px - g0), r2 = -(g0 * py - g1 * px);
-    rd[0] = t0 * wgt; rd[1] = t1 * wgt; rd[2] = t2 * wgt; rd[3] = r0 * wgt; rd[4] = r1 * wgt; rd[5] = r2 * wgt;
-    float b = w1 - w0;
-    err_d = -b * wgt;
-    float eu = err_d - pp.bias_over_sigma_depthinv;
-    float wv = pp.student_nu ? (pp.nu_depthinv + 1.f) / (pp.nu_depthinv + eu * eu) : mest_weight(eu, pp.mestimator);
-    wgt_d = (pp.weighting == RGBID_PHOT_ONLY) ? 0.f : wv;
-    any = true;
+    rd[0] = g0 * w0; rd[1] = g1 * w0; rd[2] = g2 * w0 + w0 * w1;
+    rd[3] = h2 * py - g1; rd[4] = g0 - h2 * px; rd[5] = g1 * px - g0 * py;  // -(g' x p), g' = (g0, g1, h2)
+    err_d = w0 - w1;                                                        // -(w1 - w0)
+    float eu = err_d * pp.inv_sigma_depthinv - pp.bias_over_sigma_depthinv;
+    wgt_d = pp.student_nu ? (pp.nu_depthinv + 1.f) / (pp.nu_depthinv + eu * eu) : mest_weight(eu, pp.mestimator);
+    if (pp.weighting == RGBID_PHOT_ONLY) wgt_d = 0.f;
+    s_d = n_factor * wgt_d * pp.inv_sigma2_depthinv;
   }
   // intensityConstraint (estimate_VO.cu:176-212)
-  if (!(isnan(w0) || isnan(i0) || isnan(i1) || isnan(gix) || isnan(giy))) {
+  if (valid_i) {
     float g0 = gix * pp.fx, g1 = giy * pp.fy;
     float g2 = -(g0 * px + g1 * py);
-    float wgt = pp.inv_sigma_int;
-    float r0 = -(g1 - g2 * py), r1 = -(g2 * px - g0), r2 = -(g0 * py - g1 * px);
-    ri[0] = (g0 * w0) * wgt; ri[1] = (g1 * w0) * wgt; ri[2] = (g2 * w0) * wgt;
-    ri[3] = r0 * wgt; ri[4] = r1 * wgt; ri[5] = r2 * wgt;
-    float b = i1 - i0;
-    err_i = -b * wgt;
-    float eu = err_i - pp.bias_over_sigma_int;
-    float wv = pp.student_nu ? (pp.nu_int + 1.f) / (pp.nu_int + eu * eu) : mest_weight(eu, pp.mestimator);
-    wgt_i = (pp.weighting == RGBID_GEOM_ONLY) ? 0.f : wv;
-    any = true;
+    ri[0] = g0 * w0; ri[1] = g1 * w0; ri[2] = g2 * w0;
+    ri[3] = g2 * py - g1; ri[4] = g0 - g2 * px; ri[5] = g1 * px - g0 * py;  // -(g x p)
+    err_i = i0 - i1;
+    float eu = err_i * pp.inv_sigma_int - pp.bias_over_sigma_int;
+    wgt_i = pp.student_nu ? (pp.nu_int + 1.f) / (pp.nu_int + eu * eu) : mest_weight(eu, pp.mestimator);
+    if (pp.weighting == RGBID_GEOM_ONLY) wgt_i = 0.f;
+    if (pp.weighting == RGBID_MIN_WEIGHT) wgt_i = fminf(wgt_d, wgt_i);  // wgt_d is 0 if the depth row is invalid
+    s_i = wgt_i * pp.inv_sigma2_int;
   }
   if (CHI) {
     // end-of-frame chi^2 on all finite full-resolution residuals (src/visodo.cpp:1411-1414,
@@ -111,27 +110,26 @@ __device__ __forceinline__ void accumulate_pixel(float* __restrict__ acc, int x,
       if (!(isnan(ed) || isinf(ed))) { acc[29] += chi_rho_dev(ed, pp.chi_mestimator); acc[30] += 1.f; }
     }
   }
-  if (!any) return;
-  if (pp.weighting == RGBID_MIN_WEIGHT) wgt_i = fminf(wgt_d, wgt_i);
-  // an invalid constraint contributes weight 0 (the reference multiplies stale rows by a zero weight)
-  if (wgt_i == 0.f) {
+  // an invalid (or zero-weight) constraint contributes nothing: the reference multiplies stale rows by weight 0
+  if (s_i != 0.f) {
+    int shift = 0;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) ri[k] = 0.f;
-    err_i = 0.f;
+    for (int i = 0; i < 6; ++i) {
+      const float si = s_i * ri[i];
+#pragma unroll
+      for (int j = i; j < 6; ++j) { acc[shift] = fmaf(si, ri[j], acc[shift]); ++shift; }
+      acc[shift] = fmaf(si, err_i, acc[shift]); ++shift;
+    }
   }
-  float wd = n_factor * wgt_d;
-  if (wgt_d == 0.f) {
+  if (s_d != 0.f) {
+    int shift = 0;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) rd[k] = 0.f;
-    err_d = 0.f; wd = 0.f;
-  }
-  int shift = 0;
+    for (int i = 0; i < 6; ++i) {
+      const float sd = s_d * rd[i];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    float si = wgt_i * ri[i], sd = wd * rd[i];
-#pragma unroll
-    for (int j = i; j < 6; ++j) acc[shift++] += si * ri[j] + sd * rd[j];
-    acc[shift++] += si * err_i + sd * err_d;
+      for (int j = i; j < 6; ++j) { acc[shift] = fmaf(sd, rd[j], acc[shift]); ++shift; }
+      acc[shift] = fmaf(sd, err_d, acc[shift]); ++shift;
+    }
   }
 }
 
@@ -261,6 +259,8 @@ __device__ __forceinline__ PixelParams make_pixel_params(const GnParams& P, cons
     nu_int = sc->nu_int; nu_d = sc->nu_depthinv;
   }
   pp.inv_sigma_int = 1.f / sigma_int; pp.inv_sigma_depthinv = 1.f / sigma_d;
+  pp.inv_sigma2_int = pp.inv_sigma_int * pp.inv_sigma_int;
+  pp.inv_sigma2_depthinv = pp.inv_sigma_depthinv * pp.inv_sigma_depthinv;
   pp.bias_over_sigma_int = bias_int / sigma_int; pp.bias_over_sigma_depthinv = bias_d / sigma_d;
   pp.nu_int = nu_int; pp.nu_depthinv = nu_d;
   pp.mestimator = P.mestimator; pp.weighting = P.weighting; pp.student_nu = P.student_nu;
@@ -271,7 +271,7 @@ __device__ __forceinline__ PixelParams make_pixel_params(const GnParams& P, cons
 // ------------------------------------------------------------------------------------------------------------
 // gn_build_kernel.  grid = (ctas_per_pair, batch); VEC = pixels per thread step (4: float4 path, 1: scalar).
 // ------------------------------------------------------------------------------------------------------------
-template <int VEC, bool CHI>
+template <int VEC, bool CHI, bool TEX>
 __global__ void __launch_bounds__(kBuildThreads, 2)
     gn_build_kernel(const GnLevelMaps M, const GnParams P, GnState* __restrict__ states,
                     const ScaleState* __restrict__ scales, double* __restrict__ partials, int partial_stride,
@@ -296,8 +296,10 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
 #pragma unroll
   for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
 
-  const float* Wc = M.Wc.row(b, 0);
-  const float* Ic = M.Ic.row(b, 0);
+  CurFrame cur;
+  cur.Wc = M.Wc.row(b, 0); cur.Ic = M.Ic.row(b, 0);
+  cur.wpitch = M.Wc.pitch; cur.ipitch = M.Ic.pitch;
+  cur.texW = TEX ? M.texW[b] : 0; cur.texI = TEX ? M.texI[b] : 0;
   const int cols = P.cols, rows = P.rows;
   const int upr = cols / VEC;  // units per row
   const int total = upr * rows;
@@ -319,7 +321,7 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
     float w1[VEC], i1[VEC];
 #pragma unroll
     for (int k = 0; k < VEC; ++k)
-      warp_pixel(proj, x0 + k, y, w0[k], Wc, M.Wc.pitch, Ic, M.Ic.pitch, cols, rows, geom_is_warped, w1[k], i1[k]);
+      warp_pixel<TEX>(proj, x0 + k, y, w0[k], cur, cols, rows, geom_is_warped, w1[k], i1[k]);
 #pragma unroll
     for (int k = 0; k < VEC; ++k)
       accumulate_pixel<CHI>(acc, x0 + k, y, w0[k], i0[k], gwx[k], gwy[k], gix[k], giy[k], w1[k], i1[k], pp);
@@ -372,6 +374,7 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
 // gn_scale_kernel: fused warp + residual sampling + scale estimation; one 8-CTA cluster per pair.
 // Sampling geometry of computeErrorGridStride (sigmaFuncs.cu:711-747): sample (s y, s x) -> index y*kept_cols+x.
 // ------------------------------------------------------------------------------------------------------------
+template <bool TEX>
 __global__ void __cluster_dims__(kScaleCluster, 1, 1) __launch_bounds__(kScaleThreads)
     gn_scale_kernel(const GnLevelMaps M, const GnParams P, const GnState* __restrict__ states,
                     ScaleState* __restrict__ scales)
@@ -395,8 +398,10 @@ __global__ void __cluster_dims__(kScaleCluster, 1, 1) __launch_bounds__(kScaleTh
   float* samp_int = smem_samples;
   float* samp_dep = smem_samples + chunk;
   const bool geom_is_warped = (P.mode == RGBID_MODE_TRACKER);
-  const float* Wc = M.Wc.row(b, 0);
-  const float* Ic = M.Ic.row(b, 0);
+  CurFrame cur;
+  cur.Wc = M.Wc.row(b, 0); cur.Ic = M.Ic.row(b, 0);
+  cur.wpitch = M.Wc.pitch; cur.ipitch = M.Ic.pitch;
+  cur.texW = TEX ? M.texW[b] : 0; cur.texI = TEX ? M.texI[b] : 0;
   const int s = P.sample_stride;
   for (int il = threadIdx.x; il < n_local; il += kScaleThreads) {
     const int i = begin + il;
@@ -404,7 +409,7 @@ __global__ void __cluster_dims__(kScaleCluster, 1, 1) __launch_bounds__(kScaleTh
     const int x = s * xs, y = s * ys;
     float w0 = __ldg(M.W0.row(b, y) + x), i0 = __ldg(M.I0.row(b, y) + x);
     float w1, i1;
-    warp_pixel(proj, x, y, w0, Wc, M.Wc.pitch, Ic, M.Ic.pitch, P.cols, P.rows, geom_is_warped, w1, i1);
+    warp_pixel<TEX>(proj, x, y, w0, cur, P.cols, P.rows, geom_is_warped, w1, i1);
     samp_int[il] = i1 - i0;
     samp_dep[il] = w1 - w0;
   }
@@ -449,14 +454,15 @@ inline bool aligned16(const ImgB& m) { return ((uintptr_t)m.p % 16 == 0) && (m.p
 
 int gn_build_grid_x(int rows, int cols, int batch, int num_sms)
 {
-  // Enough CTAs for one balanced wave at 2 CTAs / SM across the batch, never more than one quad per thread
-  // would need, and at most num_sms per pair so the last-block final sum stays short.
-  int units = (cols % 4 == 0) ? (cols / 4) * rows : cols * rows;
-  int need = (units + kBuildThreads - 1) / kBuildThreads;
-  int target = (2 * num_sms + batch - 1) / batch;
-  if (target < 4) target = 4;
-  if (target > num_sms) target = num_sms;
-  int g = need < target ? need : target;
+  // One balanced wave: the kernel is resident at 2 CTAs / SM, so the whole launch (all pairs) should use at
+  // most 2 * num_sms CTAs, every thread should get the same number k of units, and a pair never gets more than
+  // num_sms CTAs so that the last-block final sum stays short.
+  const int units = (cols % 4 == 0) ? (cols / 4) * rows : cols * rows;
+  int cap = (2 * num_sms) / batch;
+  if (cap < 1) cap = 1;
+  if (cap > num_sms) cap = num_sms;
+  const int k = (units + cap * kBuildThreads - 1) / (cap * kBuildThreads);  // units per thread
+  int g = (units + k * kBuildThreads - 1) / (k * kBuildThreads);
   return g < 1 ? 1 : g;
 }
 
@@ -474,11 +480,26 @@ void launch_gn_scale(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P
   size_t smem = (size_t)2 * chunk * sizeof(float);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(gn_scale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(gn_scale_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(gn_scale_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  gn_scale_kernel<<<kScaleCluster * P.batch, kScaleThreads, smem, L.stream>>>(M, P, states, scales);
+  if (M.texW != nullptr && M.texI != nullptr)
+    gn_scale_kernel<true><<<kScaleCluster * P.batch, kScaleThreads, smem, L.stream>>>(M, P, states, scales);
+  else
+    gn_scale_kernel<false><<<kScaleCluster * P.batch, kScaleThreads, smem, L.stream>>>(M, P, states, scales);
   ++*L.launches;
+}
+
+template <int VEC, bool CHI>
+static void launch_gn_build_t(const LaunchCtx& L, dim3 grid, bool tex, const GnLevelMaps& M, const GnParams& P,
+                              GnState* states, const ScaleState* scales, double* partials, int partial_stride,
+                              unsigned int* counters, rgbid_iter_trace* trace)
+{
+  if (tex)
+    gn_build_kernel<VEC, CHI, true><<<grid, kBuildThreads, 0, L.stream>>>(M, P, states, scales, partials, partial_stride, counters, trace);
+  else
+    gn_build_kernel<VEC, CHI, false><<<grid, kBuildThreads, 0, L.stream>>>(M, P, states, scales, partials, partial_stride, counters, trace);
 }
 
 void launch_gn_build(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P, GnState* states,
@@ -489,12 +510,13 @@ void launch_gn_build(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P
              aligned16(M.gIx) && aligned16(M.gIy);
   dim3 grid(gn_build_grid_x(P.rows, P.cols, P.batch, L.num_sms), P.batch);
   const bool chi = (P.chi_mestimator >= 0);
+  const bool tex = (M.texW != nullptr && M.texI != nullptr);
   if (vec) {
-    if (chi) gn_build_kernel<4, true><<<grid, kBuildThreads, 0, L.stream>>>(M, P, states, scales, partials, partial_stride, counters, trace);
-    else gn_build_kernel<4, false><<<grid, kBuildThreads, 0, L.stream>>>(M, P, states, scales, partials, partial_stride, counters, trace);
+    if (chi) launch_gn_build_t<4, true>(L, grid, tex, M, P, states, scales, partials, partial_stride, counters, trace);
+    else launch_gn_build_t<4, false>(L, grid, tex, M, P, states, scales, partials, partial_stride, counters, trace);
   } else {
-    if (chi) gn_build_kernel<1, true><<<grid, kBuildThreads, 0, L.stream>>>(M, P, states, scales, partials, partial_stride, counters, trace);
-    else gn_build_kernel<1, false><<<grid, kBuildThreads, 0, L.stream>>>(M, P, states, scales, partials, partial_stride, counters, trace);
+    if (chi) launch_gn_build_t<1, true>(L, grid, tex, M, P, states, scales, partials, partial_stride, counters, trace);
+    else launch_gn_build_t<1, false>(L, grid, tex, M, P, states, scales, partials, partial_stride, counters, trace);
   }
   ++*L.launches;
 }
@@ -506,6 +528,8 @@ void launch_build_system(const LaunchCtx& L, ImgB W0, ImgB I0, ImgB gWx, ImgB gW
   PixelParams pp;
   pp.fx = sp.fx; pp.fy = sp.fy; pp.cx = sp.cx; pp.cy = sp.cy;
   pp.inv_sigma_int = 1.f / sp.sigma_int; pp.inv_sigma_depthinv = 1.f / sp.sigma_depthinv;
+  pp.inv_sigma2_int = pp.inv_sigma_int * pp.inv_sigma_int;
+  pp.inv_sigma2_depthinv = pp.inv_sigma_depthinv * pp.inv_sigma_depthinv;
   pp.bias_over_sigma_int = sp.bias_int / sp.sigma_int;
   pp.bias_over_sigma_depthinv = sp.bias_depthinv / sp.sigma_depthinv;
   pp.nu_int = sp.nu_int; pp.nu_depthinv = sp.nu_depthinv;

@@ -75,6 +75,9 @@ void launch_chi_square(const LaunchCtx& L, const float* err_int, const float* er
 struct GnLevelMaps {
   ImgB W0, I0, gWx, gWy, gIx, gIy;  // keyframe maps of this level
   ImgB Wc, Ic;                      // current-frame maps of this level
+  // optional texture objects over Wc (point) / Ic (linear), one per stream; null -> software sampler
+  const cudaTextureObject_t* texW;
+  const cudaTextureObject_t* texI;
 };
 
 // Device-resident state of one frame pair's Gauss-Newton problem

@@ -104,6 +104,19 @@ def test_align_is_deterministic_and_batch_invariant(ctx):
         assert np.allclose(many1["t"][b], one["t"][0], atol=1e-6) and np.allclose(many1["R"][b], one["R"][0], atol=1e-6)
 
 
+def test_texture_unit_and_software_sampler_agree(ctx, monkeypatch):
+    """The fused kernels gather through texture objects by default; RGBID_SAMPLER=soft selects the software
+    sampler that reproduces the texture unit's 8-bit weights.  Both must give the same alignment."""
+    rows, cols = 480, 640
+    P = pair_maps(seed=90, rows=rows, cols=cols, noise=True)
+    tex = _gpu_align(ctx, P, rows, cols, 3, capi.MODE_TRACKER).run(want_trace=True)
+    monkeypatch.setenv("RGBID_SAMPLER", "soft")
+    soft = _gpu_align(ctx, P, rows, cols, 3, capi.MODE_TRACKER).run(want_trace=True)
+    monkeypatch.delenv("RGBID_SAMPLER")
+    assert sums_rel_err(tex["trace"][0][0]["sums27"], soft["trace"][0][0]["sums27"]) < 1e-6
+    assert np.linalg.norm(tex["t"][0] - soft["t"][0]) < 1e-6 and rot_angle(tex["R"][0], soft["R"][0]) < 1e-6
+
+
 def test_align_host_upload_path(ctx):
     rows, cols = 240, 320
     P = pair_maps(seed=79, rows=rows, cols=cols)
