@@ -249,6 +249,8 @@ int rgbid_aligner_frame_stats(rgbid_aligner* al, float* stats_out);
  * times back to back on the aligner's current maps / poses / scales (no pose update), bracketed by CUDA
  * events on the context's stream; returns the average launch duration in milliseconds.  Synchronous. */
 int rgbid_aligner_time_build(rgbid_aligner* al, int level, int reps, float* ms_per_launch_host);
+/* Same for the fused sampling + scale-estimation kernel of `level`. */
+int rgbid_aligner_time_scale(rgbid_aligner* al, int level, int reps, float* ms_per_launch_host);
 /* Device pointer + pitch of an internal pyramid map, for tests and for callers that fill maps in place.
  * which: 0 W_kf, 1 I_kf, 2 gWx, 3 gWy, 4 gIx, 5 gIy, 6 W_cur, 7 I_cur, 8..11 covariance-only gradients */
 int rgbid_aligner_map(rgbid_aligner* al, int which, int level, int index, float** ptr, size_t* pitch);

@@ -36,6 +36,7 @@ def _deps():
 
 
 def build(force=False, verbose=False):
+    extra = os.environ.get("RGBID_EXTRA_NVCC_FLAGS", "").split()
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
     newest_hdr = max(os.path.getmtime(h) for h in _deps())
@@ -48,7 +49,7 @@ def build(force=False, verbose=False):
 
     def cc(job):
         src, obj = job
-        cmd = [NVCC] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        cmd = [NVCC] + NVCC_FLAGS + extra + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         with open(obj + ".log", "w") as f:
             f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)

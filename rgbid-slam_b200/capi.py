@@ -105,6 +105,7 @@ PROTOTYPES = {
     "rgbid_aligner_fetch": (I, [P, c_double_p, c_double_p, c_double_p, c_int_p, C.POINTER(IterTrace)]),
     "rgbid_aligner_frame_stats": (I, [P, c_float_p]),
     "rgbid_aligner_time_build": (I, [P, I, I, c_float_p]),
+    "rgbid_aligner_time_scale": (I, [P, I, I, c_float_p]),
     "rgbid_aligner_map": (I, [P, I, I, I, C.POINTER(P), C.POINTER(SZ)]),
     "rgbid_tracker_create": (I, [P, C.POINTER(TrackerConfig), C.POINTER(P)]),
     "rgbid_tracker_destroy": (I, [P]),

@@ -389,7 +389,19 @@ int rgbid_aligner_frame_stats(rgbid_aligner* al, float* stats_out)
   return RGBID_OK;
 }
 
+static int time_kernel(rgbid_aligner* al, int level, int reps, float* ms_per_launch, bool scale);
+
 int rgbid_aligner_time_build(rgbid_aligner* al, int level, int reps, float* ms_per_launch)
+{
+  return time_kernel(al, level, reps, ms_per_launch, false);
+}
+
+int rgbid_aligner_time_scale(rgbid_aligner* al, int level, int reps, float* ms_per_launch)
+{
+  return time_kernel(al, level, reps, ms_per_launch, true);
+}
+
+static int time_kernel(rgbid_aligner* al, int level, int reps, float* ms_per_launch, bool scale)
 {
   if (!al || level < 0 || level >= al->cfg.levels || reps < 1 || !ms_per_launch) return RGBID_ERR_ARG;
   cudaStream_t s = al->ctx->stream;
@@ -402,10 +414,13 @@ int rgbid_aligner_time_build(rgbid_aligner* al, int level, int reps, float* ms_p
   P.use_scale = (tracker && al->cfg.sigma_estimator != RGBID_SIGMA_PDF) ? 0 : 1;
   GnLevelMaps M = level_maps(al, level, false);
   LaunchCtx L = al->ctx->L();
-  launch_gn_build(L, M, P, al->d_states, al->d_scales, al->d_partials, 32, al->d_counters, nullptr);  // warm
+  auto go = [&]() {
+    if (scale) launch_gn_scale(L, M, P, al->d_states, al->d_scales);
+    else launch_gn_build(L, M, P, al->d_states, al->d_scales, al->d_partials, 32, al->d_counters, nullptr);
+  };
+  go();  // warm
   RGBID_CUDA_TRY(cudaEventRecord(e0, s));
-  for (int r = 0; r < reps; ++r)
-    launch_gn_build(L, M, P, al->d_states, al->d_scales, al->d_partials, 32, al->d_counters, nullptr);
+  for (int r = 0; r < reps; ++r) go();
   RGBID_CUDA_TRY(cudaEventRecord(e1, s));
   RGBID_CUDA_TRY(cudaEventSynchronize(e1));
   float ms = 0.f;

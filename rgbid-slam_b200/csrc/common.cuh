@@ -152,6 +152,47 @@ __device__ __forceinline__ void warp_pixel(const Proj& P, int x, int y, float w0
   }
 }
 
+// Branch-free two-stage form of warp_pixel for the texture path: clamp addressing makes every fetch safe, so
+// a thread can issue the fetches of all its pixels back to back (memory-level parallelism) and discard the
+// invalid ones afterwards.  Stage 1 -> coordinates of the inverse-depth fetch; stage 2 (after the fetch) ->
+// warped inverse depth and coordinates of the intensity fetch; stage 3 -> warped intensity.
+struct WarpCoord {
+  float xt, yt, w3;
+  bool inside;
+};
+
+__device__ __forceinline__ WarpCoord warp_stage1(const Proj& P, int x, int y, float w0, int cols, int rows)
+{
+  WarpCoord c;
+  float xs, ys;
+  c.w3 = project_pixel(P, x, y, w0, xs, ys);
+  c.xt = xs + 0.5f; c.yt = ys + 0.5f;
+  c.inside = !isnan(w0) && in_image(c.xt, c.yt, cols, rows);
+  return c;
+}
+
+__device__ __forceinline__ float warp_stage2(const Proj& P, int x, int y, float w0, float w2, WarpCoord& c, int cols,
+                                             int rows, bool geom_is_warped)
+{
+  float tz = P.t[2];
+  float v1z = (1.f / c.w3 - tz) * w0;
+  float res = (v1z / (1.f - w2 * tz)) * w2;
+  const bool ok = c.inside && (res > 0.f);
+  const float w1 = ok ? res : qnanf();
+  if (geom_is_warped) {  // uniform
+    float xs, ys;
+    project_pixel(P, x, y, w1, xs, ys);
+    c.xt = xs + 0.5f; c.yt = ys + 0.5f;
+    c.inside = ok && in_image(c.xt, c.yt, cols, rows);
+  }
+  return w1;
+}
+
+__device__ __forceinline__ float warp_stage3(float r, const WarpCoord& c)
+{
+  return c.inside ? fmaxf(0.f, fminf(r, 255.f)) : qnanf();
+}
+
 // ------------------------------------------------------------------------------------------------
 // Reductions
 // ------------------------------------------------------------------------------------------------

@@ -23,7 +23,14 @@ namespace rgbid {
 
 namespace {
 
-constexpr int kBuildThreads = 256;
+#ifndef RGBID_BUILD_THREADS
+#define RGBID_BUILD_THREADS 256
+#endif
+#ifndef RGBID_BUILD_MINBLOCKS
+#define RGBID_BUILD_MINBLOCKS 2
+#endif
+constexpr int kBuildThreads = RGBID_BUILD_THREADS;
+constexpr int kBuildMinBlocks = RGBID_BUILD_MINBLOCKS;
 constexpr int kBuildWarps = kBuildThreads / 32;
 constexpr int kAcc = 27;
 constexpr int kAccChi = 31;  // + [rho_int, n_int, rho_depthinv, n_depthinv]
@@ -136,7 +143,7 @@ __device__ __forceinline__ void accumulate_pixel(float* __restrict__ acc, int x,
 struct BuildShared {
   double warp_part[kBuildWarps][kAccChi];
   double total[kAccChi];
-  double fin[8][kAccChi];
+  double fin[kBuildWarps][kAccChi];
   Proj proj;
   int is_last;
 };
@@ -171,17 +178,17 @@ __device__ __forceinline__ bool reduce_and_elect(BuildShared& sh, const float* a
   if (!sh.is_last) return false;
   __threadfence();
   // fixed-order final sum: value k is summed by 8 threads over interleaved CTAs, then combined in order
-  const int k = tid % 32, part = tid / 32;  // NACC <= 32, 8 parts
+  const int k = tid % 32, part = tid / 32;  // NACC <= 32, kBuildWarps parts
   if (k < NACC) {
     double v = 0.0;
-    for (int c = part; c < nblk; c += 8) v += __ldcg(&partials[(size_t)c * partial_stride + k]);
+    for (int c = part; c < nblk; c += kBuildWarps) v += __ldcg(&partials[(size_t)c * partial_stride + k]);
     sh.fin[part][k] = v;
   }
   __syncthreads();
   if (tid < NACC) {
     double v = 0.0;
 #pragma unroll
-    for (int p = 0; p < 8; ++p) v += sh.fin[p][tid];
+    for (int p = 0; p < kBuildWarps; ++p) v += sh.fin[p][tid];
     sh.total[tid] = v;
   }
   __syncthreads();
@@ -272,7 +279,7 @@ __device__ __forceinline__ PixelParams make_pixel_params(const GnParams& P, cons
 // gn_build_kernel.  grid = (ctas_per_pair, batch); VEC = pixels per thread step (4: float4 path, 1: scalar).
 // ------------------------------------------------------------------------------------------------------------
 template <int VEC, bool CHI, bool TEX>
-__global__ void __launch_bounds__(kBuildThreads, 2)
+__global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
     gn_build_kernel(const GnLevelMaps M, const GnParams P, GnState* __restrict__ states,
                     const ScaleState* __restrict__ scales, double* __restrict__ partials, int partial_stride,
                     unsigned int* __restrict__ counters, rgbid_iter_trace* __restrict__ trace)
@@ -319,9 +326,25 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
       gix[0] = __ldg(M.gIx.row(b, y) + x0); giy[0] = __ldg(M.gIy.row(b, y) + x0);
     }
     float w1[VEC], i1[VEC];
+    if (TEX) {
+      // all inverse-depth fetches of this thread in flight, then all intensity fetches
+      WarpCoord wc[VEC];
+      float fetched[VEC];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k)
-      warp_pixel<TEX>(proj, x0 + k, y, w0[k], cur, cols, rows, geom_is_warped, w1[k], i1[k]);
+      for (int k = 0; k < VEC; ++k) wc[k] = warp_stage1(proj, x0 + k, y, w0[k], cols, rows);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) fetched[k] = tex2D<float>(cur.texW, wc[k].xt, wc[k].yt);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) w1[k] = warp_stage2(proj, x0 + k, y, w0[k], fetched[k], wc[k], cols, rows, geom_is_warped);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) fetched[k] = tex2D<float>(cur.texI, wc[k].xt, wc[k].yt);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) i1[k] = warp_stage3(fetched[k], wc[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k)
+        warp_pixel<false>(proj, x0 + k, y, w0[k], cur, cols, rows, geom_is_warped, w1[k], i1[k]);
+    }
 #pragma unroll
     for (int k = 0; k < VEC; ++k)
       accumulate_pixel<CHI>(acc, x0 + k, y, w0[k], i0[k], gwx[k], gwy[k], gix[k], giy[k], w1[k], i1[k], pp);
@@ -454,11 +477,11 @@ inline bool aligned16(const ImgB& m) { return ((uintptr_t)m.p % 16 == 0) && (m.p
 
 int gn_build_grid_x(int rows, int cols, int batch, int num_sms)
 {
-  // One balanced wave: the kernel is resident at 2 CTAs / SM, so the whole launch (all pairs) should use at
-  // most 2 * num_sms CTAs, every thread should get the same number k of units, and a pair never gets more than
+  // One balanced wave: the kernel is resident at kBuildMinBlocks CTAs / SM, so the whole launch (all pairs)
+  // should use at most that many CTAs per SM, every thread should get the same number k of units, and a pair never gets more than
   // num_sms CTAs so that the last-block final sum stays short.
   const int units = (cols % 4 == 0) ? (cols / 4) * rows : cols * rows;
-  int cap = (2 * num_sms) / batch;
+  int cap = (kBuildMinBlocks * num_sms) / batch;
   if (cap < 1) cap = 1;
   if (cap > num_sms) cap = num_sms;
   const int k = (units + cap * kBuildThreads - 1) / (cap * kBuildThreads);  // units per thread
@@ -478,6 +501,8 @@ void launch_gn_scale(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P
   const int n = P.kept_rows * P.kept_cols;
   const int chunk = (n + kScaleCluster - 1) / kScaleCluster;
   size_t smem = (size_t)2 * chunk * sizeof(float);
+  static bool table_ready = false;
+  if (!table_ready) { upload_nu_table(); table_ready = true; }
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaFuncSetAttribute(gn_scale_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

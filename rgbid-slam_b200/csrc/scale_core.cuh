@@ -19,26 +19,48 @@ constexpr int kScaleCluster = 8;    // CTAs per frame pair (portable cluster siz
 constexpr int kScaleThreads = 512;  // threads per CTA
 constexpr int kScaleVals = 12;      // reduced values per round (6 per residual slot)
 
-// digamma(float): the reference uses boost::math::digamma on a float argument (src/cuda/device.hpp:76-80),
-// which evaluates in double and rounds to float.  Recurrence to x >= 10, then the asymptotic series.
-__device__ __forceinline__ float digamma_float(float xf)
+// C(nu) = -psi(nu/2) + ln(nu/2) + f + 1 + psi((nu+1)/2) - ln((nu+1)/2)   (sigmaFuncs.cu:966), float arithmetic
+// evaluated left to right.  psi is boost::math::digamma on a float argument (src/cuda/device.hpp:76-80), which
+// evaluates in double and rounds to float.  The bisection of sigmaFuncs.cu:946-1047 only ever evaluates C at
+// nu in {2, 2.5, 3, ..., 10}, so the four nu-dependent terms are tabulated on the host once (17 x 4 floats in
+// constant memory) instead of running a double-precision digamma in every thread every round.
+struct NuTerms { float neg_psi_half, log_half, psi_half1, log_half1; };
+static __constant__ NuTerms c_nu_table[17];  // one copy per translation unit (internal linkage)
+
+static inline double digamma_host(double x)
 {
-  double x = (double)xf, r = 0.0;
+  double r = 0.0;
   while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
   double f = 1.0 / (x * x);
   double t = f * (-1.0 / 12.0 + f * (1.0 / 120.0 + f * (-1.0 / 252.0 + f * (1.0 / 240.0 +
              f * (-1.0 / 132.0 + f * (691.0 / 32760.0 + f * (-1.0 / 12.0)))))));
-  return (float)(r + log(x) - 0.5 / x + t);
+  return r + log(x) - 0.5 / x + t;
 }
 
-// C(nu) of sigmaFuncs.cu:966, float arithmetic evaluated left to right (no re-association, no FMA)
+// Must be called once per translation unit that launches a kernel using c_nu_float (the table has internal
+// linkage, so this function must too).
+static void upload_nu_table()
+{
+  NuTerms h[17];
+  for (int k = 0; k < 17; ++k) {
+    float nu = 2.f + 0.5f * (float)k;
+    float a = nu / 2.f, b = (nu + 1.f) / 2.f;
+    h[k].neg_psi_half = -(float)digamma_host((double)a);
+    h[k].log_half = logf(a);
+    h[k].psi_half1 = (float)digamma_host((double)b);
+    h[k].log_half1 = logf(b);
+  }
+  cudaMemcpyToSymbol(c_nu_table, h, sizeof(h));
+}
+
 __device__ __forceinline__ float c_nu_float(float nu, float fw)
 {
-  float a = __fadd_rn(-digamma_float(nu / 2.f), logf(nu / 2.f));
+  const NuTerms t = c_nu_table[__float2int_rn((nu - 2.f) * 2.f)];
+  float a = __fadd_rn(t.neg_psi_half, t.log_half);
   a = __fadd_rn(a, fw);
   a = __fadd_rn(a, 1.f);
-  a = __fadd_rn(a, digamma_float((nu + 1.f) / 2.f));
-  return __fsub_rn(a, logf((nu + 1.f) / 2.f));
+  a = __fadd_rn(a, t.psi_half1);
+  return __fsub_rn(a, t.log_half1);
 }
 
 enum ScalePhase { PH_IRLS = 0, PH_NU_INIT = 1, PH_NU_BISECT = 2, PH_DONE = 3 };
@@ -172,10 +194,11 @@ __device__ __forceinline__ void scale_rounds(cg::cluster_group& cluster, ScaleSh
       for (int i = tid; i < n_local; i += kScaleThreads) slot_accumulate(s0, samples0[i], acc);
     if (s1.phase != PH_DONE)
       for (int i = tid; i < n_local; i += kScaleThreads) slot_accumulate(s1, samples1[i], acc + 6);
+    // float inside the warp (<= ~10 samples per lane; the reference sums in float throughout), double above
 #pragma unroll
     for (int k = 0; k < kScaleVals; ++k) {
-      double v = warp_sum((double)acc[k]);
-      if (lane == 0) sh.warp_part[wid][k] = v;
+      float v = warp_sum(acc[k]);
+      if (lane == 0) sh.warp_part[wid][k] = (double)v;
     }
     __syncthreads();
     if (tid < kScaleVals) {

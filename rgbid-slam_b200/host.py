@@ -370,9 +370,10 @@ class Aligner:
         t = np.ascontiguousarray(t, dtype=np.float64)
         capi.check(self.lib.rgbid_aligner_enqueue(self.h, _dp(R), _dp(t)), "aligner_enqueue")
 
-    def time_build(self, level=0, reps=20):
+    def time_build(self, level=0, reps=20, scale=False):
         ms = _F(0)
-        capi.check(self.lib.rgbid_aligner_time_build(self.h, level, reps, C.byref(ms)), "aligner_time_build")
+        fn = self.lib.rgbid_aligner_time_scale if scale else self.lib.rgbid_aligner_time_build
+        capi.check(fn(self.h, level, reps, C.byref(ms)), "aligner_time_build")
         return ms.value
 
     def map(self, name, level, index=0):

@@ -1,0 +1,10 @@
+#!/bin/bash
+# Builds kernel variants on the GPU box and times them (tools/bench_build.py).  Usage: tools/variants.sh "<flags1>" "<flags2>" ...
+for v in "$@"; do
+  echo "== variant: [$v]"
+  touch rgbid-slam_b200/csrc/gn_system.cu
+  RGBID_EXTRA_NVCC_FLAGS="$v" python rgbid-slam_b200/build.py > /dev/null 2>&1 || { echo build failed; continue; }
+  grep -A2 "gn_build_kernelILi4ELb0ELb1" rgbid-slam_b200/build/gn_system.cu.o.log | grep -E "Used|spill" | tr '\n' ' '; echo
+  python tools/bench_build.py 32
+  python tools/bench_build.py 1
+done
