@@ -291,6 +291,10 @@ int rgbid_tracker_reset(rgbid_tracker* trk);
  * results_host: batch entries.  Synchronous (the reference's trackNewFrame is). */
 int rgbid_tracker_track(rgbid_tracker* trk, const uint16_t* depth, const uint8_t* rgb, int from_host,
                         rgbid_frame_result* results_host);
+/* Same with pitched DEVICE buffers (what VisodoTracker::depth_ / rgb24_ are: DeviceArray2D, include/visodo.h:118-119):
+ * row pitch and per-stream stride in bytes (stride is ignored when batch == 1). */
+int rgbid_tracker_track_device(rgbid_tracker* trk, const uint16_t* depth, size_t depth_pitch, size_t depth_stride,
+                               const uint8_t* rgb, size_t rgb_pitch, size_t rgb_stride, rgbid_frame_result* results_host);
 /* Integration-keyframe maps of stream `index` (device pointers; pitch in bytes):
  * which: 0 fused inverse depth, 1 fusion weight, 2 raw inverse depth, 3 vertex map (3*rows), 4 normal map
  * (3*rows) */

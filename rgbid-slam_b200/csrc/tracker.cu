@@ -203,10 +203,27 @@ int rgbid_tracker_overlap_mask(rgbid_tracker* t, int index, uint8_t** ptr, size_
   return RGBID_OK;
 }
 
+static int track_core(rgbid_tracker* t, const uint16_t* depth, const uint8_t* rgb, int from_host, size_t in_dpitch,
+                      size_t in_dstride, size_t in_cpitch, size_t in_cstride, rgbid_frame_result* results);
+
 int rgbid_tracker_track(rgbid_tracker* t, const uint16_t* depth, const uint8_t* rgb, int from_host,
                         rgbid_frame_result* results)
 {
   if (!t || !depth || !rgb || !results) return RGBID_ERR_ARG;
+  const size_t rows = t->al->cfg.rows, cols = t->al->cfg.cols;
+  return track_core(t, depth, rgb, from_host, cols * 2, rows * cols * 2, cols * 3, rows * cols * 3, results);
+}
+
+int rgbid_tracker_track_device(rgbid_tracker* t, const uint16_t* depth, size_t depth_pitch, size_t depth_stride,
+                               const uint8_t* rgb, size_t rgb_pitch, size_t rgb_stride, rgbid_frame_result* results)
+{
+  if (!t || !depth || !rgb || !results) return RGBID_ERR_ARG;
+  return track_core(t, depth, rgb, 0, depth_pitch, depth_stride, rgb_pitch, rgb_stride, results);
+}
+
+static int track_core(rgbid_tracker* t, const uint16_t* depth, const uint8_t* rgb, int from_host, size_t in_dpitch,
+                      size_t in_dstride, size_t in_cpitch, size_t in_cstride, rgbid_frame_result* results)
+{
   rgbid_aligner* al = t->al;
   rgbid_ctx* ctx = t->ctx;
   const rgbid_align_config& c = al->cfg;
@@ -219,8 +236,9 @@ int rgbid_tracker_track(rgbid_tracker* t, const uint16_t* depth, const uint8_t* 
   // ---- prepareImages (src/visodo.cpp:760-773): ingest + pyramid for all streams --------------------------
   const uint16_t* d_depth = depth;
   const uint8_t* d_rgb = rgb;
-  size_t dstride = dsz, cstride = csz;
+  size_t dstride = in_dstride, cstride = in_cstride, dpitch = in_dpitch, cpitch = in_cpitch;
   if (from_host) {
+    dpitch = (size_t)cols * 2; cpitch = (size_t)cols * 3;
     size_t raw_depth = align_up(dsz, 256), raw_rgb = align_up(csz, 256);
     if (raw_depth == dsz && raw_rgb == csz) {
       RGBID_CUDA_TRY(cudaMemcpyAsync(al->d_depth_raw, depth, dsz * B, cudaMemcpyHostToDevice, s));
@@ -233,7 +251,7 @@ int rgbid_tracker_track(rgbid_tracker* t, const uint16_t* depth, const uint8_t* 
     }
     d_depth = al->d_depth_raw; d_rgb = al->d_rgb_raw; dstride = raw_depth; cstride = raw_rgb;
   }
-  launch_ingest(L, d_depth, (size_t)cols * 2, dstride, d_rgb, (size_t)cols * 3, cstride, al->maps[MAP_W_CUR][0],
+  launch_ingest(L, d_depth, dpitch, dstride, d_rgb, cpitch, cstride, al->maps[MAP_W_CUR][0],
                 al->maps[MAP_I_CUR][0], B, c.factor_depth);
   aligner_current_pyramid(al, 0, B);
 
@@ -243,7 +261,8 @@ int rgbid_tracker_track(rgbid_tracker* t, const uint16_t* depth, const uint8_t* 
     aligner_keyframe_derivatives(al, 0, B, nullptr, false);
     save_integration_keyframes(t, nullptr);
     for (int b = 0; b < B; ++b)
-      RGBID_CUDA_TRY(cudaMemcpyAsync(t->d_colors + t->colors_sstride * b, (const char*)d_rgb + cstride * b, csz, cudaMemcpyDeviceToDevice, s));
+      RGBID_CUDA_TRY(cudaMemcpy2DAsync(t->d_colors + t->colors_sstride * b, (size_t)cols * 3, (const char*)d_rgb + cstride * b,
+                                       cpitch, (size_t)cols * 3, rows, cudaMemcpyDeviceToDevice, s));
     refresh_integration_maps(t);
     launch_fill_u8(L, t->d_mask, t->mask_pitch, t->mask_sstride, rows, cols, 0, B);
     RGBID_CUDA_TRY(cudaStreamSynchronize(s));
@@ -398,7 +417,8 @@ int rgbid_tracker_track(rgbid_tracker* t, const uint16_t* depth, const uint8_t* 
     save_integration_keyframes(t, t->d_flags + 1 * B);
     for (int b = 0; b < B; ++b)
       if (t->h_flags[1 * B + b])
-        RGBID_CUDA_TRY(cudaMemcpyAsync(t->d_colors + t->colors_sstride * b, (const char*)d_rgb + cstride * b, csz, cudaMemcpyDeviceToDevice, s));
+        RGBID_CUDA_TRY(cudaMemcpy2DAsync(t->d_colors + t->colors_sstride * b, (size_t)cols * 3, (const char*)d_rgb + cstride * b,
+                                         cpitch, (size_t)cols * 3, rows, cudaMemcpyDeviceToDevice, s));
   }
   if (any_fuse) {
     // integrateImagesIntoKeyframes (:1674-1764): K6 + K7 fused; transform = integrKF->cur (h_proj[3])

@@ -1,0 +1,286 @@
+// visodo.hpp -- RGBID_SLAM::VisodoTracker and RGBID_SLAM::KeyframeAlign with the reference's entry points
+// (include/visodo.h:47-135, include/keyframe_align.h:40-54) on top of the C ABI.  The per-frame state machine,
+// the Gauss-Newton loop and all kernels live in librgbid_b200.so (csrc/tracker.cu, aligner.cu); these classes own
+// the configuration surface the application touches: constructor arguments, the [VISODO] INI keys
+// (src/visodo.cpp:321-435), the calibration file ([CALIBRATION] | [RGB_CALIBRATION], src/visodo.cpp:99-180), the
+// public device input buffers rgb24_ / depth_, and the pose accessors.
+//
+// Eigen is not available in this image, so poses are returned as plain row-major structs (Affine3) instead of
+// Eigen::Affine3f / Affine3d; everything else keeps the reference's names.  Header-only.
+#pragma once
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/rgbid_b200/internal.hpp"
+#include "settings.hpp"
+
+namespace RGBID_SLAM {
+
+struct PixelRGB { unsigned char r, g, b; };  // include/types.h:88-91
+typedef DeviceArray2D<PixelRGB> View;
+typedef DeviceArray2D<unsigned short> DepthMap;
+
+/** Rigid transform, row-major: X_world = R X_cam + t */
+struct Affine3 {
+  double R[9];
+  double t[3];
+  Affine3() { for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0; t[0] = t[1] = t[2] = 0.0; }
+};
+
+class VisodoTracker {
+ public:
+  enum { LEVELS = 3 };  // include/visodo.h:52; `levels` below generalises it (4 for the 4-level benchmark)
+
+  VisodoTracker(int optim_dim = 6, int Mestimator = device::DEFAULT_MESTIMATOR,
+                int motion_model = device::DEFAULT_MOTION_MODEL, int sigma_estimator = device::SIGMA_PDF,
+                int weighting = device::DEFAULT_WEIGHTING, int warping = device::PYR_FIRST,
+                int max_odoKF_count = device::DEFAULT_ODO_KF_COUNT, int finest_level = 0,
+                int termination = device::DEFAULT_TERMINATION, float visratio_odo = device::DEFAULT_VISRATIO_ODO,
+                int image_filtering = device::DEFAULT_IMAGE_FILTERING, float visratio_integr = device::DEFAULT_VISRATIO_INTEGR,
+                int max_integrKF_count = device::DEFAULT_INTEGR_KF_COUNT, int Nsamples = 10000, int rows = 480,
+                int cols = 640, int levels = LEVELS)
+      : rows_(rows), cols_(cols), levels_(levels), optim_dim_(optim_dim), Mestimator_(Mestimator),
+        motion_model_(motion_model), sigma_estimator_(sigma_estimator), weighting_(weighting), warping_(warping),
+        max_odoKF_count_(max_odoKF_count), finest_level_(finest_level), termination_(termination),
+        visibility_ratio_odo_threshold_(visratio_odo), image_filtering_(image_filtering),
+        visibility_ratio_integr_threshold_(visratio_integr), max_integrKF_count_(max_integrKF_count),
+        Nsamples_(Nsamples), trk_(nullptr), lost_(false), global_time_(0)
+  {
+    if (optim_dim != 6) throw std::invalid_argument("only the 6-DoF optimisation of the reference is implemented");
+    if (warping != device::PYR_FIRST)
+      std::cerr << "VisodoTracker: WARP_ORDER warpFirst is not implemented on this path; using pyrFirst "
+                   "(the shipped configuration, config_data/visodoRGBDconfig.ini:9)" << std::endl;
+    if (termination != device::ALL_ITERS)
+      std::cerr << "VisodoTracker: CHI_SQUARED early termination is not implemented; using ALL_ITERS (the default)" << std::endl;
+    setRGBIntrinsics(device::FOCAL_LENGTH, device::FOCAL_LENGTH, device::CENTER_X, device::CENTER_Y);
+    factor_depth_ = 1.f;
+    compute_deltat_flag_ = false;
+    real_time_flag_ = false;
+    const int iters[] = {10, 5, 3, 0, 0, 0, 0, 0};  // src/visodo.cpp:65
+    for (int i = 0; i < RGBID_MAX_LEVELS; ++i) visodo_iterations_[i] = i < levels_ ? iters[i] : 0;
+    rgb24_.create(rows_, cols_);
+    depth_.create(rows_, cols_);
+  }
+
+  ~VisodoTracker() { if (trk_) rgbid_tracker_destroy(trk_); }
+
+  /** [VISODO] keys of the reference (src/visodo.cpp:321-435) */
+  void loadSettings(Settings& settings)
+  {
+    Section s;
+    if (!settings.getSection("VISODO", s)) return;
+    Entry e;
+    if (s.getEntry("M_ESTIMATOR", e)) {
+      const std::string v = e.getValue();
+      if (v == "Student") Mestimator_ = device::STUDENT;
+      if (v == "LeastSquares") Mestimator_ = device::LSQ;
+      if (v == "Tukey") Mestimator_ = device::TUKEY;
+      if (v == "Huber") Mestimator_ = device::HUBER;
+    }
+    if (s.getEntry("MOTION_MODEL", e)) {
+      if (e.getValue() == "none") motion_model_ = device::NO_MM;
+      if (e.getValue() == "constVelocity") motion_model_ = device::CONSTANT_VELOCITY;
+    }
+    if (s.getEntry("WARP_ORDER", e)) {
+      if (e.getValue() == "warpFirst") warping_ = device::WARP_FIRST;
+      if (e.getValue() == "pyrFirst") warping_ = device::PYR_FIRST;
+    }
+    if (s.getEntry("IMAGE_FILTERING", e)) {
+      if (e.getValue() == "none") image_filtering_ = device::NO_FILTERS;
+      if (e.getValue() == "gradients") image_filtering_ = device::FILTER_GRADS;
+    }
+    if (s.getEntry("SIGMA_ESTIMATOR", e)) {
+      if (e.getValue() == "sigmaMAD") sigma_estimator_ = device::SIGMA_MAD;
+      if (e.getValue() == "sigmaML") sigma_estimator_ = device::SIGMA_PDF;
+      if (e.getValue() == "sigmaConst") sigma_estimator_ = device::SIGMA_CONS;
+    }
+    if (s.getEntry("INTEGRATION_VISRATIO_THRESHOLD", e)) visibility_ratio_integr_threshold_ = (float)atof(e.getValue().c_str());
+    if (s.getEntry("ODOMETRY_VISRATIO_THRESHOLD", e)) visibility_ratio_odo_threshold_ = (float)atof(e.getValue().c_str());
+    if (s.getEntry("FINEST_PYR_LEVEL", e)) finest_level_ = (int)atof(e.getValue().c_str());
+  }
+
+  /** [CALIBRATION] | [RGB_CALIBRATION]: fx fy cx cy kd factor_depth (src/visodo.cpp:99-180) */
+  void loadCalibration(const std::string& calib_file)
+  {
+    std::ifstream f(calib_file.c_str());
+    if (!f.is_open()) { std::cout << "Could not open configuration file " << calib_file << std::endl; return; }
+    Settings settings(f);
+    Section c;
+    if (!(settings.getSection("CALIBRATION", c) || settings.getSection("RGB_CALIBRATION", c))) return;
+    Entry e;
+    if (c.getEntry("fx", e)) fx_ = (float)atof(e.getValue().c_str());
+    if (c.getEntry("fy", e)) fy_ = (float)atof(e.getValue().c_str());
+    if (c.getEntry("cx", e)) cx_ = (float)atof(e.getValue().c_str());
+    if (c.getEntry("cy", e)) cy_ = (float)atof(e.getValue().c_str());
+    if (c.getEntry("factor_depth", e)) factor_depth_ = (float)atof(e.getValue().c_str());
+  }
+
+  void setRGBIntrinsics(float fx, float fy, float cx = -1, float cy = -1, float = 0.f, float = 0.f, float = 0.f,
+                        float = 0.f, float = 0.f)
+  {
+    fx_ = fx; fy_ = fy;
+    cx_ = (cx == -1) ? cols_ / 2 - 0.5f : cx;
+    cy_ = (cy == -1) ? rows_ / 2 - 0.5f : cy;
+  }
+
+  int cols() { return cols_; }
+  int rows() { return rows_; }
+  bool visOdoIsLost() { return lost_; }
+  size_t getNumberOfPoses() const { return poses_.size(); }
+
+  /** Process the frame held in rgb24_ / depth_ (device buffers, as filled by the application's grabber thread,
+      tools/RGBID_SLAMapp.cpp:144-214).  Returns false for the first frame and when tracking is lost, like the
+      reference. */
+  bool trackNewFrame()
+  {
+    ensure_created();
+    rgbid_frame_result r;
+    int rc = rgbid_tracker_track_device(trk_, depth_.ptr(), depth_.step(), 0, (const uint8_t*)rgb24_.ptr(), rgb24_.step(), 0, &r);
+    if (rc != RGBID_OK) throw std::runtime_error(std::string("rgbid_tracker_track: ") + rgbid_status_string(rc));
+    last_ = r;
+    lost_ = (r.status != RGBID_OK);
+    Affine3 p;
+    std::memcpy(p.R, r.R, sizeof(p.R));
+    std::memcpy(p.t, r.t, sizeof(p.t));
+    poses_.push_back(p);
+    vis_odo_times_.push_back(0.f);
+    const bool first = (global_time_ == 0);
+    ++global_time_;
+    return !first && !lost_;
+  }
+
+  /** Camera-to-world pose of frame `time` (-1: latest) */
+  Affine3 getCameraPose(int time = -1) const
+  {
+    if (poses_.empty()) return Affine3();
+    if (time > (int)poses_.size() || time < 0) time = (int)poses_.size() - 1;
+    return poses_[time];
+  }
+
+  const rgbid_frame_result& lastResult() const { return last_; }
+  rgbid_tracker* handle() { ensure_created(); return trk_; }
+
+  void reset()
+  {
+    poses_.clear();
+    global_time_ = 0;
+    lost_ = false;
+    if (trk_) rgbid_tracker_reset(trk_);
+  }
+
+  // public inputs of the reference (include/visodo.h:118-119)
+  View rgb24_;
+  DepthMap depth_;
+  uint64_t timestamp_rgb_curr_ = 0, timestamp_depth_curr_ = 0, timestamp_ini_ = 0;
+  bool compute_deltat_flag_, real_time_flag_;
+  int visodo_iterations_[RGBID_MAX_LEVELS];
+
+ private:
+  void ensure_created()
+  {
+    if (trk_) return;
+    rgbid_tracker_config c;
+    std::memset(&c, 0, sizeof(c));
+    c.align.rows = rows_; c.align.cols = cols_; c.align.levels = levels_; c.align.finest_level = finest_level_;
+    for (int i = 0; i < RGBID_MAX_LEVELS; ++i) c.align.iterations[i] = visodo_iterations_[i];
+    if (real_time_flag_) c.align.iterations[0] = 5;  // src/visodo.cpp:961-964
+    c.align.batch = 1; c.align.mode = RGBID_MODE_TRACKER;
+    c.align.mestimator = Mestimator_; c.align.weighting = weighting_;
+    // SIGMA_MAD parses but has no implementation in the reference: it falls through to the constants
+    c.align.sigma_estimator = (sigma_estimator_ == device::SIGMA_PDF) ? RGBID_SIGMA_PDF : RGBID_SIGMA_CONS;
+    c.align.nsamples = Nsamples_;
+    c.align.fx = fx_; c.align.fy = fy_; c.align.cx = cx_; c.align.cy = cy_;
+    c.align.factor_depth = factor_depth_;
+    c.motion_model = motion_model_;
+    c.visratio_odo = visibility_ratio_odo_threshold_; c.visratio_integr = visibility_ratio_integr_threshold_;
+    c.max_odo_kf_count = max_odoKF_count_; c.max_integr_kf_count = max_integrKF_count_;
+    c.image_filtering = image_filtering_;
+    c.delta_t = 0.03333f;  // computeInterframeTime in evaluation mode, src/visodo.cpp:1932
+    int rc = rgbid_tracker_create(device::thread_context().ctx, &c, &trk_);
+    if (rc != RGBID_OK) throw std::runtime_error(std::string("rgbid_tracker_create: ") + rgbid_status_string(rc));
+  }
+
+  int rows_, cols_, levels_, optim_dim_, Mestimator_, motion_model_, sigma_estimator_, weighting_, warping_;
+  int max_odoKF_count_, finest_level_, termination_;
+  float visibility_ratio_odo_threshold_;
+  int image_filtering_;
+  float visibility_ratio_integr_threshold_;
+  int max_integrKF_count_, Nsamples_;
+  float fx_, fy_, cx_, cy_, factor_depth_;
+  rgbid_tracker* trk_;
+  bool lost_;
+  int global_time_;
+  rgbid_frame_result last_;
+  std::vector<Affine3> poses_;
+  std::vector<float> vis_odo_times_;
+};
+
+/** The three fields of the reference's Keyframe that KeyframeAlign reads (src/keyframe_align.cpp:119-129):
+    K_, depthinv_image_ (CV_32F) and grey_image_ (CV_8U), as plain host pointers (OpenCV is not available). */
+struct KeyframeView {
+  int rows, cols;
+  double K[9];              // row-major 3x3
+  const float* depthinv;    // rows x cols, dense
+  const unsigned char* grey;  // rows x cols, dense
+};
+
+class KeyframeAlign {
+ public:
+  enum { LEVELS = 4 };  // include/keyframe_align.h:50
+
+  KeyframeAlign() : al_(nullptr), rows_(0), cols_(0) {}
+  ~KeyframeAlign() { if (al_) rgbid_aligner_destroy(al_); }
+
+  /** alignKeyframes(kf_ini, kf_end, rotation_ini2end, translation_ini2end, covariance_ini2end)
+      (include/keyframe_align.h:52-54; src/keyframe_align.cpp:115-357).  R (row-major 3x3) and t hold the initial
+      guess on entry (from the loop closer's RANSAC) and the refined pose on return; cov is 6x6 row-major. */
+  bool alignKeyframes(const KeyframeView& kf_ini, const KeyframeView& kf_end, double* R, double* t, double* cov)
+  {
+    if (!al_ || kf_ini.rows != rows_ || kf_ini.cols != cols_ || kf_ini.K[0] != K_[0] || kf_ini.K[2] != K_[2]) create(kf_ini);
+    grey_f_.resize((size_t)rows_ * cols_);
+    const size_t pitch = (size_t)cols_ * sizeof(float);
+    for (size_t i = 0; i < grey_f_.size(); ++i) grey_f_[i] = (float)kf_ini.grey[i];  // cv::Mat::convertTo(CV_32F)
+    check(rgbid_aligner_set_keyframe(al_, 0, kf_ini.depthinv, pitch, grey_f_.data(), pitch, 1));
+    check(rgbid_ctx_sync(device::thread_context().ctx));
+    for (size_t i = 0; i < grey_f_.size(); ++i) grey_f_[i] = (float)kf_end.grey[i];
+    check(rgbid_aligner_set_current(al_, 0, kf_end.depthinv, pitch, grey_f_.data(), pitch, 1));
+    int status = 0;
+    check(rgbid_aligner_run(al_, R, t, cov, &status, nullptr));
+    return true;  // the reference returns true unconditionally (src/keyframe_align.cpp:356)
+  }
+
+ private:
+  static void check(int rc)
+  {
+    if (rc != RGBID_OK) throw std::runtime_error(std::string("KeyframeAlign: ") + rgbid_status_string(rc));
+  }
+  void create(const KeyframeView& kf)
+  {
+    if (al_) { rgbid_aligner_destroy(al_); al_ = nullptr; }
+    rows_ = kf.rows; cols_ = kf.cols;
+    std::memcpy(K_, kf.K, sizeof(K_));
+    rgbid_align_config c;
+    std::memset(&c, 0, sizeof(c));
+    c.rows = rows_; c.cols = cols_; c.levels = LEVELS; c.finest_level = 0;
+    const int iters[] = {5, 5, 3, 0};  // src/keyframe_align.cpp:44
+    for (int i = 0; i < LEVELS; ++i) c.iterations[i] = iters[i];
+    c.batch = 1; c.mode = RGBID_MODE_ALIGN; c.mestimator = RGBID_STUDENT; c.weighting = RGBID_INDEPENDENT;
+    c.nsamples = 19200;  // src/keyframe_align.cpp:247-248
+    c.fx = (float)kf.K[0]; c.fy = (float)kf.K[4]; c.cx = (float)kf.K[2]; c.cy = (float)kf.K[5];
+    c.factor_depth = 1.f;
+    check(rgbid_aligner_create(device::thread_context().ctx, &c, &al_));
+  }
+  rgbid_aligner* al_;
+  int rows_, cols_;
+  double K_[9];
+  std::vector<float> grey_f_;
+};
+
+}  // namespace RGBID_SLAM
