@@ -101,6 +101,22 @@ def shard_streams(total_streams, world, rank):
     return [s for s in range(total_streams) if s % world == rank]
 
 
+def gather_systems(local_sys, world, out=None):
+    """All-gather of the per-stream results ([streams, 48] float64: 6x6 system/covariance, R, t) across ranks --
+    the one exchange step of the batched mode.  NCCL on the GPU, gloo in the CPU tests."""
+    import torch.distributed as dist
+    if out is None:
+        out = torch.empty((world * local_sys.shape[0],) + tuple(local_sys.shape[1:]), dtype=local_sys.dtype,
+                          device=local_sys.device)
+    if dist.get_backend() == "gloo":
+        parts = [torch.empty_like(local_sys) for _ in range(world)]
+        dist.all_gather(parts, local_sys)
+        out.copy_(torch.cat(parts, 0))
+    else:
+        dist.all_gather_into_tensor(out, local_sys)
+    return out
+
+
 def make_frames(args, stream_ids, n_frames, device):
     """[n_frames, S, rows, cols] uint16 depth and [n_frames, S, rows, cols, 3] uint8 RGB, rendered on `device`."""
     from rgbid_slam_b200 import synth
@@ -141,7 +157,7 @@ def run_b200(args, world, rank, local):
             arr = np.array([list(r.cov) + list(r.R) + list(r.t) for r in results], dtype=np.float64)
             with torch.cuda.stream(side):
                 local_sys.copy_(torch.from_numpy(arr), non_blocking=True)
-                dist.all_gather_into_tensor(all_sys, local_sys)
+                gather_systems(local_sys, world, all_sys)
 
     def barrier():
         if world > 1:
