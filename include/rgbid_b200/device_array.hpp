@@ -4,7 +4,9 @@
 // (src/visodo.cpp, src/keyframe_align.cpp) compiles unchanged.  Header-only; written from scratch on the CUDA
 // runtime.  Differences: errors throw std::runtime_error instead of calling exit(0)
 // (ThirdParty/pcl_gpu_containers/src/error.cpp:42-46), and copies are issued on the legacy default stream only
-// when no stream is given (upload/download stay synchronous, as in the reference).
+// when no stream is given; every copy is followed by cudaStreamSynchronize(0) as in the reference
+// (ThirdParty/pcl_gpu_containers/src/device_memory.cpp:284-307): a pageable-memory cudaMemcpy may return before the DMA
+// has landed and a device-to-device one is asynchronous, and the kernels run on a non-blocking stream.
 #pragma once
 #include <cuda_runtime.h>
 #include <cstddef>
@@ -92,10 +94,10 @@ class DeviceMemory {
   {
     if (empty()) { other.release(); return; }
     other.create(sizeBytes_);
-    cudaSafeCall(cudaMemcpy(other.data_, data_, sizeBytes_, cudaMemcpyDeviceToDevice));
+    cudaSafeCall(cudaMemcpy(other.data_, data_, sizeBytes_, cudaMemcpyDeviceToDevice)); cudaSafeCall(cudaStreamSynchronize(0));
   }
-  void upload(const void* host, size_t bytes) { create(bytes); cudaSafeCall(cudaMemcpy(data_, host, bytes, cudaMemcpyHostToDevice)); }
-  void download(void* host) const { cudaSafeCall(cudaMemcpy(host, data_, sizeBytes_, cudaMemcpyDeviceToHost)); }
+  void upload(const void* host, size_t bytes) { create(bytes); cudaSafeCall(cudaMemcpy(data_, host, bytes, cudaMemcpyHostToDevice)); cudaSafeCall(cudaStreamSynchronize(0)); }
+  void download(void* host) const { cudaSafeCall(cudaMemcpy(host, data_, sizeBytes_, cudaMemcpyDeviceToHost)); cudaSafeCall(cudaStreamSynchronize(0)); }
   void swap(DeviceMemory& o) { std::swap(data_, o.data_); std::swap(sizeBytes_, o.sizeBytes_); std::swap(refcount_, o.refcount_); }
   template <class T> T* ptr() { return (T*)data_; }
   template <class T> const T* ptr() const { return (const T*)data_; }
@@ -145,16 +147,16 @@ class DeviceMemory2D {
   {
     if (empty()) { other.release(); return; }
     other.create(rows_, colsBytes_);
-    cudaSafeCall(cudaMemcpy2D(other.data_, other.step_, data_, step_, colsBytes_, rows_, cudaMemcpyDeviceToDevice));
+    cudaSafeCall(cudaMemcpy2D(other.data_, other.step_, data_, step_, colsBytes_, rows_, cudaMemcpyDeviceToDevice)); cudaSafeCall(cudaStreamSynchronize(0));
   }
   void upload(const void* host, size_t hostStep, int rows, int colsBytes)
   {
     create(rows, colsBytes);
-    cudaSafeCall(cudaMemcpy2D(data_, step_, host, hostStep, colsBytes_, rows_, cudaMemcpyHostToDevice));
+    cudaSafeCall(cudaMemcpy2D(data_, step_, host, hostStep, colsBytes_, rows_, cudaMemcpyHostToDevice)); cudaSafeCall(cudaStreamSynchronize(0));
   }
   void download(void* host, size_t hostStep) const
   {
-    cudaSafeCall(cudaMemcpy2D(host, hostStep, data_, step_, colsBytes_, rows_, cudaMemcpyDeviceToHost));
+    cudaSafeCall(cudaMemcpy2D(host, hostStep, data_, step_, colsBytes_, rows_, cudaMemcpyDeviceToHost)); cudaSafeCall(cudaStreamSynchronize(0));
   }
   void swap(DeviceMemory2D& o)
   {

@@ -101,6 +101,7 @@ static GnLevelMaps level_maps(const rgbid_aligner* al, int level, bool cov_gradi
   const int B = al->cfg.batch;
   M.texW = al->use_tex ? al->d_tex + (size_t)(level * 2 + 0) * B : nullptr;
   M.texI = al->use_tex ? al->d_tex + (size_t)(level * 2 + 1) * B : nullptr;
+  M.tex_border = al->use_tex ? 1 : 0;
   return M;
 }
 
@@ -242,7 +243,10 @@ int rgbid_aligner_create(rgbid_ctx* ctx, const rgbid_align_config* cfg, rgbid_al
           cudaTextureDesc td;
           memset(&td, 0, sizeof(td));
           td.readMode = cudaReadModeElementType;
-          td.addressMode[0] = cudaAddressModeClamp; td.addressMode[1] = cudaAddressModeClamp;
+          // inverse depth: border addressing (0 outside the image; every user either tests in-image first, as
+          // the reference does, or relies on the reference's own `res > 0` test); intensity: clamp as in the
+          // reference (the bilinear footprint may touch the clamped edge)
+          td.addressMode[0] = td.addressMode[1] = (which == 0) ? cudaAddressModeBorder : cudaAddressModeClamp;
           td.filterMode = which == 0 ? cudaFilterModePoint : cudaFilterModeLinear;
           td.normalizedCoords = 0;
           e = cudaCreateTextureObject(&al->h_tex[(size_t)(l * 2 + which) * B + b], &rd, &td, nullptr);

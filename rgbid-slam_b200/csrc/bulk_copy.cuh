@@ -1,0 +1,101 @@
+// bulk_copy.cuh -- sm_100a asynchronous bulk copies (TMA engine, SASS: UBLKCP) with mbarrier completion, and the
+// packed-FP32 (f32x2) arithmetic used by the fused Gauss-Newton kernel.
+//
+// The keyframe maps are flat fp32 arrays (pitch == cols * 4), so a warp's slice of a tile is one contiguous
+// 512-byte segment per map: a 1-D bulk copy needs no tensor map and is issued by a single lane.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rgbid {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_fence_init()
+{
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+// global -> shared bulk copy; bytes, both addresses multiples of 16
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MBAR_DONE;\n"
+      "bra MBAR_WAIT;\n"
+      "MBAR_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
+// true in exactly one lane of a converged warp (the compiler then knows a single thread issues the bulk copies)
+__device__ __forceinline__ bool elect_one()
+{
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// ---- packed FP32 pairs (FFMA2 / FMUL2: one issue slot for two lanes of the FMA pipe) -------------------------
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
+{
+  f32x2 r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi)
+{
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// d += a * b where flag != 0 (predicated, not branched: invalid pixels carry NaN operands that must not be
+// accumulated, and a branch per pixel and constraint would serialise the four pixels of a thread)
+__device__ __forceinline__ void pfma2(f32x2& d, f32x2 a, f32x2 b, int flag)
+{
+  asm("{\n.reg .pred p;\nsetp.ne.s32 p, %3, 0;\n@p fma.rn.f32x2 %0, %1, %2, %0;\n}" : "+l"(d) : "l"(a), "l"(b), "r"(flag));
+}
+
+__device__ __forceinline__ void pfma(float& d, float a, float b, int flag)
+{
+  asm("{\n.reg .pred p;\nsetp.ne.s32 p, %3, 0;\n@p fma.rn.f32 %0, %1, %2, %0;\n}" : "+f"(d) : "f"(a), "f"(b), "r"(flag));
+}
+
+}  // namespace rgbid

@@ -17,7 +17,9 @@
 //
 // Algorithmic HBM bytes: 32 B per keyframe pixel per iteration (6 keyframe maps + 2 current-frame maps,
 // fp32); this kernel is bandwidth bound (about 5 flop/B), tensor cores do not apply.
+#include <cstdlib>
 #include "scale_core.cuh"
+#include "bulk_copy.cuh"
 
 namespace rgbid {
 
@@ -357,6 +359,307 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// gn_build_fast_kernel: the shipped configuration (Student-t weights, INDEPENDENT weighting, texture gathers, flat
+// keyframe maps) of gn_build_kernel, rebuilt around the measured limits of the B200 SM (tools/ubench/pipes.cu):
+// FP32 FMA-pipe instructions issue at ~0.9 / clk / SMSP, ALU-pipe instructions (compares, selects, min/max,
+// integer) at half that, so the kernel is bound by instruction issue long before DRAM unless the per-pixel
+// instruction count is cut.  What it does differently from the generic kernel:
+//   * the six keyframe maps arrive through the TMA engine: each warp owns a ring of kFastStages x 6 x 512 B
+//     shared-memory slots, one lane issues 1-D bulk copies (cp.async.bulk, SASS UBLKCP) two chunks ahead and the
+//     warp waits on an mbarrier -- no CTA-wide barrier in the loop, no staging registers, DRAM latency hidden;
+//   * the projection is factored as  K R K^-1 (x, y, 1)^T / w + K t : the pixel-dependent part is computed once and
+//     reused by the second projection of tracker mode (2 FMAs per coordinate instead of 5);
+//   * the inverse-depth texture uses border addressing (0 outside), so "outside the image" falls out of the
+//     reference's own `res > 0` test and only the intensity fetch needs an explicit in-image test, done as two
+//     |fma| < 1 compares; validity is carried by NaN propagation into the weight and ONE compare per constraint;
+//   * the 2 x 27 accumulations are predicated packed FMAs (fma.rn.f32x2, SASS FFMA2): 15 + 3 issue slots per
+//     constraint instead of 27 + 6, free operand swaps / broadcasts.
+// Arithmetic differs from the generic kernel only in rounding (same formulas re-associated); the parity tests
+// hold both against the oracle and the reference's own kernels.
+// ------------------------------------------------------------------------------------------------------------
+#ifndef RGBID_FAST_STAGES
+#define RGBID_FAST_STAGES 3
+#endif
+#ifndef RGBID_ACC2
+#define RGBID_ACC2 1
+#endif
+constexpr int kFastStages = RGBID_FAST_STAGES;
+constexpr int kChunkPx = 128;                   // one warp-chunk: 4 pixels per lane
+constexpr int kChunkBytes = kChunkPx * 4;       // per map
+constexpr int kStageBytes = 6 * kChunkBytes;    // 3 KiB per warp and stage
+constexpr int kFastSmemBytes = kBuildWarps * kFastStages * kStageBytes;
+
+struct FastGeom {
+  int npx;        // rows * cols
+  int nchunks;    // ceil(npx / 128)
+  float colsf, inv_cols;
+  float inv_hx, inv_hy;  // 2 / cols, 2 / rows
+};
+
+// the 27 sums in the reference's order from the 15 packed accumulators (see accumulate_packed)
+__device__ __forceinline__ void unpack_acc(const f32x2* a2, float* acc)
+{
+  float lo[15], hi[15];
+#pragma unroll
+  for (int k = 0; k < 15; ++k) unpack2(a2[k], lo[k], hi[k]);
+  // row 0: 00 01 02 03 04 05 0e
+  acc[0] = lo[0]; acc[1] = lo[1]; acc[2] = lo[2]; acc[3] = lo[3]; acc[4] = lo[4]; acc[5] = lo[5]; acc[6] = lo[12];
+  // row 1: 11 12 13 14 15 1e
+  acc[7] = hi[0]; acc[8] = hi[3]; acc[9] = hi[2]; acc[10] = hi[5]; acc[11] = hi[4]; acc[12] = hi[12];
+  // row 2: 22 23 24 25 2e
+  acc[13] = lo[6]; acc[14] = lo[7]; acc[15] = lo[8]; acc[16] = lo[9]; acc[17] = lo[13];
+  // row 3: 33 34 35 3e
+  acc[18] = hi[6]; acc[19] = hi[9]; acc[20] = hi[8]; acc[21] = hi[13];
+  // row 4: 44 45 4e ; row 5: 55 5e
+  acc[22] = lo[10]; acc[23] = lo[11]; acc[24] = lo[14];
+  acc[25] = hi[10]; acc[26] = hi[14];
+}
+
+// acc2 += s * (r, e) (r, e)^T restricted to the 27 needed terms; rows as pairs A = (r0, r1), B = (r2, r3),
+// C = (r4, r5).  Cross products of two different pairs fill both lanes (X * Y and X * swap(Y)); the three
+// within-pair products waste one lane each.
+__device__ __forceinline__ void accumulate_packed(f32x2* a2, float s, float r0, float r1, float r2, float r3, float r4,
+                                                  float r5, float e, int flag)
+{
+  const f32x2 A = pack2(r0, r1), B = pack2(r2, r3), C = pack2(r4, r5);
+  const f32x2 As = pack2(r1, r0), Bs = pack2(r3, r2), Cs = pack2(r5, r4);
+  const f32x2 S = pack2(s, s), E = pack2(e, e);
+  const f32x2 sA = mul2(S, A), sB = mul2(S, B), sC = mul2(S, C);
+  pfma2(a2[0], sA, A, flag);   pfma2(a2[1], sA, As, flag);
+  pfma2(a2[2], sA, B, flag);   pfma2(a2[3], sA, Bs, flag);
+  pfma2(a2[4], sA, C, flag);   pfma2(a2[5], sA, Cs, flag);
+  pfma2(a2[6], sB, B, flag);   pfma2(a2[7], sB, Bs, flag);
+  pfma2(a2[8], sB, C, flag);   pfma2(a2[9], sB, Cs, flag);
+  pfma2(a2[10], sC, C, flag);  pfma2(a2[11], sC, Cs, flag);
+  pfma2(a2[12], sA, E, flag);  pfma2(a2[13], sB, E, flag);  pfma2(a2[14], sC, E, flag);
+}
+
+__device__ __forceinline__ void accumulate_scalar(float* acc, float s, const float* r, float e, int flag)
+{
+  int shift = 0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const float si = s * r[i];
+#pragma unroll
+    for (int j = i; j < 6; ++j) { pfma(acc[shift], si, r[j], flag); ++shift; }
+    pfma(acc[shift], si, e, flag); ++shift;
+  }
+}
+
+template <bool TRACKER, bool CHI>
+__global__ void __launch_bounds__(kBuildThreads, 2)
+    gn_build_fast_kernel(const GnLevelMaps M, const GnParams P, const FastGeom G, GnState* __restrict__ states,
+                         const ScaleState* __restrict__ scales, double* __restrict__ partials, int partial_stride,
+                         unsigned int* __restrict__ counters, rgbid_iter_trace* __restrict__ trace)
+{
+  constexpr int NACC = CHI ? kAccChi : kAcc;
+  extern __shared__ __align__(128) unsigned char ring[];
+  __shared__ BuildShared sh;
+  __shared__ __align__(8) unsigned long long bars[kBuildWarps * kFastStages];
+  const int b = blockIdx.y;
+  GnState& st = states[b];
+  if (st.status != RGBID_OK) return;  // lost pairs are skipped consistently by every CTA
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: bulk-copy operands stay in uniform registers
+  if (tid < 12) ((float*)&sh.proj)[tid] = ((const float*)&st.proj[P.level])[tid];
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < kBuildWarps * kFastStages; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // chunks [c_begin, c_end) of this stream belong to this CTA; warp w takes c_begin + w, + 8, ...
+  const int c_begin = (int)(((long long)blockIdx.x * G.nchunks) / gridDim.x);
+  const int c_end = (int)(((long long)(blockIdx.x + 1) * G.nchunks) / gridDim.x);
+  const int my_first = c_begin + wid;
+  const int my_n = (c_end - my_first + kBuildWarps - 1) / kBuildWarps;  // may be <= 0
+
+  const uint32_t ring_base = smem_u32(ring) + (uint32_t)wid * (kFastStages * kStageBytes);
+  const uint32_t bar_base = smem_u32(&bars[wid * kFastStages]);
+  const char* gW0 = (const char*)M.W0.row(b, 0);
+  const char* gI0 = (const char*)M.I0.row(b, 0);
+  const char* gWx = (const char*)M.gWx.row(b, 0);
+  const char* gWy = (const char*)M.gWy.row(b, 0);
+  const char* gIx = (const char*)M.gIx.row(b, 0);
+  const char* gIy = (const char*)M.gIy.row(b, 0);
+  auto issue = [&](int i) {  // lane 0 only: bulk copies of this warp's i-th chunk into stage i % kFastStages
+    const int s = i % kFastStages;
+    const int px0 = (my_first + i * kBuildWarps) * kChunkPx;
+    constexpr uint32_t bytes = kChunkBytes;  // the last chunk of a stream runs into the map's NaN padding (see launch_gn_build)
+    const uint32_t dst = ring_base + (uint32_t)s * kStageBytes, bar = bar_base + (uint32_t)s * 8u;
+    const size_t off = (size_t)px0 * 4u;
+    mbar_arrive_expect_tx(bar, 6u * bytes);
+    bulk_g2s(dst + 0 * kChunkBytes, gW0 + off, bytes, bar);
+    bulk_g2s(dst + 1 * kChunkBytes, gI0 + off, bytes, bar);
+    bulk_g2s(dst + 2 * kChunkBytes, gWx + off, bytes, bar);
+    bulk_g2s(dst + 3 * kChunkBytes, gWy + off, bytes, bar);
+    bulk_g2s(dst + 4 * kChunkBytes, gIx + off, bytes, bar);
+    bulk_g2s(dst + 5 * kChunkBytes, gIy + off, bytes, bar);
+  };
+  if (elect_one()) {
+#pragma unroll
+    for (int i = 0; i < kFastStages; ++i)
+      if (i < my_n) issue(i);
+  }
+
+  // per-stream constants
+  const float r0 = sh.proj.r[0], r3 = sh.proj.r[3], r6 = sh.proj.r[6];
+  const float t0 = sh.proj.t[0], t1 = sh.proj.t[1], tz = sh.proj.t[2];
+  const ScaleState* sc = scales ? &scales[b] : nullptr;
+  float sigma_i = 5.f, sigma_d = 0.0025f, bias_i = 0.f, bias_d = 0.f, nu_i = 5.f, nu_d = 5.f;
+  if (P.use_scale && sc != nullptr) {
+    sigma_i = sc->sigma_int; sigma_d = sc->sigma_depthinv; bias_i = sc->bias_int; bias_d = sc->bias_depthinv;
+    nu_i = sc->nu_int; nu_d = sc->nu_depthinv;
+  }
+  if (!P.student_nu) { nu_i = 5.f; nu_d = 5.f; }  // computeWeight(STUDENT), estimate_VO.cu:160-163
+  const float is_i = 1.f / sigma_i, is_d = 1.f / sigma_d;
+  const float bos_i = bias_i / sigma_i, bos_d = bias_d / sigma_d;
+  const float c_i = (nu_i + 1.f) * (is_i * is_i), c_d = (nu_d + 1.f) * (is_d * is_d);  // (nu + 1) / sigma^2
+  const float ifx = 1.f / P.fx, ify = 1.f / P.fy;
+  const cudaTextureObject_t texW = M.texW[b], texI = M.texI[b];
+
+#if RGBID_ACC2
+  f32x2 acc2[15];
+#pragma unroll
+  for (int k = 0; k < 15; ++k) acc2[k] = 0ull;
+#else
+  float accs[kAcc];
+#pragma unroll
+  for (int k = 0; k < kAcc; ++k) accs[k] = 0.f;
+#endif
+  float chi[4] = {0.f, 0.f, 0.f, 0.f};
+
+  for (int i = 0; i < my_n; ++i) {
+    const int s = i % kFastStages;
+    const uint32_t buf = ring_base + (uint32_t)s * kStageBytes + (uint32_t)lane * 16u;
+    mbar_wait(bar_base + (uint32_t)s * 8u, (uint32_t)(i / kFastStages) & 1u);
+    float w0[4], i0[4], gwx[4], gwy[4], gix[4], giy[4];
+    *(float4*)w0 = lds128(buf + 0 * kChunkBytes);
+    *(float4*)i0 = lds128(buf + 1 * kChunkBytes);
+    *(float4*)gwx = lds128(buf + 2 * kChunkBytes);
+    *(float4*)gwy = lds128(buf + 3 * kChunkBytes);
+    *(float4*)gix = lds128(buf + 4 * kChunkBytes);
+    *(float4*)giy = lds128(buf + 5 * kChunkBytes);
+
+    const int idx = (my_first + i * kBuildWarps) * kChunkPx + lane * 4;
+    const float idxf = __int2float_rn(idx);
+    const float yf = floorf((idxf + 0.5f) * G.inv_cols);
+    const float xf0 = fmaf(-yf, G.colsf, idxf);
+    const float py = (yf - P.cy) * ify;
+    const float py2p1 = fmaf(py, py, 1.f);
+    const float rcx = fmaf(sh.proj.r[1], yf, sh.proj.r[2]);
+    const float rcy = fmaf(sh.proj.r[4], yf, sh.proj.r[5]);
+    const float rcz = fmaf(sh.proj.r[7], yf, sh.proj.r[8]);
+
+    // --- warp: first projection (geometry = keyframe inverse depth) and inverse-depth gather -------------------
+    float ax[4], ay[4], az[4], z[4], wc[4], xt[4], yt[4], w2[4], w1[4];
+    bool pin[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float xf = xf0 + (float)k;
+      ax[k] = fmaf(r0, xf, rcx); ay[k] = fmaf(r3, xf, rcy); az[k] = fmaf(r6, xf, rcz);
+      z[k] = 1.f / w0[k];
+      const float Xc = fmaf(ax[k], z[k], t0), Yc = fmaf(ay[k], z[k], t1), Zc = fmaf(az[k], z[k], tz);
+      wc[k] = 1.f / Zc;
+      xt[k] = fmaf(Xc, wc[k], 0.5f); yt[k] = fmaf(Yc, wc[k], 0.5f);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w2[k] = tex2D<float>(texW, xt[k], yt[k]);  // border addressing: 0 outside
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      // trafo3DKernelInvDepthGridStride, warping_registration.cu:533-538
+      // (a / b is written a * (1 / b): what div.approx does for |b| < 2^126, without its range fix-up)
+      const float v1z = (1.f / wc[k] - tz) * w0[k];
+      const float res = (v1z * (1.f / (1.f - w2[k] * tz))) * w2[k];
+      w1[k] = (res > 0.f) ? res : qnanf();  // NaN, <= 0 and the border value 0 are all invalid
+      if (TRACKER) {
+        // second projection with the warped inverse depth as geometry (src/visodo.cpp:1121-1126)
+        const float z1 = 1.f / w1[k];
+        const float Xc = fmaf(ax[k], z1, t0), Yc = fmaf(ay[k], z1, t1), Zc = fmaf(az[k], z1, tz);
+        const float wc1 = 1.f / Zc;
+        xt[k] = fmaf(Xc, wc1, 0.5f); yt[k] = fmaf(Yc, wc1, 0.5f);
+      }
+      // 0 <= xt < cols && 0 <= yt < rows as |2 xt / cols - 1| < 1 (false for NaN coordinates)
+      // (in tracker mode an invalid w1 gives NaN coordinates)
+      pin[k] = fmaxf(fabsf(fmaf(xt[k], G.inv_hx, -1.f)), fabsf(fmaf(yt[k], G.inv_hy, -1.f))) < 1.f;
+    }
+    float i1[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float r = tex2D<float>(texI, xt[k], yt[k]);
+      // max(0, min(r, 255)): a NaN sample becomes 255 like in the reference
+      i1[k] = pin[k] ? fmaxf(0.f, fminf(r, 255.f)) : qnanf();
+    }
+
+    // --- constraints + accumulation ----------------------------------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float xf = xf0 + (float)k;
+      const float px = (xf - P.cx) * ifx;
+      float rd[6], ri[6];
+      // invDepthConstraint (estimate_VO.cu:214-262)
+      const float gd0 = gwx[k] * P.fx, gd1 = gwy[k] * P.fy;
+      const float gd2 = -fmaf(gd0, px, gd1 * py);
+      const float n0 = gd0 * z[k], n1 = gd1 * z[k], n2 = fmaf(gd2, z[k], 1.f);
+      const float ndot = fmaf(n0, px, fmaf(n1, py, n2));
+      const float nn = fmaf(n0, n0, fmaf(n1, n1, n2 * n2));
+      const float nf = fabsf(ndot) * rsqrtf(nn * fmaf(px, px, py2p1));
+      const float h2 = gd2 + w1[k];
+      rd[0] = gd0 * w0[k]; rd[1] = gd1 * w0[k]; rd[2] = h2 * w0[k];
+      rd[3] = fmaf(h2, py, -gd1); rd[4] = fmaf(-h2, px, gd0); rd[5] = fmaf(gd1, px, -(gd0 * py));
+      const float ed = w0[k] - w1[k];
+      const float eud = fmaf(ed, is_d, -bos_d);
+      const float sd = nf * (c_d * (1.f / fmaf(eud, eud, nu_d)));  // NaN if any of w0, w1, gwx, gwy is NaN
+      const int fd = (sd > 0.f);
+      // intensityConstraint (estimate_VO.cu:176-212)
+      const float gi0 = gix[k] * P.fx, gi1 = giy[k] * P.fy;
+      const float gi2 = -fmaf(gi0, px, gi1 * py);
+      ri[0] = gi0 * w0[k]; ri[1] = gi1 * w0[k]; ri[2] = gi2 * w0[k];
+      ri[3] = fmaf(gi2, py, -gi1); ri[4] = fmaf(-gi2, px, gi0); ri[5] = fmaf(gi1, px, -(gi0 * py));
+      const float ei = i0[k] - i1[k];
+      const float eui = fmaf(ei, is_i, -bos_i);
+      float si = c_i * (1.f / fmaf(eui, eui, nu_i));
+      si = fmaf(0.f, gi2, si);  // NaN gradients invalidate the row (a NaN w0 gives a NaN i1, i0 and i1 enter ei)
+      const int fi = (si > 0.f);
+      if (CHI) {
+        // end-of-frame chi^2 on all finite full-resolution residuals (src/visodo.cpp:1411-1414,
+        // sigmaFuncs.cu:137-150, 541-611) with the reference scales 5 / 0.0025
+        if (P.chi_mestimator >= 0) {
+          const float ci = (i1[k] - i0[k]) / 5.f;
+          const float cd = (w1[k] - w0[k]) / 0.0025f;
+          if (!(isnan(ci) || isinf(ci))) { chi[0] += chi_rho_dev(ci, P.chi_mestimator); chi[1] += 1.f; }
+          if (!(isnan(cd) || isinf(cd))) { chi[2] += chi_rho_dev(cd, P.chi_mestimator); chi[3] += 1.f; }
+        }
+      }
+#if RGBID_ACC2
+      accumulate_packed(acc2, si, ri[0], ri[1], ri[2], ri[3], ri[4], ri[5], ei, fi);
+      accumulate_packed(acc2, sd, rd[0], rd[1], rd[2], rd[3], rd[4], rd[5], ed, fd);
+#else
+      accumulate_scalar(accs, si, ri, ei, fi);
+      accumulate_scalar(accs, sd, rd, ed, fd);
+#endif
+    }
+    __syncwarp();
+    if (i + kFastStages < my_n && elect_one()) issue(i + kFastStages);
+  }
+
+  float acc[NACC];
+#if RGBID_ACC2
+  unpack_acc(acc2, acc);
+#else
+#pragma unroll
+  for (int k = 0; k < kAcc; ++k) acc[k] = accs[k];
+#endif
+  if (CHI) { acc[27] = chi[0]; acc[28] = chi[1]; acc[29] = chi[2]; acc[30] = chi[3]; }
+
+  if (!reduce_and_elect<NACC>(sh, acc, partials + (size_t)b * gridDim.x * partial_stride, partial_stride,
+                              &counters[b], gridDim.x, blockIdx.x))
+    return;
+  if (threadIdx.x == 0) gn_tail(st, sh.total, P, sc, trace, b, CHI);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Un-fused drop-in for buildSystem(StudentNu)GridStride on pre-warped maps (one pair)
 // ------------------------------------------------------------------------------------------------------------
 template <int VEC>
@@ -471,6 +774,14 @@ __global__ void gn_init_kernel(GnState* __restrict__ states, const double* __res
   refresh_proj(st, levels, fx0, fy0, cx0, cy0);
 }
 
+// every stream of the map owns whole 128-pixel chunks (the aligner NaN-fills the padding and nothing writes it),
+// so the fast kernel may read the last chunk in full
+inline bool padded(const ImgB& m, const GnParams& P)
+{
+  const size_t need = (((size_t)P.rows * P.cols + 127) / 128) * 512;
+  return m.sstride >= need;
+}
+
 inline bool aligned16(const ImgB& m) { return ((uintptr_t)m.p % 16 == 0) && (m.pitch % 16 == 0) && (m.sstride % 16 == 0); }
 
 }  // namespace
@@ -533,9 +844,49 @@ void launch_gn_build(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P
 {
   bool vec = (P.cols % 4 == 0) && aligned16(M.W0) && aligned16(M.I0) && aligned16(M.gWx) && aligned16(M.gWy) &&
              aligned16(M.gIx) && aligned16(M.gIy);
-  dim3 grid(gn_build_grid_x(P.rows, P.cols, P.batch, L.num_sms), P.batch);
   const bool chi = (P.chi_mestimator >= 0);
   const bool tex = (M.texW != nullptr && M.texI != nullptr);
+  // Fast path: flat keyframe maps (pitch == cols * 4, so a chunk of 128 pixels is one contiguous segment per map),
+  // texture gathers (inverse-depth texture with border addressing), Student-t weights (estimated nu, or the fixed
+  // nu = 5 of computeWeight(STUDENT): the same expression), INDEPENDENT weighting.
+  static const bool no_fast = [] { const char* e = getenv("RGBID_NO_FAST"); return e && e[0] == '1'; }();
+  const size_t flat = (size_t)P.cols * sizeof(float);
+  const bool fast = !no_fast && vec && tex && M.tex_border && P.weighting == RGBID_INDEPENDENT &&
+                    (P.student_nu || P.mestimator == RGBID_STUDENT) && M.W0.pitch == flat && M.I0.pitch == flat &&
+                    M.gWx.pitch == flat && M.gWy.pitch == flat && M.gIx.pitch == flat && M.gIy.pitch == flat &&
+                    (long long)P.rows * P.cols <= 2500000ll && padded(M.W0, P) && padded(M.I0, P) && padded(M.gWx, P) &&
+                    padded(M.gWy, P) && padded(M.gIx, P) && padded(M.gIy, P);
+  if (fast) {
+    FastGeom G;
+    G.npx = P.rows * P.cols;
+    G.nchunks = (G.npx + kChunkPx - 1) / kChunkPx;
+    G.colsf = (float)P.cols; G.inv_cols = 1.f / (float)P.cols;
+    G.inv_hx = 2.f / (float)P.cols; G.inv_hy = 2.f / (float)P.rows;
+    // one balanced wave of 2 CTAs / SM over all pairs; a pair never gets more CTAs than it has 8-chunk groups
+    int cap = (2 * L.num_sms) / P.batch;
+    if (cap < 1) cap = 1;
+    if (cap > L.num_sms) cap = L.num_sms;
+    int gx = (G.nchunks + kBuildWarps - 1) / kBuildWarps;
+    if (gx > cap) gx = cap;
+    dim3 grid(gx, P.batch);
+    static bool configured = false;
+    if (!configured) {
+      cudaFuncSetAttribute(gn_build_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
+      cudaFuncSetAttribute(gn_build_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
+      cudaFuncSetAttribute(gn_build_fast_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
+      cudaFuncSetAttribute(gn_build_fast_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
+      configured = true;
+    }
+    const bool tracker = (P.mode == RGBID_MODE_TRACKER);
+#define RGBID_FAST_LAUNCH(T, C) \
+    gn_build_fast_kernel<T, C><<<grid, kBuildThreads, kFastSmemBytes, L.stream>>>(M, P, G, states, scales, partials, partial_stride, counters, trace)
+    if (tracker) { if (chi) RGBID_FAST_LAUNCH(true, true); else RGBID_FAST_LAUNCH(true, false); }
+    else { if (chi) RGBID_FAST_LAUNCH(false, true); else RGBID_FAST_LAUNCH(false, false); }
+#undef RGBID_FAST_LAUNCH
+    ++*L.launches;
+    return;
+  }
+  dim3 grid(gn_build_grid_x(P.rows, P.cols, P.batch, L.num_sms), P.batch);
   if (vec) {
     if (chi) launch_gn_build_t<4, true>(L, grid, tex, M, P, states, scales, partials, partial_stride, counters, trace);
     else launch_gn_build_t<4, false>(L, grid, tex, M, P, states, scales, partials, partial_stride, counters, trace);

@@ -78,6 +78,7 @@ struct GnLevelMaps {
   // optional texture objects over Wc (point) / Ic (linear), one per stream; null -> software sampler
   const cudaTextureObject_t* texW;
   const cudaTextureObject_t* texI;
+  int tex_border;  // 1: texW was created with border addressing (0 outside), which the fast build kernel relies on
 };
 
 // Device-resident state of one frame pair's Gauss-Newton problem
