@@ -377,17 +377,18 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
 // Arithmetic differs from the generic kernel only in rounding (same formulas re-associated); the parity tests
 // hold both against the oracle and the reference's own kernels.
 // ------------------------------------------------------------------------------------------------------------
-#ifndef RGBID_FAST_STAGES
-#define RGBID_FAST_STAGES 3
-#endif
 #ifndef RGBID_ACC2
 #define RGBID_ACC2 1
 #endif
-constexpr int kFastStages = RGBID_FAST_STAGES;
 constexpr int kChunkPx = 128;                   // one warp-chunk: 4 pixels per lane
 constexpr int kChunkBytes = kChunkPx * 4;       // per map
-constexpr int kStageBytes = 6 * kChunkBytes;    // 3 KiB per warp and stage
-constexpr int kFastSmemBytes = kBuildWarps * kFastStages * kStageBytes;
+// Two rings per warp: the keyframe inverse depth is needed by three pipeline stages (gather, second projection,
+// constraints) and therefore lives two iterations longer than the other five maps.
+constexpr int kStagesW = 5;                     // W0 ring: 5 x 512 B
+constexpr int kStagesL = 3;                     // I0, gWx, gWy, gIx, gIy ring: 3 x 2560 B
+constexpr int kLateBytes = 5 * kChunkBytes;
+constexpr int kWarpRingBytes = kStagesW * kChunkBytes + kStagesL * kLateBytes;  // 10 KiB
+constexpr int kFastSmemBytes = kBuildWarps * kWarpRingBytes;                    // 80 KiB per CTA
 
 struct FastGeom {
   int npx;        // rows * cols
@@ -455,7 +456,7 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
   constexpr int NACC = CHI ? kAccChi : kAcc;
   extern __shared__ __align__(128) unsigned char ring[];
   __shared__ BuildShared sh;
-  __shared__ __align__(8) unsigned long long bars[kBuildWarps * kFastStages];
+  __shared__ __align__(8) unsigned long long bars[kBuildWarps * (kStagesW + kStagesL)];
   const int b = blockIdx.y;
   GnState& st = states[b];
   if (st.status != RGBID_OK) return;  // lost pairs are skipped consistently by every CTA
@@ -464,7 +465,7 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
   if (tid < 12) ((float*)&sh.proj)[tid] = ((const float*)&st.proj[P.level])[tid];
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < kBuildWarps * kFastStages; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    for (int i = 0; i < kBuildWarps * (kStagesW + kStagesL); ++i) mbar_init(smem_u32(&bars[i]), 1);
     mbar_fence_init();
   }
   __syncthreads();
@@ -475,32 +476,42 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
   const int my_first = c_begin + wid;
   const int my_n = (c_end - my_first + kBuildWarps - 1) / kBuildWarps;  // may be <= 0
 
-  const uint32_t ring_base = smem_u32(ring) + (uint32_t)wid * (kFastStages * kStageBytes);
-  const uint32_t bar_base = smem_u32(&bars[wid * kFastStages]);
+  const uint32_t ringW = smem_u32(ring) + (uint32_t)wid * kWarpRingBytes;
+  const uint32_t ringL = ringW + kStagesW * kChunkBytes;
+  const uint32_t barW = smem_u32(&bars[wid * (kStagesW + kStagesL)]);
+  const uint32_t barL = barW + kStagesW * 8u;
   const char* gW0 = (const char*)M.W0.row(b, 0);
   const char* gI0 = (const char*)M.I0.row(b, 0);
   const char* gWx = (const char*)M.gWx.row(b, 0);
   const char* gWy = (const char*)M.gWy.row(b, 0);
   const char* gIx = (const char*)M.gIx.row(b, 0);
   const char* gIy = (const char*)M.gIy.row(b, 0);
-  auto issue = [&](int i) {  // lane 0 only: bulk copies of this warp's i-th chunk into stage i % kFastStages
-    const int s = i % kFastStages;
-    const int px0 = (my_first + i * kBuildWarps) * kChunkPx;
-    constexpr uint32_t bytes = kChunkBytes;  // the last chunk of a stream runs into the map's NaN padding (see launch_gn_build)
-    const uint32_t dst = ring_base + (uint32_t)s * kStageBytes, bar = bar_base + (uint32_t)s * 8u;
-    const size_t off = (size_t)px0 * 4u;
-    mbar_arrive_expect_tx(bar, 6u * bytes);
-    bulk_g2s(dst + 0 * kChunkBytes, gW0 + off, bytes, bar);
-    bulk_g2s(dst + 1 * kChunkBytes, gI0 + off, bytes, bar);
-    bulk_g2s(dst + 2 * kChunkBytes, gWx + off, bytes, bar);
-    bulk_g2s(dst + 3 * kChunkBytes, gWy + off, bytes, bar);
-    bulk_g2s(dst + 4 * kChunkBytes, gIx + off, bytes, bar);
-    bulk_g2s(dst + 5 * kChunkBytes, gIy + off, bytes, bar);
+  // (one elected lane) bulk copies of this warp's i-th chunk; the last chunk of a stream runs into the map's NaN
+  // padding (see launch_gn_build), so every copy is a full 512 bytes
+  auto issue_w = [&](int i) {
+    const int s = i % kStagesW;
+    const size_t off = (size_t)(my_first + i * kBuildWarps) * kChunkBytes;
+    mbar_arrive_expect_tx(barW + (uint32_t)s * 8u, kChunkBytes);
+    bulk_g2s(ringW + (uint32_t)s * kChunkBytes, gW0 + off, kChunkBytes, barW + (uint32_t)s * 8u);
+  };
+  auto issue_l = [&](int i) {
+    const int s = i % kStagesL;
+    const size_t off = (size_t)(my_first + i * kBuildWarps) * kChunkBytes;
+    const uint32_t dst = ringL + (uint32_t)s * kLateBytes, bar = barL + (uint32_t)s * 8u;
+    mbar_arrive_expect_tx(bar, kLateBytes);
+    bulk_g2s(dst + 0 * kChunkBytes, gI0 + off, kChunkBytes, bar);
+    bulk_g2s(dst + 1 * kChunkBytes, gWx + off, kChunkBytes, bar);
+    bulk_g2s(dst + 2 * kChunkBytes, gWy + off, kChunkBytes, bar);
+    bulk_g2s(dst + 3 * kChunkBytes, gIx + off, kChunkBytes, bar);
+    bulk_g2s(dst + 4 * kChunkBytes, gIy + off, kChunkBytes, bar);
   };
   if (elect_one()) {
 #pragma unroll
-    for (int i = 0; i < kFastStages; ++i)
-      if (i < my_n) issue(i);
+    for (int i = 0; i < kStagesW; ++i)
+      if (i < my_n) issue_w(i);
+#pragma unroll
+    for (int i = 0; i < kStagesL; ++i)
+      if (i < my_n) issue_l(i);
   }
 
   // per-stream constants
@@ -530,118 +541,200 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
 #endif
   float chi[4] = {0.f, 0.f, 0.f, 0.f};
 
-  for (int i = 0; i < my_n; ++i) {
-    const int s = i % kFastStages;
-    const uint32_t buf = ring_base + (uint32_t)s * kStageBytes + (uint32_t)lane * 16u;
-    mbar_wait(bar_base + (uint32_t)s * 8u, (uint32_t)(i / kFastStages) & 1u);
-    float w0[4], i0[4], gwx[4], gwy[4], gix[4], giy[4];
-    *(float4*)w0 = lds128(buf + 0 * kChunkBytes);
-    *(float4*)i0 = lds128(buf + 1 * kChunkBytes);
-    *(float4*)gwx = lds128(buf + 2 * kChunkBytes);
-    *(float4*)gwy = lds128(buf + 3 * kChunkBytes);
-    *(float4*)gix = lds128(buf + 4 * kChunkBytes);
-    *(float4*)giy = lds128(buf + 5 * kChunkBytes);
-
+  // Software pipeline over this warp's chunks.  With 128 registers only four warps share a scheduler, so the two
+  // dependent texture latencies of a pixel (inverse depth -> warped inverse depth -> intensity, tracker mode) are
+  // covered by independent arithmetic of the SAME warp.  Iteration i
+  //   S1  chunk i + 1 : warped inverse depth from the gathered one, second projection, intensity gather issued
+  //   S2  chunk i + 2 : first projection, inverse-depth gather issued
+  //   S3  chunk i     : both constraints + 2 x 27 accumulations
+  // and 12 + 4 registers travel between iterations.  KeyframeAlign mode samples the intensity where it sampled the
+  // inverse depth, so both gathers are issued in S2 and S1 disappears.
+  struct ChunkGeom { float xf0, py, py2p1, rcx, rcy, rcz; };
+  auto chunk_geom = [&](int i) {
+    ChunkGeom g;
     const int idx = (my_first + i * kBuildWarps) * kChunkPx + lane * 4;
     const float idxf = __int2float_rn(idx);
-    const float yf = floorf((idxf + 0.5f) * G.inv_cols);
-    const float xf0 = fmaf(-yf, G.colsf, idxf);
-    const float py = (yf - P.cy) * ify;
-    const float py2p1 = fmaf(py, py, 1.f);
-    const float rcx = fmaf(sh.proj.r[1], yf, sh.proj.r[2]);
-    const float rcy = fmaf(sh.proj.r[4], yf, sh.proj.r[5]);
-    const float rcz = fmaf(sh.proj.r[7], yf, sh.proj.r[8]);
-
-    // --- warp: first projection (geometry = keyframe inverse depth) and inverse-depth gather -------------------
-    float ax[4], ay[4], az[4], z[4], wc[4], xt[4], yt[4], w2[4], w1[4];
-    bool pin[4];
+    const float yf = floorf((idxf + 0.5f) * G.inv_cols);  // exact for rows * cols <= 2.5 M (checked by the launcher)
+    g.xf0 = fmaf(-yf, G.colsf, idxf);
+    g.py = (yf - P.cy) * ify;
+    g.py2p1 = fmaf(g.py, g.py, 1.f);
+    g.rcx = fmaf(sh.proj.r[1], yf, sh.proj.r[2]);
+    g.rcy = fmaf(sh.proj.r[4], yf, sh.proj.r[5]);
+    g.rcz = fmaf(sh.proj.r[7], yf, sh.proj.r[8]);
+    return g;
+  };
+  auto lds_w0 = [&](int i, float* w0) { *(float4*)w0 = lds128(ringW + (uint32_t)(i % kStagesW) * kChunkBytes + (uint32_t)lane * 16u); };
+  // 0 <= xt < cols && 0 <= yt < rows as max(|2 xt / cols - 1|, |2 yt / rows - 1|) < 1 (false for the NaN coordinates
+  // of an invalid geometry); returned as 0 / NaN so that it can be added to the sample later
+  auto in_image_nan = [&](float xt, float yt) {
+    return (fmaxf(fabsf(fmaf(xt, G.inv_hx, -1.f)), fabsf(fmaf(yt, G.inv_hy, -1.f))) < 1.f) ? 0.f : qnanf();
+  };
+  // S2: first projection (geometry = keyframe inverse depth) of chunk i and its gather(s)
+  auto gather = [&](int i, float* w2, float* wcs, float* i1, float* pinf) {
+    mbar_wait(barW + (uint32_t)(i % kStagesW) * 8u, (uint32_t)(i / kStagesW) & 1u);
+    float w0[4], xt[4], yt[4];
+    lds_w0(i, w0);
+    const ChunkGeom g = chunk_geom(i);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float xf = xf0 + (float)k;
-      ax[k] = fmaf(r0, xf, rcx); ay[k] = fmaf(r3, xf, rcy); az[k] = fmaf(r6, xf, rcz);
-      z[k] = 1.f / w0[k];
-      const float Xc = fmaf(ax[k], z[k], t0), Yc = fmaf(ay[k], z[k], t1), Zc = fmaf(az[k], z[k], tz);
-      wc[k] = 1.f / Zc;
-      xt[k] = fmaf(Xc, wc[k], 0.5f); yt[k] = fmaf(Yc, wc[k], 0.5f);
+      const float xf = g.xf0 + (float)k;
+      const float z = 1.f / w0[k];
+      const float Xc = fmaf(fmaf(r0, xf, g.rcx), z, t0), Yc = fmaf(fmaf(r3, xf, g.rcy), z, t1);
+      const float Zc = fmaf(fmaf(r6, xf, g.rcz), z, tz);
+      const float wc = 1.f / Zc;
+      wcs[k] = wc;
+      xt[k] = fmaf(Xc, wc, 0.5f); yt[k] = fmaf(Yc, wc, 0.5f);
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) w2[k] = tex2D<float>(texW, xt[k], yt[k]);  // border addressing: 0 outside
+    if (!TRACKER) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      // trafo3DKernelInvDepthGridStride, warping_registration.cu:533-538
-      // (a / b is written a * (1 / b): what div.approx does for |b| < 2^126, without its range fix-up)
-      const float v1z = (1.f / wc[k] - tz) * w0[k];
-      const float res = (v1z * (1.f / (1.f - w2[k] * tz))) * w2[k];
-      w1[k] = (res > 0.f) ? res : qnanf();  // NaN, <= 0 and the border value 0 are all invalid
-      if (TRACKER) {
-        // second projection with the warped inverse depth as geometry (src/visodo.cpp:1121-1126)
-        const float z1 = 1.f / w1[k];
-        const float Xc = fmaf(ax[k], z1, t0), Yc = fmaf(ay[k], z1, t1), Zc = fmaf(az[k], z1, tz);
-        const float wc1 = 1.f / Zc;
-        xt[k] = fmaf(Xc, wc1, 0.5f); yt[k] = fmaf(Yc, wc1, 0.5f);
-      }
-      // 0 <= xt < cols && 0 <= yt < rows as |2 xt / cols - 1| < 1 (false for NaN coordinates)
-      // (in tracker mode an invalid w1 gives NaN coordinates)
-      pin[k] = fmaxf(fabsf(fmaf(xt[k], G.inv_hx, -1.f)), fabsf(fmaf(yt[k], G.inv_hy, -1.f))) < 1.f;
+      for (int k = 0; k < 4; ++k) i1[k] = tex2D<float>(texI, xt[k], yt[k]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) pinf[k] = in_image_nan(xt[k], yt[k]);
     }
-    float i1[4];
+  };
+  // trafo3DKernelInvDepthGridStride, warping_registration.cu:533-538, operation for operation (v1z is
+  // algebraically (K R K^-1 (x, y, 1))_z, but the residual w0 - w1 is small against w and feels the rounding);
+  // a / b is written a * (1 / b): what div.approx does for |b| < 2^126, without its range fix-up
+  auto warped_invdepth = [&](float w0, float wc, float w2) {
+    const float v1z = (1.f / wc - tz) * w0;
+    const float res = (v1z * (1.f / (1.f - w2 * tz))) * w2;
+    return (res > 0.f) ? res : qnanf();  // NaN, <= 0 and the border value 0 are all invalid
+  };
+  // S1 (tracker mode): intensity is sampled where the keyframe pixel lands with the WARPED inverse depth as geometry
+  // (src/visodo.cpp:1121-1126)
+  auto second_projection = [&](int i, const float* w2, const float* wcs, float* w1, float* i1, float* pinf) {
+    const ChunkGeom g = chunk_geom(i);
+    float w0[4], xt[4], yt[4];
+    lds_w0(i, w0);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float r = tex2D<float>(texI, xt[k], yt[k]);
-      // max(0, min(r, 255)): a NaN sample becomes 255 like in the reference
-      i1[k] = pin[k] ? fmaxf(0.f, fminf(r, 255.f)) : qnanf();
+      const float xf = g.xf0 + (float)k;
+      w1[k] = warped_invdepth(w0[k], wcs[k], w2[k]);
+      const float zz = 1.f / w1[k];
+      const float Xc = fmaf(fmaf(r0, xf, g.rcx), zz, t0), Yc = fmaf(fmaf(r3, xf, g.rcy), zz, t1);
+      const float wc1 = 1.f / fmaf(fmaf(r6, xf, g.rcz), zz, tz);
+      xt[k] = fmaf(Xc, wc1, 0.5f); yt[k] = fmaf(Yc, wc1, 0.5f);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) i1[k] = tex2D<float>(texI, xt[k], yt[k]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) pinf[k] = in_image_nan(xt[k], yt[k]);
+  };
+
+  float w2n[4], wcn[4];                  // S2 -> S1 (tracker) / S3 (align): gathered inverse depth, 1 / Zc
+  float w1c[4], i1c[4], pinc[4];         // S1 -> S3: warped inverse depth, raw intensity sample, 0 / NaN in-image flag
+  if (my_n > 0) {
+    if (TRACKER) {
+      gather(0, w2n, wcn, nullptr, nullptr);
+      second_projection(0, w2n, wcn, w1c, i1c, pinc);
+      if (my_n > 1) gather(1, w2n, wcn, nullptr, nullptr);
+    } else {
+      gather(0, w2n, wcn, i1c, pinc);
+    }
+  }
+  for (int i = 0; i < my_n; ++i) {
+    float w1[4], i1[4], pin[4];
+    if (TRACKER) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { w1[k] = w1c[k]; i1[k] = i1c[k]; pin[k] = pinc[k]; }
+      if (i + 1 < my_n) second_projection(i + 1, w2n, wcn, w1c, i1c, pinc);  // warp-uniform
+      if (i + 2 < my_n) gather(i + 2, w2n, wcn, nullptr, nullptr);
+    } else {
+      float w0a[4];
+      lds_w0(i, w0a);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        w1[k] = warped_invdepth(w0a[k], wcn[k], w2n[k]);
+        i1[k] = i1c[k]; pin[k] = pinc[k];
+      }
+      if (i + 1 < my_n) gather(i + 1, w2n, wcn, i1c, pinc);
     }
 
-    // --- constraints + accumulation ----------------------------------------------------------------------------
+    // --- S3: inverse-depth constraint + accumulation -----------------------------------------------------------
+    const ChunkGeom g = chunk_geom(i);
+    const uint32_t buf = ringL + (uint32_t)(i % kStagesL) * kLateBytes + (uint32_t)lane * 16u;
+    mbar_wait(barL + (uint32_t)(i % kStagesL) * 8u, (uint32_t)(i / kStagesL) & 1u);
+    float w0[4], gwx[4], gwy[4];
+    lds_w0(i, w0);
+    *(float4*)gwx = lds128(buf + 1 * kChunkBytes);
+    *(float4*)gwy = lds128(buf + 2 * kChunkBytes);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float xf = xf0 + (float)k;
-      const float px = (xf - P.cx) * ifx;
-      float rd[6], ri[6];
-      // invDepthConstraint (estimate_VO.cu:214-262)
+      const float xf = g.xf0 + (float)k;
+      const float px = (xf - P.cx) * ifx, py = g.py;
+      // invDepthConstraint (estimate_VO.cu:214-262).  The reference's n = (g0, g1, g2) / w0 + (0, 0, 1) satisfies
+      // n . p = 1 identically (g2 = -(g0 px + g1 py)), so n_factor = |n . p| / (|n| |p|) = |w0| / (|m| |p|) with
+      // m = (g0, g1, g2 + w0).
       const float gd0 = gwx[k] * P.fx, gd1 = gwy[k] * P.fy;
       const float gd2 = -fmaf(gd0, px, gd1 * py);
-      const float n0 = gd0 * z[k], n1 = gd1 * z[k], n2 = fmaf(gd2, z[k], 1.f);
-      const float ndot = fmaf(n0, px, fmaf(n1, py, n2));
-      const float nn = fmaf(n0, n0, fmaf(n1, n1, n2 * n2));
-      const float nf = fabsf(ndot) * rsqrtf(nn * fmaf(px, px, py2p1));
+      const float m2 = gd2 + w0[k];
+      const float mm = fmaf(gd0, gd0, fmaf(gd1, gd1, m2 * m2));
+      const float nf = fabsf(w0[k]) * rsqrtf(mm * fmaf(px, px, g.py2p1));
       const float h2 = gd2 + w1[k];
+      float rd[6];
       rd[0] = gd0 * w0[k]; rd[1] = gd1 * w0[k]; rd[2] = h2 * w0[k];
       rd[3] = fmaf(h2, py, -gd1); rd[4] = fmaf(-h2, px, gd0); rd[5] = fmaf(gd1, px, -(gd0 * py));
       const float ed = w0[k] - w1[k];
       const float eud = fmaf(ed, is_d, -bos_d);
       const float sd = nf * (c_d * (1.f / fmaf(eud, eud, nu_d)));  // NaN if any of w0, w1, gwx, gwy is NaN
       const int fd = (sd > 0.f);
+      if (CHI) {
+        // end-of-frame chi^2 on all finite full-resolution residuals (src/visodo.cpp:1411-1414,
+        // sigmaFuncs.cu:137-150, 541-611) with the reference scales 5 / 0.0025
+        if (P.chi_mestimator >= 0) {
+          const float cd = (w1[k] - w0[k]) / 0.0025f;
+          if (!(isnan(cd) || isinf(cd))) { chi[2] += chi_rho_dev(cd, P.chi_mestimator); chi[3] += 1.f; }
+        }
+      }
+#if RGBID_ACC2
+      accumulate_packed(acc2, sd, rd[0], rd[1], rd[2], rd[3], rd[4], rd[5], ed, fd);
+#else
+      accumulate_scalar(accs, sd, rd, ed, fd);
+#endif
+    }
+
+    // --- S3: intensity constraint + accumulation ---------------------------------------------------------------
+    float i0[4], gix[4], giy[4];
+    *(float4*)i0 = lds128(buf + 0 * kChunkBytes);
+    *(float4*)gix = lds128(buf + 3 * kChunkBytes);
+    *(float4*)giy = lds128(buf + 4 * kChunkBytes);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float xf = g.xf0 + (float)k;
+      const float px = (xf - P.cx) * ifx, py = g.py;
+      // max(0, min(r, 255)): a NaN sample becomes 255 like in the reference (warping_registration.cu:493-494);
+      // + 0 / NaN: outside the image or invalid geometry
+      const float i1v = fmaxf(0.f, fminf(i1[k], 255.f)) + pin[k];
       // intensityConstraint (estimate_VO.cu:176-212)
       const float gi0 = gix[k] * P.fx, gi1 = giy[k] * P.fy;
       const float gi2 = -fmaf(gi0, px, gi1 * py);
+      float ri[6];
       ri[0] = gi0 * w0[k]; ri[1] = gi1 * w0[k]; ri[2] = gi2 * w0[k];
       ri[3] = fmaf(gi2, py, -gi1); ri[4] = fmaf(-gi2, px, gi0); ri[5] = fmaf(gi1, px, -(gi0 * py));
-      const float ei = i0[k] - i1[k];
+      const float ei = i0[k] - i1v;
       const float eui = fmaf(ei, is_i, -bos_i);
       float si = c_i * (1.f / fmaf(eui, eui, nu_i));
       si = fmaf(0.f, gi2, si);  // NaN gradients invalidate the row (a NaN w0 gives a NaN i1, i0 and i1 enter ei)
       const int fi = (si > 0.f);
       if (CHI) {
-        // end-of-frame chi^2 on all finite full-resolution residuals (src/visodo.cpp:1411-1414,
-        // sigmaFuncs.cu:137-150, 541-611) with the reference scales 5 / 0.0025
         if (P.chi_mestimator >= 0) {
-          const float ci = (i1[k] - i0[k]) / 5.f;
-          const float cd = (w1[k] - w0[k]) / 0.0025f;
+          const float ci = (i1v - i0[k]) / 5.f;
           if (!(isnan(ci) || isinf(ci))) { chi[0] += chi_rho_dev(ci, P.chi_mestimator); chi[1] += 1.f; }
-          if (!(isnan(cd) || isinf(cd))) { chi[2] += chi_rho_dev(cd, P.chi_mestimator); chi[3] += 1.f; }
         }
       }
 #if RGBID_ACC2
       accumulate_packed(acc2, si, ri[0], ri[1], ri[2], ri[3], ri[4], ri[5], ei, fi);
-      accumulate_packed(acc2, sd, rd[0], rd[1], rd[2], rd[3], rd[4], rd[5], ed, fd);
 #else
       accumulate_scalar(accs, si, ri, ei, fi);
-      accumulate_scalar(accs, sd, rd, ed, fd);
 #endif
     }
     __syncwarp();
-    if (i + kFastStages < my_n && elect_one()) issue(i + kFastStages);
+    if (elect_one()) {
+      if (i + kStagesW < my_n) issue_w(i + kStagesW);
+      if (i + kStagesL < my_n) issue_l(i + kStagesL);
+    }
   }
 
   float acc[NACC];
