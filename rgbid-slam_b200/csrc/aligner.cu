@@ -86,6 +86,7 @@ static GnParams base_params(const rgbid_aligner* al, int level)
   P.kept_rows = al->geom[level].kept_rows; P.kept_cols = al->geom[level].kept_cols;
   P.sample_stride = al->geom[level].sample_stride;
   P.sigma_op = (c.mode == RGBID_MODE_TRACKER) ? SCALE_SIGMA_NU : SCALE_NU_ONLY;
+  P.next_level = -1;
   return P;
 }
 
@@ -118,6 +119,14 @@ void aligner_record_schedule(rgbid_aligner* al)
     for (int it = 0; it < c.iterations[level]; ++it) {
       GnParams P = base_params(al, level);
       P.iter_index = done;
+      // the updated pose is consumed at this level again, at the next coarser-to-finer level that has iterations,
+      // or by the covariance pass at the finest level
+      P.next_level = level;
+      if (it + 1 == c.iterations[level]) {
+        P.next_level = c.finest_level;
+        for (int l = level - 1; l >= c.finest_level; --l)
+          if (c.iterations[l] > 0) { P.next_level = l; break; }
+      }
       P.use_scale = estimate_scale ? 1 : 0;
       ++done;
       // KeyframeAlign: covariance = inverse of the LAST iteration's A (keyframe_align.cpp:339-350)

@@ -86,6 +86,11 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
   return d;
 }
 
+__device__ __forceinline__ void fma2(f32x2& d, f32x2 a, f32x2 b)
+{
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+
 // d += a * b where flag != 0 (predicated, not branched: invalid pixels carry NaN operands that must not be
 // accumulated, and a branch per pixel and constraint would serialise the four pixels of a thread)
 __device__ __forceinline__ void pfma2(f32x2& d, f32x2 a, f32x2 b, int flag)

@@ -198,13 +198,16 @@ __device__ __forceinline__ bool reduce_and_elect(BuildShared& sh, const float* a
   return true;
 }
 
-__device__ __forceinline__ void refresh_proj(GnState& st, int levels, float fx0, float fy0, float cx0, float cy0)
+// only: the one level the next launch reads (-1: all levels)
+__device__ __forceinline__ void refresh_proj(GnState& st, int levels, float fx0, float fy0, float cx0, float cy0,
+                                             int only = -1)
 {
   double Ri[9], ti[3];
   mat3_inverse(st.R, Ri);
   mat3_vec(Ri, st.t, ti);
   ti[0] = -ti[0]; ti[1] = -ti[1]; ti[2] = -ti[2];
   for (int l = 0; l < levels; ++l) {
+    if (only >= 0 && l != only) continue;
     float div = (float)(1 << l);  // Intr::operator()(level), src/internal.h:128-132
     projective_pose(Ri, ti, fx0 / div, fy0 / div, cx0 / div, cy0 / div, st.proj[l].r, st.proj[l].t);
   }
@@ -238,7 +241,7 @@ __device__ __noinline__ void gn_tail(GnState& st, const double* tot, const GnPar
       for (int i = 0; i < 3; ++i) st.t[i] = st.t0[i];
       for (int i = 0; i < 36; ++i) st.cov[i] = (i % 7 == 0) ? 100.0 : 0.0;
     }
-    refresh_proj(st, P.levels, P.fx0, P.fy0, P.cx0, P.cy0);
+    refresh_proj(st, P.levels, P.fx0, P.fy0, P.cx0, P.cy0, P.next_level);
   }
   if (trace != nullptr && P.trace_stride > 0 && P.iter_index >= 0 && P.iter_index < P.trace_stride) {
     rgbid_iter_trace& T = trace[(size_t)b * P.trace_stride + P.iter_index];
@@ -377,8 +380,12 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
 // Arithmetic differs from the generic kernel only in rounding (same formulas re-associated); the parity tests
 // hold both against the oracle and the reference's own kernels.
 // ------------------------------------------------------------------------------------------------------------
+// RGBID_ACC2=1 selects the packed (FFMA2) accumulation.  Measured on B200 (tools/ubench/pipes.cu): an FFMA2 on three
+// distinct register pairs issues every 3.1 clk per SMSP -- the same FP32 rate as scalar FFMAs on distinct registers
+// (0.68 / clk) -- so packing saves issue slots but no FMA-pipe time, and this kernel is FMA-pipe bound: the packed
+// variant (178 instead of 195 instructions per pixel) is not faster (90.2 vs 89.3 us).  Kept as an experiment.
 #ifndef RGBID_ACC2
-#define RGBID_ACC2 1
+#define RGBID_ACC2 0
 #endif
 constexpr int kChunkPx = 128;                   // one warp-chunk: 4 pixels per lane
 constexpr int kChunkBytes = kChunkPx * 4;       // per map
@@ -418,21 +425,22 @@ __device__ __forceinline__ void unpack_acc(const f32x2* a2, float* acc)
 
 // acc2 += s * (r, e) (r, e)^T restricted to the 27 needed terms; rows as pairs A = (r0, r1), B = (r2, r3),
 // C = (r4, r5).  Cross products of two different pairs fill both lanes (X * Y and X * swap(Y)); the three
-// within-pair products waste one lane each.
+// within-pair products waste one lane each.  FFMA2 cannot be predicated (ptxas turns a predicated one into FFMA2 +
+// two selects), so the caller passes s = 0 and FINITE rows for an invalid pixel.
 __device__ __forceinline__ void accumulate_packed(f32x2* a2, float s, float r0, float r1, float r2, float r3, float r4,
-                                                  float r5, float e, int flag)
+                                                  float r5, float e)
 {
   const f32x2 A = pack2(r0, r1), B = pack2(r2, r3), C = pack2(r4, r5);
   const f32x2 As = pack2(r1, r0), Bs = pack2(r3, r2), Cs = pack2(r5, r4);
   const f32x2 S = pack2(s, s), E = pack2(e, e);
   const f32x2 sA = mul2(S, A), sB = mul2(S, B), sC = mul2(S, C);
-  pfma2(a2[0], sA, A, flag);   pfma2(a2[1], sA, As, flag);
-  pfma2(a2[2], sA, B, flag);   pfma2(a2[3], sA, Bs, flag);
-  pfma2(a2[4], sA, C, flag);   pfma2(a2[5], sA, Cs, flag);
-  pfma2(a2[6], sB, B, flag);   pfma2(a2[7], sB, Bs, flag);
-  pfma2(a2[8], sB, C, flag);   pfma2(a2[9], sB, Cs, flag);
-  pfma2(a2[10], sC, C, flag);  pfma2(a2[11], sC, Cs, flag);
-  pfma2(a2[12], sA, E, flag);  pfma2(a2[13], sB, E, flag);  pfma2(a2[14], sC, E, flag);
+  fma2(a2[0], sA, A);   fma2(a2[1], sA, As);
+  fma2(a2[2], sA, B);   fma2(a2[3], sA, Bs);
+  fma2(a2[4], sA, C);   fma2(a2[5], sA, Cs);
+  fma2(a2[6], sB, B);   fma2(a2[7], sB, Bs);
+  fma2(a2[8], sB, C);   fma2(a2[9], sB, Cs);
+  fma2(a2[10], sC, C);  fma2(a2[11], sC, Cs);
+  fma2(a2[12], sA, E);  fma2(a2[13], sB, E);  fma2(a2[14], sC, E);
 }
 
 __device__ __forceinline__ void accumulate_scalar(float* acc, float s, const float* r, float e, int flag)
@@ -549,18 +557,17 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
   //   S3  chunk i     : both constraints + 2 x 27 accumulations
   // and 12 + 4 registers travel between iterations.  KeyframeAlign mode samples the intensity where it sampled the
   // inverse depth, so both gathers are issued in S2 and S1 disappears.
-  struct ChunkGeom { float xf0, py, py2p1, rcx, rcy, rcz; };
+  struct ChunkGeom { float xf0, yf, rcx, rcy, rcz; };
+  const float r1 = sh.proj.r[1], r2 = sh.proj.r[2], r4 = sh.proj.r[4], r5 = sh.proj.r[5], r7 = sh.proj.r[7], r8 = sh.proj.r[8];
+  const float idxf0 = __int2float_rn(my_first * kChunkPx + lane * 4) + 0.5f;  // pixel index + 0.5, exact below 2^23
   auto chunk_geom = [&](int i) {
     ChunkGeom g;
-    const int idx = (my_first + i * kBuildWarps) * kChunkPx + lane * 4;
-    const float idxf = __int2float_rn(idx);
-    const float yf = floorf((idxf + 0.5f) * G.inv_cols);  // exact for rows * cols <= 2.5 M (checked by the launcher)
-    g.xf0 = fmaf(-yf, G.colsf, idxf);
-    g.py = (yf - P.cy) * ify;
-    g.py2p1 = fmaf(g.py, g.py, 1.f);
-    g.rcx = fmaf(sh.proj.r[1], yf, sh.proj.r[2]);
-    g.rcy = fmaf(sh.proj.r[4], yf, sh.proj.r[5]);
-    g.rcz = fmaf(sh.proj.r[7], yf, sh.proj.r[8]);
+    const float idxh = fmaf(__int2float_rn(i), (float)(kBuildWarps * kChunkPx), idxf0);
+    g.yf = floorf(idxh * G.inv_cols);  // exact for rows * cols <= 2.5 M (checked by the launcher)
+    g.xf0 = fmaf(-g.yf, G.colsf, idxh) - 0.5f;
+    g.rcx = fmaf(r1, g.yf, r2);
+    g.rcy = fmaf(r4, g.yf, r5);
+    g.rcz = fmaf(r7, g.yf, r8);
     return g;
   };
   auto lds_w0 = [&](int i, float* w0) { *(float4*)w0 = lds128(ringW + (uint32_t)(i % kStagesW) * kChunkBytes + (uint32_t)lane * 16u); };
@@ -624,36 +631,36 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
   };
 
   float w2n[4], wcn[4];                  // S2 -> S1 (tracker) / S3 (align): gathered inverse depth, 1 / Zc
-  float w1c[4], i1c[4], pinc[4];         // S1 -> S3: warped inverse depth, raw intensity sample, 0 / NaN in-image flag
+  // S1 -> S3: warped inverse depth, raw intensity sample, 0 / NaN in-image flag.  Two sets, used alternately by a
+  // loop unrolled by two, so that nothing has to be copied between iterations.
+  float w1a[4], i1a[4], pina[4], w1b[4], i1b[4], pinb[4];
   if (my_n > 0) {
     if (TRACKER) {
       gather(0, w2n, wcn, nullptr, nullptr);
-      second_projection(0, w2n, wcn, w1c, i1c, pinc);
+      second_projection(0, w2n, wcn, w1a, i1a, pina);
       if (my_n > 1) gather(1, w2n, wcn, nullptr, nullptr);
     } else {
-      gather(0, w2n, wcn, i1c, pinc);
+      gather(0, w2n, wcn, i1a, pina);
     }
   }
-  for (int i = 0; i < my_n; ++i) {
-    float w1[4], i1[4], pin[4];
+  // one iteration: S1 + S2 fill the `n` set for chunk i + 1, S3 consumes the `c` set of chunk i
+  auto iteration = [&](int i, float* w1c, float* i1c, float* pinc, float* w1n, float* i1n, float* pinn) {
+    float* w1 = w1c; float* i1 = i1c; float* pin = pinc;
     if (TRACKER) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { w1[k] = w1c[k]; i1[k] = i1c[k]; pin[k] = pinc[k]; }
-      if (i + 1 < my_n) second_projection(i + 1, w2n, wcn, w1c, i1c, pinc);  // warp-uniform
+      if (i + 1 < my_n) second_projection(i + 1, w2n, wcn, w1n, i1n, pinn);  // warp-uniform
       if (i + 2 < my_n) gather(i + 2, w2n, wcn, nullptr, nullptr);
     } else {
       float w0a[4];
       lds_w0(i, w0a);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        w1[k] = warped_invdepth(w0a[k], wcn[k], w2n[k]);
-        i1[k] = i1c[k]; pin[k] = pinc[k];
-      }
-      if (i + 1 < my_n) gather(i + 1, w2n, wcn, i1c, pinc);
+      for (int k = 0; k < 4; ++k) w1c[k] = warped_invdepth(w0a[k], wcn[k], w2n[k]);
+      if (i + 1 < my_n) gather(i + 1, w2n, wcn, i1n, pinn);
     }
 
     // --- S3: inverse-depth constraint + accumulation -----------------------------------------------------------
     const ChunkGeom g = chunk_geom(i);
+    const float py = (g.yf - P.cy) * ify;
+    const float py2p1 = fmaf(py, py, 1.f);
     const uint32_t buf = ringL + (uint32_t)(i % kStagesL) * kLateBytes + (uint32_t)lane * 16u;
     mbar_wait(barL + (uint32_t)(i % kStagesL) * 8u, (uint32_t)(i / kStagesL) & 1u);
     float w0[4], gwx[4], gwy[4];
@@ -663,15 +670,32 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float xf = g.xf0 + (float)k;
-      const float px = (xf - P.cx) * ifx, py = g.py;
+      const float px = (xf - P.cx) * ifx;
       // invDepthConstraint (estimate_VO.cu:214-262).  The reference's n = (g0, g1, g2) / w0 + (0, 0, 1) satisfies
       // n . p = 1 identically (g2 = -(g0 px + g1 py)), so n_factor = |n . p| / (|n| |p|) = |w0| / (|m| |p|) with
       // m = (g0, g1, g2 + w0).
       const float gd0 = gwx[k] * P.fx, gd1 = gwy[k] * P.fy;
+#if RGBID_ACC2
+      // rows from sanitised inputs (NaN -> a finite value that a zero weight annihilates), weight from the raw ones
+      // (NaN propagates into sd and fmaxf(sd, 0) turns it into 0)
+      const float gs0 = fmaxf(gd0, -1e30f), gs1 = fmaxf(gd1, -1e30f);
+      const float w0s = fmaxf(w0[k], 0.f), w1s = fmaxf(w1[k], 0.f);
+      const float gs2 = -fmaf(gs0, px, gs1 * py);
+      const float m2 = gs2 + w0[k];
+      const float mm = fmaf(gd0, gd0, fmaf(gd1, gd1, m2 * m2));
+      const float nf = fabsf(w0[k]) * rsqrtf(mm * fmaf(px, px, py2p1));
+      const float h2 = gs2 + w1s;
+      float rd[6];
+      rd[0] = gs0 * w0s; rd[1] = gs1 * w0s; rd[2] = h2 * w0s;
+      rd[3] = fmaf(h2, py, -gs1); rd[4] = fmaf(-h2, px, gs0); rd[5] = fmaf(gs1, px, -(gs0 * py));
+      const float ed = w0s - w1s;
+      const float eud = fmaf(w0[k] - w1[k], is_d, -bos_d);
+      const float sd = fmaxf(nf * (c_d * (1.f / fmaf(eud, eud, nu_d))), 0.f);
+#else
       const float gd2 = -fmaf(gd0, px, gd1 * py);
       const float m2 = gd2 + w0[k];
       const float mm = fmaf(gd0, gd0, fmaf(gd1, gd1, m2 * m2));
-      const float nf = fabsf(w0[k]) * rsqrtf(mm * fmaf(px, px, g.py2p1));
+      const float nf = fabsf(w0[k]) * rsqrtf(mm * fmaf(px, px, py2p1));
       const float h2 = gd2 + w1[k];
       float rd[6];
       rd[0] = gd0 * w0[k]; rd[1] = gd1 * w0[k]; rd[2] = h2 * w0[k];
@@ -680,6 +704,7 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
       const float eud = fmaf(ed, is_d, -bos_d);
       const float sd = nf * (c_d * (1.f / fmaf(eud, eud, nu_d)));  // NaN if any of w0, w1, gwx, gwy is NaN
       const int fd = (sd > 0.f);
+#endif
       if (CHI) {
         // end-of-frame chi^2 on all finite full-resolution residuals (src/visodo.cpp:1411-1414,
         // sigmaFuncs.cu:137-150, 541-611) with the reference scales 5 / 0.0025
@@ -689,7 +714,7 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
         }
       }
 #if RGBID_ACC2
-      accumulate_packed(acc2, sd, rd[0], rd[1], rd[2], rd[3], rd[4], rd[5], ed, fd);
+      accumulate_packed(acc2, sd, rd[0], rd[1], rd[2], rd[3], rd[4], rd[5], ed);
 #else
       accumulate_scalar(accs, sd, rd, ed, fd);
 #endif
@@ -703,12 +728,24 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float xf = g.xf0 + (float)k;
-      const float px = (xf - P.cx) * ifx, py = g.py;
+      const float px = (xf - P.cx) * ifx;
       // max(0, min(r, 255)): a NaN sample becomes 255 like in the reference (warping_registration.cu:493-494);
       // + 0 / NaN: outside the image or invalid geometry
       const float i1v = fmaxf(0.f, fminf(i1[k], 255.f)) + pin[k];
       // intensityConstraint (estimate_VO.cu:176-212)
       const float gi0 = gix[k] * P.fx, gi1 = giy[k] * P.fy;
+#if RGBID_ACC2
+      const float gs0 = fmaxf(gi0, -1e30f), gs1 = fmaxf(gi1, -1e30f), w0s = fmaxf(w0[k], 0.f);
+      const float gs2 = -fmaf(gs0, px, gs1 * py);
+      float ri[6];
+      ri[0] = gs0 * w0s; ri[1] = gs1 * w0s; ri[2] = gs2 * w0s;
+      ri[3] = fmaf(gs2, py, -gs1); ri[4] = fmaf(-gs2, px, gs0); ri[5] = fmaf(gs1, px, -(gs0 * py));
+      const float ei_raw = i0[k] - i1v;
+      const float ei = fmaxf(ei_raw, -1e30f);
+      const float eui = fmaf(ei_raw, is_i, -bos_i);
+      // NaN gradients invalidate the row (a NaN w0 gives a NaN i1; i0 and i1 enter ei)
+      const float si = fmaxf(fmaf(0.f, gi0 + gi1, c_i * (1.f / fmaf(eui, eui, nu_i))), 0.f);
+#else
       const float gi2 = -fmaf(gi0, px, gi1 * py);
       float ri[6];
       ri[0] = gi0 * w0[k]; ri[1] = gi1 * w0[k]; ri[2] = gi2 * w0[k];
@@ -718,6 +755,7 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
       float si = c_i * (1.f / fmaf(eui, eui, nu_i));
       si = fmaf(0.f, gi2, si);  // NaN gradients invalidate the row (a NaN w0 gives a NaN i1, i0 and i1 enter ei)
       const int fi = (si > 0.f);
+#endif
       if (CHI) {
         if (P.chi_mestimator >= 0) {
           const float ci = (i1v - i0[k]) / 5.f;
@@ -725,7 +763,7 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
         }
       }
 #if RGBID_ACC2
-      accumulate_packed(acc2, si, ri[0], ri[1], ri[2], ri[3], ri[4], ri[5], ei, fi);
+      accumulate_packed(acc2, si, ri[0], ri[1], ri[2], ri[3], ri[4], ri[5], ei);
 #else
       accumulate_scalar(accs, si, ri, ei, fi);
 #endif
@@ -735,6 +773,10 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
       if (i + kStagesW < my_n) issue_w(i + kStagesW);
       if (i + kStagesL < my_n) issue_l(i + kStagesL);
     }
+  };
+  for (int i = 0; i < my_n; i += 2) {
+    iteration(i, w1a, i1a, pina, w1b, i1b, pinb);
+    if (i + 1 < my_n) iteration(i + 1, w1b, i1b, pinb, w1a, i1a, pina);
   }
 
   float acc[NACC];

@@ -110,6 +110,7 @@ struct GnParams {
   int trace_stride;             // entries per pair (0: no trace)
   int kept_rows, kept_cols, sample_stride;  // residual sampling geometry of this level
   int sigma_op;                 // ScaleOp used by the sampling kernel
+  int next_level;               // level of the launch that consumes the updated pose (-1: refresh proj[] of all levels)
 };
 
 // fused warp + sample + residual -> IRLS sigma / nu (8-CTA cluster per pair)

@@ -124,6 +124,65 @@ __device__ __forceinline__ void slot_accumulate(const ScaleSlot& s, float e, flo
   }
 }
 
+// One round over this CTA's samples.  The phase is uniform over the cluster, so it is tested once per round, not
+// once per sample; the Student-t phases (every round of the shipped configuration) are written out with the
+// divisions as multiplications by one reciprocal -- what div.approx computes, minus its per-call range fix-up.
+// This loop is where the scale kernel spends its time (38 400 samples x ~14 rounds per frame pair and launch).
+__device__ __forceinline__ void slot_accumulate_all(const ScaleSlot& s, const float* __restrict__ samples, int n, float* acc)
+{
+  const int tid = threadIdx.x;
+  if (s.phase == PH_IRLS && s.op == SCALE_SIGMA_NU) {
+    // partialBiasAndSigmaStudent, sigmaFuncs.cu:281-360 (nu fixed at 5 during IRLS, :907)
+    if (s.lsq) {
+#pragma unroll 5
+      for (int i = tid; i < n; i += kScaleThreads) {
+        const float e = samples[i];
+        if (fabsf(e) < __int_as_float(0x7f800000)) {  // finite (sigmaFuncs.cu:308)
+          acc[0] += e * e; acc[1] += e; acc[2] += 1.f; acc[5] += 1.f;
+        }
+      }
+    } else {
+      const float bias = s.bias, rsigma = 1.f / s.sigma;
+#pragma unroll 5
+      for (int i = tid; i < n; i += kScaleThreads) {
+        const float e = samples[i];
+        if (fabsf(e) < __int_as_float(0x7f800000)) {
+          const float en = (e - bias) * rsigma;
+          const float weight = (5.f + 1.f) * (1.f / (5.f + en * en));
+          const float wr = e * weight;
+          acc[0] += wr * e; acc[1] += wr; acc[2] += weight; acc[5] += 1.f;
+        }
+      }
+    }
+  } else if (s.phase == PH_NU_INIT) {
+    // partialFuncWeightsNu, sigmaFuncs.cu:412-475 at nu = 2 and nu = 10
+    const float bias = s.bias, rsigma = 1.f / s.sigma;
+#pragma unroll 5
+    for (int i = tid; i < n; i += kScaleThreads) {
+      const float e = samples[i];
+      if (fabsf(e) < __int_as_float(0x7f800000)) {
+        const float en = (e - bias) * rsigma;
+        const float e2 = en * en;
+        const float w2 = (2.f + 1.f) * (1.f / (2.f + e2)), w10 = (10.f + 1.f) * (1.f / (10.f + e2));
+        acc[0] += logf(w2); acc[1] += w2; acc[2] += logf(w10); acc[3] += w10; acc[5] += 1.f;
+      }
+    }
+  } else if (s.phase == PH_NU_BISECT) {
+    const float bias = s.bias, rsigma = 1.f / s.sigma, nu = s.nu_new, nu1 = s.nu_new + 1.f;
+#pragma unroll 5
+    for (int i = tid; i < n; i += kScaleThreads) {
+      const float e = samples[i];
+      if (fabsf(e) < __int_as_float(0x7f800000)) {
+        const float en = (e - bias) * rsigma;
+        const float w = nu1 * (1.f / (nu + en * en));
+        acc[0] += logf(w); acc[1] += w; acc[5] += 1.f;
+      }
+    }
+  } else {
+    for (int i = tid; i < n; i += kScaleThreads) slot_accumulate(s, samples[i], acc);
+  }
+}
+
 // Host-side control flow of computeSigmaAndNuStudent / computeSigmaPdf / computeNuStudent, advanced by
 // one round given the cluster-wide totals tot[0..5] of this slot.
 __device__ __forceinline__ void slot_advance(ScaleSlot& s, const double* tot)
@@ -190,10 +249,8 @@ __device__ __forceinline__ void scale_rounds(cg::cluster_group& cluster, ScaleSh
     float acc[kScaleVals];
 #pragma unroll
     for (int k = 0; k < kScaleVals; ++k) acc[k] = 0.f;
-    if (s0.phase != PH_DONE)
-      for (int i = tid; i < n_local; i += kScaleThreads) slot_accumulate(s0, samples0[i], acc);
-    if (s1.phase != PH_DONE)
-      for (int i = tid; i < n_local; i += kScaleThreads) slot_accumulate(s1, samples1[i], acc + 6);
+    if (s0.phase != PH_DONE) slot_accumulate_all(s0, samples0, n_local, acc);
+    if (s1.phase != PH_DONE) slot_accumulate_all(s1, samples1, n_local, acc + 6);
     // float inside the warp (<= ~10 samples per lane; the reference sums in float throughout), double above
 #pragma unroll
     for (int k = 0; k < kScaleVals; ++k) {
@@ -209,11 +266,14 @@ __device__ __forceinline__ void scale_rounds(cg::cluster_group& cluster, ScaleSh
     }
     cluster.sync();
     if (tid < kScaleVals) {
+      // all remote reads in flight at once (a DSMEM load is a few hundred ns; issued one after the other they
+      // were most of a round), then the fixed-order sum
+      double part[kScaleCluster];
+#pragma unroll
+      for (int r = 0; r < kScaleCluster; ++r) part[r] = cluster.map_shared_rank(&sh.xchg[parity][0], r)[tid];
       double v = 0.0;
-      for (unsigned r = 0; r < cluster.num_blocks(); ++r) {
-        const double* remote = cluster.map_shared_rank(&sh.xchg[parity][0], r);
-        v += remote[tid];
-      }
+#pragma unroll
+      for (int r = 0; r < kScaleCluster; ++r) v += part[r];
       sh.total[tid] = v;
     }
     __syncthreads();

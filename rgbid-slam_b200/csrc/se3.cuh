@@ -9,8 +9,13 @@
 
 #if defined(__CUDACC__)
 #define RGBID_HD __host__ __device__ __forceinline__
+// every fixed-count loop is unrolled on the device: the Gauss-Newton tail runs in ONE thread per frame pair while the
+// GPU waits, so it must be straight-line register code with instruction-level parallelism, not loops over local
+// memory
+#define RGBID_UNROLL _Pragma("unroll")
 #else
 #define RGBID_HD inline
+#define RGBID_UNROLL
 #endif
 
 namespace rgbid {
@@ -18,9 +23,12 @@ namespace rgbid {
 RGBID_HD void mat3_mul(const double* A, const double* B, double* C)
 {
   double T[9];
+  RGBID_UNROLL
   for (int i = 0; i < 3; ++i)
+    RGBID_UNROLL
     for (int j = 0; j < 3; ++j)
       T[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+  RGBID_UNROLL
   for (int i = 0; i < 9; ++i) C[i] = T[i];
 }
 
@@ -35,6 +43,7 @@ RGBID_HD void mat3_vec(const double* A, const double* v, double* r)
 RGBID_HD void mat3_transpose(const double* A, double* At)
 {
   double T[9] = {A[0], A[3], A[6], A[1], A[4], A[7], A[2], A[5], A[8]};
+  RGBID_UNROLL
   for (int i = 0; i < 9; ++i) At[i] = T[i];
 }
 
@@ -48,6 +57,7 @@ RGBID_HD void mat3_inverse(const double* M, double* Mi)
   T[0] = c00 * id; T[1] = (M[2] * M[7] - M[1] * M[8]) * id; T[2] = (M[1] * M[5] - M[2] * M[4]) * id;
   T[3] = c01 * id; T[4] = (M[0] * M[8] - M[2] * M[6]) * id; T[5] = (M[2] * M[3] - M[0] * M[5]) * id;
   T[6] = c02 * id; T[7] = (M[1] * M[6] - M[0] * M[7]) * id; T[8] = (M[0] * M[4] - M[1] * M[3]) * id;
+  RGBID_UNROLL
   for (int i = 0; i < 9; ++i) Mi[i] = T[i];
 }
 
@@ -56,19 +66,26 @@ RGBID_HD void mat3_inverse(const double* M, double* Mi)
 RGBID_HD void force_orthogonal(const double* M, double* R)
 {
   double X[9];
+  RGBID_UNROLL
   for (int i = 0; i < 9; ++i) X[i] = M[i];
   for (int it = 0; it < 12; ++it) {
     double Xi[9], d = 0.0;
     mat3_inverse(X, Xi);
+    RGBID_UNROLL
     for (int i = 0; i < 3; ++i)
+      RGBID_UNROLL
       for (int j = 0; j < 3; ++j) {
         double y = 0.5 * (X[3 * i + j] + Xi[3 * j + i]);
         d += fabs(y - X[3 * i + j]);
         R[3 * i + j] = y;
       }
+    RGBID_UNROLL
     for (int i = 0; i < 9; ++i) X[i] = R[i];
-    if (d < 1e-16) break;
+    // quadratic convergence: a step below 1e-14 leaves an error far below one ulp (a tighter test never fires on
+    // rounding noise and burns all 12 iterations in the single-thread tail of every Gauss-Newton launch)
+    if (d < 1e-14) break;
   }
+  RGBID_UNROLL
   for (int i = 0; i < 9; ++i) R[i] = X[i];
 }
 
@@ -88,6 +105,7 @@ RGBID_HD void exp_map_rot(const double* omega, double* R)
   mat3_mul(O, O, O2);
   if (theta < 0.00001) { a = 1.0; b = 0.5; }
   else { a = sin(theta) / theta; b = (1.0 - cos(theta)) / (theta * theta); }
+  RGBID_UNROLL
   for (int i = 0; i < 9; ++i) M[i] = ((i % 4 == 0) ? 1.0 : 0.0) + a * O[i] + b * O2[i];
   force_orthogonal(M, R);
 }
@@ -105,6 +123,7 @@ RGBID_HD void exp_map(const double* omega, const double* v, double* R, double* t
     b = (1.0 - cos(theta)) / (theta * theta);
     c = (1.0 - a) / (theta * theta);
   }
+  RGBID_UNROLL
   for (int i = 0; i < 9; ++i) {
     double I = (i % 4 == 0) ? 1.0 : 0.0;
     M[i] = I + a * O[i] + b * O2[i];
@@ -133,6 +152,7 @@ RGBID_HD void log_map(const double* Rin, const double* trans, double* twist)
   double th = sqrt(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]);
   if (th < 0.00001) { b = 0.5; cc = 1.0 / 6.0; }
   else { b = (1.0 - cos(theta)) / (theta * theta); cc = (1.0 - (sin(theta) / theta)) / (theta * theta); }
+  RGBID_UNROLL
   for (int i = 0; i < 9; ++i) Q[i] = ((i % 4 == 0) ? 1.0 : 0.0) + b * O[i] + cc * O2[i];
   mat3_inverse(Q, Qi);
   mat3_vec(Qi, trans, twist);
@@ -143,7 +163,9 @@ RGBID_HD void log_map(const double* Rin, const double* trans, double* twist)
 RGBID_HD void unpack_system(const double* s27, double* A36, double* b6)
 {
   int shift = 0;
+  RGBID_UNROLL
   for (int i = 0; i < 6; ++i)
+    RGBID_UNROLL
     for (int j = i; j < 7; ++j) {
       double v = s27[shift++];
       if (j == 6) b6[i] = v;
@@ -155,29 +177,46 @@ RGBID_HD void unpack_system(const double* s27, double* A36, double* b6)
 // A non-SPD matrix yields NaN in x, which reaches the NaN-pose guard exactly as in the reference.
 RGBID_HD void llt_solve6(const double* A, const double* b, double* x)
 {
-  double L[36];
+  // One reciprocal square root per column instead of a square root and (5 - j) + 2 divisions: this runs in a
+  // single thread at the end of every Gauss-Newton launch while the rest of the GPU waits, and a double-precision
+  // division is a ~40-instruction dependent chain there.
+  double L[36], inv[6];
+  RGBID_UNROLL
   for (int i = 0; i < 36; ++i) L[i] = 0.0;
+  RGBID_UNROLL
   for (int j = 0; j < 6; ++j) {
     double d = A[j * 6 + j];
+    RGBID_UNROLL
     for (int k = 0; k < j; ++k) d -= L[j * 6 + k] * L[j * 6 + k];
-    double ljj = sqrt(d);
-    L[j * 6 + j] = ljj;
+#if defined(__CUDA_ARCH__)
+    const double r = rsqrt(d);
+#else
+    const double r = 1.0 / sqrt(d);
+#endif
+    inv[j] = r;
+    L[j * 6 + j] = d * r;
+    RGBID_UNROLL
     for (int i = j + 1; i < 6; ++i) {
       double s = A[i * 6 + j];
+      RGBID_UNROLL
       for (int k = 0; k < j; ++k) s -= L[i * 6 + k] * L[j * 6 + k];
-      L[i * 6 + j] = s / ljj;
+      L[i * 6 + j] = s * r;
     }
   }
   double y[6];
+  RGBID_UNROLL
   for (int i = 0; i < 6; ++i) {
     double s = b[i];
+    RGBID_UNROLL
     for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * y[k];
-    y[i] = s / L[i * 6 + i];
+    y[i] = s * inv[i];
   }
+  RGBID_UNROLL
   for (int i = 5; i >= 0; --i) {
     double s = y[i];
+    RGBID_UNROLL
     for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * x[k];
-    x[i] = s / L[i * 6 + i];
+    x[i] = s * inv[i];
   }
 }
 
@@ -185,20 +224,27 @@ RGBID_HD void llt_solve6(const double* A, const double* b, double* x)
 RGBID_HD bool inverse6(const double* A, double* Ai)
 {
   double M[6][12];
+  RGBID_UNROLL
   for (int i = 0; i < 6; ++i)
+    RGBID_UNROLL
     for (int j = 0; j < 6; ++j) { M[i][j] = A[i * 6 + j]; M[i][6 + j] = (i == j) ? 1.0 : 0.0; }
+  RGBID_UNROLL
   for (int c = 0; c < 6; ++c) {
     int p = c;
+    RGBID_UNROLL
     for (int r = c + 1; r < 6; ++r) if (fabs(M[r][c]) > fabs(M[p][c])) p = r;
     if (M[p][c] == 0.0) return false;
     if (p != c) for (int j = 0; j < 12; ++j) { double t = M[c][j]; M[c][j] = M[p][j]; M[p][j] = t; }
     double ip = 1.0 / M[c][c];
+    RGBID_UNROLL
     for (int j = 0; j < 12; ++j) M[c][j] *= ip;
+    RGBID_UNROLL
     for (int r = 0; r < 6; ++r) if (r != c) {
       double f = M[r][c];
       if (f != 0.0) for (int j = 0; j < 12; ++j) M[r][j] -= f * M[c][j];
     }
   }
+  RGBID_UNROLL
   for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) Ai[i * 6 + j] = M[i][6 + j];
   return true;
 }
@@ -212,10 +258,13 @@ RGBID_HD bool gn_update(const double* x, double* R, double* t)
   mat3_inverse(Rinc_inv, Rinc);
   mat3_vec(Rinc, x, tinc);
   mat3_vec(Rinc, t, tn);
+  RGBID_UNROLL
   for (int k = 0; k < 3; ++k) t[k] = tn[k] - tinc[k];
   mat3_mul(Rinc, R, R);
   double nr = 0, nt = 0;
+  RGBID_UNROLL
   for (int k = 0; k < 9; ++k) nr += R[k] * R[k];
+  RGBID_UNROLL
   for (int k = 0; k < 3; ++k) nt += t[k] * t[k];
   return (nr != nr) || (nt != nt);
 }
@@ -225,16 +274,22 @@ RGBID_HD void projective_pose(const double* R, const double* t, float fx, float 
                               float* Rp, float* tp)
 {
   float Rf[9], T[9];
+  RGBID_UNROLL
   for (int k = 0; k < 9; ++k) Rf[k] = (float)R[k];
   float tf0 = (float)t[0], tf1 = (float)t[1], tf2 = (float)t[2];
   const float K[9] = {fx, 0.f, cx, 0.f, fy, cy, 0.f, 0.f, 1.f};
   const float Ki[9] = {1.f / fx, 0.f, -cx / fx, 0.f, 1.f / fy, -cy / fy, 0.f, 0.f, 1.f};
+  RGBID_UNROLL
   for (int i = 0; i < 3; ++i)
+    RGBID_UNROLL
     for (int j = 0; j < 3; ++j)
       T[3 * i + j] = K[3 * i] * Rf[j] + K[3 * i + 1] * Rf[3 + j] + K[3 * i + 2] * Rf[6 + j];
+  RGBID_UNROLL
   for (int i = 0; i < 3; ++i)
+    RGBID_UNROLL
     for (int j = 0; j < 3; ++j)
       Rp[3 * i + j] = T[3 * i] * Ki[j] + T[3 * i + 1] * Ki[3 + j] + T[3 * i + 2] * Ki[6 + j];
+  RGBID_UNROLL
   for (int i = 0; i < 3; ++i) tp[i] = K[3 * i] * tf0 + K[3 * i + 1] * tf1 + K[3 * i + 2] * tf2;
 }
 

@@ -1,5 +1,5 @@
 """Instruction mix of the main loop of a kernel from cuobjdump -sass (static count between the loop head and the
-smallest backward branch that contains the FMA work).  Usage: python tools/sass_mix.py <obj-or-so> <substring of kernel name> [px per iteration]"""
+largest loop that contains the gathers and the FMA work but not the final reduction).  Usage: python tools/sass_mix.py <obj-or-so> <substring of kernel name> [px per iteration]"""
 import collections
 import re
 import subprocess
@@ -28,9 +28,9 @@ def main():
                 if m and int(m.group(1), 16) < int(a, 16):
                     span = int(a, 16) - int(m.group(1), 16)
                     lo_i = addr.get(int(m.group(1), 16), 0)
-                    has_tex = any(o.startswith(("TEX", "LDG")) for _, _, o, _ in ins[lo_i:i + 1]) and \
-                        sum(o.startswith("FFMA") for _, _, o, _ in ins[lo_i:i + 1]) > 50
-                    if has_tex and (best is None or span < best[0]):
+                    ops = [o.split(".")[0] for _, _, o, _ in ins[lo_i:i + 1]]
+                    ok = ("TEX" in ops or "LDG" in ops) and "SHFL" not in ops and ops.count("FFMA") + 2 * ops.count("FFMA2") > 50
+                    if ok and (best is None or span > best[0]):
                         best = (span, lo_i, i)
         if best is None:
             print(name, ": no loop"); continue

@@ -18,6 +18,9 @@ __global__ void __launch_bounds__(256) kern(float* out, long long* cyc, float a,
   int ii[UNR];
   for (int j = 0; j < UNR; ++j) { r[j] = threadIdx.x * 0.001f + j; q[j] = pk(r[j], r[j] + 1.f); ii[j] = threadIdx.x + j; }
   u64 pa = pk(a, b), pb = pk(b, a);
+  float x[UNR], y[UNR]; u64 q2[UNR];
+  for (int j = 0; j < UNR; ++j) { x[j] = a + j * 0.01f + threadIdx.x * 1e-6f; y[j] = b - j * 0.02f; q2[j] = pk(x[j], y[j]); }
+  int flag = (a > 0.f) ? (threadIdx.x | 1) : 0;
   long long t0 = clock64();
   for (int it = 0; it < N_IT; ++it) {
 #pragma unroll
@@ -32,11 +35,16 @@ __global__ void __launch_bounds__(256) kern(float* out, long long* cyc, float a,
       if (MODE == 7) { r[j] = fmaf(r[j], a, b); asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(q[j]) : "l"(pa), "l"(pb)); }
       if (MODE == 8) r[j] = r[j] + a;                                              // FADD
       if (MODE == 9) { r[j] = fmaf(r[j], a, b); r[j] = fmaxf(r[j], a); }           // FFMA + FMNMX(alu)
+      if (MODE == 10) r[j] = fmaf(x[j], y[(j + 5) % UNR], r[j]);                   // FFMA, three distinct registers
+      if (MODE == 11) asm volatile("{.reg .pred p; setp.ne.s32 p, %3, 0; @p fma.rn.f32 %0, %1, %2, %0;}" : "+f"(r[j]) : "f"(x[j]), "f"(y[(j + 5) % UNR]), "r"(flag));
+      if (MODE == 12) asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(q[j]) : "l"(q2[j]), "l"(q2[(j + 5) % UNR]));
+      if (MODE == 13) { r[j] = fmaf(x[j], y[(j + 5) % UNR], r[j]); r[j] = fmaxf(r[j], x[(j + 3) % UNR]); }  // FFMA + FMNMX distinct regs
+      if (MODE == 14) { r[j] = fmaf(x[j], y[(j + 5) % UNR], r[j]); asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(x[j])); }
     }
   }
   long long t1 = clock64();
   float s = 0.f;
-  for (int j = 0; j < UNR; ++j) s += r[j] + lo(q[j]) + ii[j];
+  for (int j = 0; j < UNR; ++j) s += r[j] + lo(q[j]) + ii[j] + x[j] + y[j] + lo(q2[j]);
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
@@ -57,7 +65,8 @@ void run(const char* name, int instr_per_j, cudaTextureObject_t tex, int warps_p
   long long h[148 * 8]; cudaMemcpy(h, cyc, nb * 8, cudaMemcpyDeviceToHost);
   double c = 0; for (int i = 0; i < nb; ++i) c += h[i]; c /= nb;
   double winstr = (double)N_IT * UNR * instr_per_j * warps_per_sm;  // warp instructions per SM
-  printf("%-28s warps/SM %2d : %.3f warp-instr/clk/SM (%.3f per SMSP), %.1f us, %s\n", name, warps_per_sm, winstr / c,
+  double ev = winstr / (ms * 1e-3 * 1.965e9);  // per SM per clock from the event time at 1965 MHz
+  printf("%-28s warps/SM %2d : %.3f warp-instr/clk/SMSP (events), %.3f (clock64), %.1f us, %s\n", name, warps_per_sm, ev / 4,
          winstr / c / 4, ms * 1e3, cudaGetErrorString(cudaGetLastError()));
   cudaFree(out); cudaFree(cyc);
 }
@@ -70,7 +79,7 @@ int main()
   cudaTextureDesc td = {}; td.filterMode = cudaFilterModeLinear; td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
   td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
   cudaTextureObject_t tex; cudaCreateTextureObject(&tex, &rd, &td, nullptr);
-  for (int w : {8, 16, 32}) {
+  for (int w : {16}) {
     run<0>("FFMA r,r,r", 1, tex, w);
     run<1>("FFMA2", 1, tex, w);
     run<2>("FMUL2", 1, tex, w);
@@ -79,6 +88,11 @@ int main()
     run<7>("FFMA + FFMA2", 2, tex, w);
     run<8>("FADD", 1, tex, w);
     run<9>("FFMA + FMNMX", 2, tex, w);
+    run<10>("FFMA 3 distinct regs", 1, tex, w);
+    run<11>("@p FFMA 3 distinct regs", 1, tex, w);
+    run<12>("FFMA2 3 distinct pairs", 1, tex, w);
+    run<13>("FFMA + FMNMX distinct", 2, tex, w);
+    run<14>("FFMA + MUFU.RCP", 2, tex, w);
   }
   run<6>("TEX 2D linear (same texel)", 1, tex, 16);
   return 0;
