@@ -122,6 +122,53 @@ __global__ void __launch_bounds__(BX* BY) pyr_down2_kernel(ImgB srcA, ImgB dstA,
   dst.row(b, y)[x] = (count > 12) ? sum1 / sum2 : qnanf();
 }
 
+// Two horizontally adjacent outputs per thread from three vector loads per source row (the scalar kernel above issues
+// 25 loads per output).  Same taps in the same order (rows, then columns, ascending), the six distinct Gaussian
+// weights evaluated once with the reference's expression, taps outside the image treated as NaN = skipped.
+__global__ void __launch_bounds__(BX* BY) pyr_down2_vec_kernel(ImgB srcA, ImgB dstA, ImgB srcB, ImgB dstB, int batch,
+                                                                const int* __restrict__ active)
+{
+  const int z = blockIdx.z;
+  const int b = z % batch;
+  RGBID_ACTIVE_GUARD(b);
+  const ImgB& src = (z < batch) ? srcA : srcB;
+  const ImgB& dst = (z < batch) ? dstA : dstB;
+  const int xp = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (2 * xp >= dst.cols || y >= dst.rows) return;
+  // weight(space2) = __expf(-(space2 * 0.5f)), space2 = dx^2 + dy^2 in {0, 1, 2, 4, 5, 8}
+  const float wt[3][3] = {{__expf(-(0.f * 0.5f)), __expf(-(1.f * 0.5f)), __expf(-(4.f * 0.5f))},
+                          {__expf(-(1.f * 0.5f)), __expf(-(2.f * 0.5f)), __expf(-(5.f * 0.5f))},
+                          {__expf(-(4.f * 0.5f)), __expf(-(5.f * 0.5f)), __expf(-(8.f * 0.5f))}};
+  const float nan = qnanf();
+  const bool has_left = xp > 0, has_right = 4 * xp + 4 < src.cols;
+  float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
+  int ca = 0, cb = 0;
+#pragma unroll
+  for (int dy = -2; dy <= 2; ++dy) {
+    const int cy = 2 * y + dy;
+    if (cy < 0 || cy >= src.rows) continue;
+    const float* srow = src.row(b, cy) + 4 * xp;
+    const float4 M = __ldg((const float4*)srow);
+    float4 L = make_float4(nan, nan, nan, nan);
+    if (has_left) L = __ldg((const float4*)(srow - 4));
+    const float R = has_right ? __ldg(srow + 4) : nan;
+    const int ady = dy < 0 ? -dy : dy;
+    const float va[5] = {L.z, L.w, M.x, M.y, M.z};  // output 2 xp    : source columns 4 xp - 2 .. 4 xp + 2
+    const float vb[5] = {M.x, M.y, M.z, M.w, R};    // output 2 xp + 1: source columns 4 xp     .. 4 xp + 4
+#pragma unroll
+    for (int dx = -2; dx <= 2; ++dx) {
+      const float w = wt[ady][dx < 0 ? -dx : dx];
+      const float a = va[dx + 2], c = vb[dx + 2];
+      if (!isnan(a)) { s1a += a * w; s2a += w; ++ca; }
+      if (!isnan(c)) { s1b += c * w; s2b += w; ++cb; }
+    }
+  }
+  float2 out;
+  out.x = (ca > 12) ? s1a / s2a : nan;
+  out.y = (cb > 12) ? s1b / s2b : nan;
+  *(float2*)(dst.row(b, y) + 2 * xp) = out;
+}
+
 // ---- gradients: K21 (src/cuda/misc.cu:176-220) ----------------------------------------------------
 __global__ void __launch_bounds__(BX* BY) gradient2_kernel(ImgB srcA, ImgB gxA, ImgB gyA, ImgB srcB, ImgB gxB,
                                                             ImgB gyB, int batch, const int* __restrict__ active)
@@ -149,6 +196,46 @@ __global__ void __launch_bounds__(BX* BY) gradient2_kernel(ImgB srcA, ImgB gxA, 
   }
   gx.row(b, y)[x] = rh / 8.f;
   gy.row(b, y)[x] = rv / 8.f;
+}
+
+// Four pixels per thread: per source row one float4 plus the two clamped neighbours instead of 9 scalar loads per
+// pixel; same taps, same order, same zero weights as above, float4 stores.
+__global__ void __launch_bounds__(BX* BY) gradient2_vec_kernel(ImgB srcA, ImgB gxA, ImgB gyA, ImgB srcB, ImgB gxB,
+                                                                ImgB gyB, int batch, const int* __restrict__ active)
+{
+  const int z = blockIdx.z;
+  const int b = z % batch;
+  RGBID_ACTIVE_GUARD(b);
+  const ImgB& src = (z < batch) ? srcA : srcB;
+  const ImgB& gx = (z < batch) ? gxA : gxB;
+  const ImgB& gy = (z < batch) ? gyA : gyB;
+  const int x0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x), y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x0 >= src.cols || y >= src.rows) return;
+  float v[3][6];
+#pragma unroll
+  for (int dy = -1; dy < 2; ++dy) {
+    const float* srow = src.row(b, min(max(0, y + dy), src.rows - 1));
+    const float4 c = __ldg((const float4*)(srow + x0));
+    v[dy + 1][0] = __ldg(srow + max(x0 - 1, 0));
+    v[dy + 1][1] = c.x; v[dy + 1][2] = c.y; v[dy + 1][3] = c.z; v[dy + 1][4] = c.w;
+    v[dy + 1][5] = __ldg(srow + min(x0 + 4, src.cols - 1));
+  }
+  float rh[4], rv[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    rh[k] = 0.f; rv[k] = 0.f;
+#pragma unroll
+    for (int dx = -1; dx < 2; ++dx) {
+#pragma unroll
+      for (int dy = -1; dy < 2; ++dy) {
+        const float t = v[dy + 1][k + dx + 1];
+        rh[k] += t * (float)(dx * (2 - dy * dy));
+        rv[k] += t * (float)(dy * (2 - dx * dx));
+      }
+    }
+  }
+  *(float4*)(gx.row(b, y) + x0) = make_float4(rh[0] / 8.f, rh[1] / 8.f, rh[2] / 8.f, rh[3] / 8.f);
+  *(float4*)(gy.row(b, y) + x0) = make_float4(rv[0] / 8.f, rv[1] / 8.f, rv[2] / 8.f, rv[3] / 8.f);
 }
 
 // ---- bilateral: K23 (src/cuda/filters.cu:86-135) ----------------------------------------------------
@@ -197,6 +284,18 @@ __global__ void copy2_kernel(ImgB srcA, ImgB dstA, ImgB srcB, ImgB dstB, int bat
   int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= src.cols || y >= src.rows) return;
   dst.row(b, y)[x] = src.row(b, y)[x];
+}
+
+__global__ void copy2_vec_kernel(ImgB srcA, ImgB dstA, ImgB srcB, ImgB dstB, int batch, const int* __restrict__ active)
+{
+  const int z = blockIdx.z;
+  const int b = z % batch;
+  RGBID_ACTIVE_GUARD(b);
+  const ImgB& src = (z < batch) ? srcA : srcB;
+  const ImgB& dst = (z < batch) ? dstA : dstB;
+  const int x0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x), y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x0 >= src.cols || y >= src.rows) return;
+  *(float4*)(dst.row(b, y) + x0) = *(const float4*)(src.row(b, y) + x0);
 }
 
 __global__ void fill_kernel(ImgB dst, float value, const int* __restrict__ active)
@@ -311,8 +410,16 @@ void launch_decompose_rgb(const LaunchCtx& L, const uint8_t* rgb, size_t spitch,
 void launch_pyr_down2(const LaunchCtx& L, ImgB srcA, ImgB dstA, ImgB srcB, ImgB dstB, int batch, const int* active)
 {
   int nm = srcB.p ? 2 : 1;
-  pyr_down2_kernel<<<grid2d(dstA.cols, dstA.rows, batch * nm), dim3(BX, BY), 0, L.stream>>>(srcA, dstA, srcB, dstB,
-                                                                                            batch, active);
+  auto vec_ok = [](const ImgB& s, const ImgB& d) {
+    return s.cols % 4 == 0 && d.cols * 2 == s.cols && aligned(s.p, 16) && s.pitch % 16 == 0 && s.sstride % 16 == 0 &&
+           aligned(d.p, 8) && d.pitch % 8 == 0 && d.sstride % 8 == 0;
+  };
+  if (vec_ok(srcA, dstA) && (nm == 1 || vec_ok(srcB, dstB)))
+    pyr_down2_vec_kernel<<<grid2d(dstA.cols / 2, dstA.rows, batch * nm), dim3(BX, BY), 0, L.stream>>>(srcA, dstA, srcB,
+                                                                                                 dstB, batch, active);
+  else
+    pyr_down2_kernel<<<grid2d(dstA.cols, dstA.rows, batch * nm), dim3(BX, BY), 0, L.stream>>>(srcA, dstA, srcB, dstB,
+                                                                                              batch, active);
   ++*L.launches;
 }
 
@@ -320,8 +427,15 @@ void launch_gradient2(const LaunchCtx& L, ImgB srcA, ImgB gxA, ImgB gyA, ImgB sr
                       const int* active)
 {
   int nm = srcB.p ? 2 : 1;
-  gradient2_kernel<<<grid2d(srcA.cols, srcA.rows, batch * nm), dim3(BX, BY), 0, L.stream>>>(srcA, gxA, gyA, srcB, gxB,
-                                                                                            gyB, batch, active);
+  auto v16 = [](const ImgB& m) { return aligned(m.p, 16) && m.pitch % 16 == 0 && m.sstride % 16 == 0; };
+  bool vec = srcA.cols % 4 == 0 && v16(srcA) && v16(gxA) && v16(gyA);
+  if (nm == 2) vec = vec && v16(srcB) && v16(gxB) && v16(gyB);
+  if (vec)
+    gradient2_vec_kernel<<<grid2d(srcA.cols / 4, srcA.rows, batch * nm), dim3(BX, BY), 0, L.stream>>>(
+        srcA, gxA, gyA, srcB, gxB, gyB, batch, active);
+  else
+    gradient2_kernel<<<grid2d(srcA.cols, srcA.rows, batch * nm), dim3(BX, BY), 0, L.stream>>>(srcA, gxA, gyA, srcB,
+                                                                                              gxB, gyB, batch, active);
   ++*L.launches;
 }
 
@@ -337,8 +451,15 @@ void launch_bilateral2(const LaunchCtx& L, ImgB srcA, ImgB dstA, float sigmaA, I
 void launch_copy2(const LaunchCtx& L, ImgB srcA, ImgB dstA, ImgB srcB, ImgB dstB, int batch, const int* active)
 {
   int nm = srcB.p ? 2 : 1;
-  copy2_kernel<<<grid2d(srcA.cols, srcA.rows, batch * nm), dim3(BX, BY), 0, L.stream>>>(srcA, dstA, srcB, dstB, batch,
-                                                                                        active);
+  auto v16 = [](const ImgB& m) { return aligned(m.p, 16) && m.pitch % 16 == 0 && m.sstride % 16 == 0; };
+  bool vec = srcA.cols % 4 == 0 && v16(srcA) && v16(dstA);
+  if (nm == 2) vec = vec && v16(srcB) && v16(dstB);
+  if (vec)
+    copy2_vec_kernel<<<grid2d(srcA.cols / 4, srcA.rows, batch * nm), dim3(BX, BY), 0, L.stream>>>(srcA, dstA, srcB, dstB,
+                                                                                             batch, active);
+  else
+    copy2_kernel<<<grid2d(srcA.cols, srcA.rows, batch * nm), dim3(BX, BY), 0, L.stream>>>(srcA, dstA, srcB, dstB, batch,
+                                                                                          active);
   ++*L.launches;
 }
 
