@@ -49,6 +49,9 @@ struct rgbid_aligner {
   cudaGraphExec_t gn_exec;
   long long gn_graph_launches;
   int image_filtering;
+  // second stream + fork / join events: the schedule is issued as two chains of frame-pair groups
+  cudaStream_t side_stream;
+  cudaEvent_t ev_fork, ev_join;
   // texture objects over the current-frame pyramid: [level][0: W point | 1: I linear][batch]
   bool use_tex;
   cudaTextureObject_t* h_tex;

@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
                     unsigned int* __restrict__ counters, rgbid_iter_trace* __restrict__ trace)
 {
   constexpr int NACC = CHI ? kAccChi : kAcc;
-  const int b = blockIdx.y;
+  const int b = blockIdx.y + P.first;
   GnState& st = states[b];
   if (st.status != RGBID_OK) return;  // lost pairs are skipped consistently by every CTA
   __shared__ BuildShared sh;
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
   extern __shared__ __align__(128) unsigned char ring[];
   __shared__ BuildShared sh;
   __shared__ __align__(8) unsigned long long bars[kBuildWarps * (kStagesW + kStagesL)];
-  const int b = blockIdx.y;
+  const int b = blockIdx.y + P.first;
   GnState& st = states[b];
   if (st.status != RGBID_OK) return;  // lost pairs are skipped consistently by every CTA
   const int tid = threadIdx.x, lane = tid & 31;
@@ -844,7 +844,7 @@ __global__ void __cluster_dims__(kScaleCluster, 1, 1) __launch_bounds__(kScaleTh
   extern __shared__ float smem_samples[];
   __shared__ ScaleShared sh;
   __shared__ Proj s_proj;
-  const int b = blockIdx.x / kScaleCluster;
+  const int b = blockIdx.x / kScaleCluster + P.first;
   const int rank = (int)cluster.block_rank();
   const GnState& st = states[b];
   if (st.status != RGBID_OK) return;  // uniform over the whole cluster
@@ -998,7 +998,7 @@ void launch_gn_build(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P
     G.colsf = (float)P.cols; G.inv_cols = 1.f / (float)P.cols;
     G.inv_hx = 2.f / (float)P.cols; G.inv_hy = 2.f / (float)P.rows;
     // one balanced wave of 2 CTAs / SM over all pairs; a pair never gets more CTAs than it has 8-chunk groups
-    int cap = (2 * L.num_sms) / P.batch;
+    int cap = (2 * L.num_sms) / (P.batch_total > 0 ? P.batch_total : P.batch);
     if (cap < 1) cap = 1;
     if (cap > L.num_sms) cap = L.num_sms;
     int gx = (G.nchunks + kBuildWarps - 1) / kBuildWarps;
@@ -1021,7 +1021,7 @@ void launch_gn_build(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P
     ++*L.launches;
     return;
   }
-  dim3 grid(gn_build_grid_x(P.rows, P.cols, P.batch, L.num_sms), P.batch);
+  dim3 grid(gn_build_grid_x(P.rows, P.cols, P.batch_total > 0 ? P.batch_total : P.batch, L.num_sms), P.batch);
   if (vec) {
     if (chi) launch_gn_build_t<4, true>(L, grid, tex, M, P, states, scales, partials, partial_stride, counters, trace);
     else launch_gn_build_t<4, false>(L, grid, tex, M, P, states, scales, partials, partial_stride, counters, trace);

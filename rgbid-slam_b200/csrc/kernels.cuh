@@ -111,6 +111,8 @@ struct GnParams {
   int kept_rows, kept_cols, sample_stride;  // residual sampling geometry of this level
   int sigma_op;                 // ScaleOp used by the sampling kernel
   int next_level;               // level of the launch that consumes the updated pose (-1: refresh proj[] of all levels)
+  int first;                    // first frame pair of this launch (the batch may be launched in groups, see aligner.cu)
+  int batch_total;              // pairs of the whole batch (grid sizing); 0: same as batch
 };
 
 // fused warp + sample + residual -> IRLS sigma / nu (8-CTA cluster per pair)
