@@ -174,6 +174,8 @@ def run_b200(args, world, rank, local):
         with torch.cuda.stream(ctx.stream):
             e0.record()
             for k in range(K):
+                if host_path and k + 1 < K and not os.environ.get("RGBID_BENCH_NO_PREFETCH"):
+                    trk.prefetch(frames_d[k + 1], frames_c[k + 1])  # upload of the next frame overlaps this one
                 res = trk.track(frames_d[k], frames_c[k])
                 if gather:
                     gather(res)
@@ -241,7 +243,10 @@ def run_b200(args, world, rank, local):
                                     % (S * 39.0)},
             "clocks": clocks,
             "e2e": {"value": total_frames / e2e_s, "unit": UNIT, "h2d_bytes_per_step": bytes_in,
-                    "d2h_bytes_per_step": int(S * 1208)},  # per stream: solver state 1176 B + 8 covisibility counters
+                    "d2h_bytes_per_step": int(S * 1208),  # per stream: solver state 1176 B + 8 covisibility counters
+                    "device_ms_per_step": e2e_dev_s / K * 1e3, "wall_ms_per_step": e2e_wall_s / K * 1e3,
+                    "upload": "next frame prefetched on a copy stream (rgbid_tracker_prefetch)"
+                              if not os.environ.get("RGBID_BENCH_NO_PREFETCH") else "inside rgbid_tracker_track"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "gn_build_kernel<4,false> level 0 (fused warp+residual+JtJ)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -291,6 +291,12 @@ int rgbid_tracker_reset(rgbid_tracker* trk);
  * results_host: batch entries.  Synchronous (the reference's trackNewFrame is). */
 int rgbid_tracker_track(rgbid_tracker* trk, const uint16_t* depth, const uint8_t* rgb, int from_host,
                         rgbid_frame_result* results_host);
+/* Optional: start the host->device upload of the NEXT frame (same layout as rgbid_tracker_track with from_host != 0)
+ * on a copy stream and return immediately.  A following rgbid_tracker_track(trk, depth, rgb, 1, ...) with the same two
+ * pointers uses the uploaded copy instead of copying again, so the upload overlaps the tracking of the current frame
+ * (the reference uploads and tracks strictly one after the other, tools/RGBID_SLAMapp.cpp:163-214).  One frame may be
+ * in flight; the host buffers must stay valid and unchanged until that track call returns. */
+int rgbid_tracker_prefetch(rgbid_tracker* trk, const uint16_t* depth, const uint8_t* rgb);
 /* Same with pitched DEVICE buffers (what VisodoTracker::depth_ / rgb24_ are: DeviceArray2D, include/visodo.h:118-119):
  * row pitch and per-stream stride in bytes (stride is ignored when batch == 1). */
 int rgbid_tracker_track_device(rgbid_tracker* trk, const uint16_t* depth, size_t depth_pitch, size_t depth_stride,

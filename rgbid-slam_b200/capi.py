@@ -111,6 +111,7 @@ PROTOTYPES = {
     "rgbid_tracker_destroy": (I, [P]),
     "rgbid_tracker_reset": (I, [P]),
     "rgbid_tracker_track": (I, [P, P, P, I, C.POINTER(FrameResult)]),
+    "rgbid_tracker_prefetch": (I, [P, P, P]),
     "rgbid_tracker_track_device": (I, [P, P, SZ, SZ, P, SZ, SZ, C.POINTER(FrameResult)]),
     "rgbid_tracker_keyframe_map": (I, [P, I, I, C.POINTER(P), C.POINTER(SZ)]),
     "rgbid_tracker_overlap_mask": (I, [P, I, C.POINTER(P), C.POINTER(SZ)]),

@@ -452,6 +452,16 @@ class Tracker:
         capi.check(self.lib.rgbid_tracker_track(self.h, pd, pc, host, self.results), "tracker_track")
         return self.results
 
+    def prefetch(self, depth, rgb):
+        """Start uploading the NEXT frame (CPU tensors / numpy arrays, ideally pinned) while the current one is tracked;
+        the following track(depth, rgb) with the same buffers uses the uploaded copy."""
+        if isinstance(depth, torch.Tensor):
+            assert not depth.is_cuda
+            pd, pc = depth.data_ptr(), rgb.data_ptr()
+        else:
+            pd, pc = depth.ctypes.data, rgb.ctypes.data
+        capi.check(self.lib.rgbid_tracker_prefetch(self.h, pd, pc), "tracker_prefetch")
+
     @property
     def aligner_handle(self):
         return C.c_void_p(self.lib.rgbid_tracker_aligner(self.h))

@@ -230,3 +230,26 @@ def test_tracker_sequence(ctx, kind):
     m = ~(np.isnan(fused) | np.isnan(want))
     assert np.mean(np.abs(fused[m] - want[m]) / want[m] < 1e-4) > 0.999
     trk.close()
+
+
+def test_tracker_prefetch_is_the_same_tracker(ctx):
+    """rgbid_tracker_prefetch uploads frame k + 1 on a copy stream while frame k is tracked; the results must be
+    bit-identical to the plain host path (same kernels on the same bytes)."""
+    rows, cols, n = 240, 320, 6
+    seq = synth.make_sequence(seed=77, n_frames=n, rows=rows, cols=cols, noise=True)
+    acfg = host.make_align_config(rows, cols, 3, capi.MODE_TRACKER, batch=2, **seq["intr"])
+    frames = [(torch.stack([seq["depth"][k]] * 2).contiguous().pin_memory(), torch.stack([seq["rgb"][k]] * 2).contiguous().pin_memory())
+              for k in range(n)]
+    poses = []
+    for use_prefetch in (False, True):
+        trk = host.Tracker(ctx, host.make_tracker_config(acfg))
+        out = []
+        for k in range(n):
+            if use_prefetch and k + 1 < n:
+                trk.prefetch(*frames[k + 1])
+            res = trk.track(*frames[k])
+            out.append((np.array(res[0].R[:]), np.array(res[0].t[:]), res[0].new_odo_keyframe))
+        trk.close()
+        poses.append(out)
+    for (Ra, ta, ka), (Rb, tb, kb) in zip(*poses):
+        assert np.array_equal(Ra, Rb) and np.array_equal(ta, tb) and ka == kb
