@@ -1,0 +1,58 @@
+"""the RGBID_SLAMapp-compatible driver (apps/rgbid_slam_app) on a synthetic TUM-format sequence --
+PNG + association files in, "<stamp> tx ty tz qx qy qz qw" pose log out -- against the restated trackNewFrame on the
+CPU oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from util import rot_angle
+from oracle.tracker import OracleTracker
+from rgbid_slam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+APP = os.path.join(ROOT, "apps", "rgbid_slam_app")
+
+
+def quat_to_R(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def test_app_on_tum_sequence(built, tmp_path):
+    assert os.path.exists(APP), "apps/rgbid_slam_app was not built (see __graft_entry__.build)"
+    rows, cols, n = 240, 320, 6
+    seq = synth.make_sequence(seed=11, n_frames=n, rows=rows, cols=cols, noise=True)
+    intr = seq["intr"]
+    folder = str(tmp_path / "rgbd_dataset_synth")
+    synth.write_tum_sequence(seq, folder)
+    calib = tmp_path / "calibration.ini"
+    calib.write_text("[CALIBRATION]\nfx=%r\nfy=%r\ncx=%r\ncy=%r\n" % (intr["fx"], intr["fy"], intr["cx"], intr["cy"]))
+    config = tmp_path / "visodo.ini"
+    config.write_text("[VISODO]\nM_ESTIMATOR = Student\nSIGMA_ESTIMATOR = sigmaML\nWARP_ORDER = pyrFirst\nIMAGE_FILTERING = none\n")
+    log = tmp_path / "poses.txt"
+    r = subprocess.run([APP, "-eval", folder + "/", "-match_file", "matches.txt", "-calib", str(calib), "-config", str(config),
+                        "-o", str(log)], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "lost 0" in r.stdout
+    rowsf = [[float(v) for v in ln.split()] for ln in log.read_text().splitlines()]
+    assert len(rowsf) == n
+    depth = seq["depth"].numpy().astype(np.uint16)
+    rgb = seq["rgb"].numpy()
+    ot = OracleTracker(rows, cols, intr, levels=3, iterations=(10, 5, 3), kind="cpu")
+    for k in range(n):
+        o = ot.track(depth[k], rgb[k])
+        stamp, t, q = rowsf[k][0], np.array(rowsf[k][1:4]), np.array(rowsf[k][4:8])
+        assert abs(stamp - (1000.0 + k / 30.0)) < 1e-5
+        # the log is written with 6 decimals (ios::fixed, default precision)
+        assert np.linalg.norm(t - o["t"]) < 1e-4 and rot_angle(quat_to_R(q), o["R"]) < 1e-4
+
+    # default log name: "<dataset>_poses.txt" in the working directory (tools/RGBID_SLAMapp.cpp:414-428)
+    r = subprocess.run([APP, "-eval", folder + "/", "-match_file", "matches.txt", "-calib", str(calib), "-n", "2"],
+                       capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert os.path.exists(tmp_path / "rgbd_dataset_synth_poses.txt")
