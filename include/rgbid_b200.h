@@ -281,7 +281,36 @@ typedef struct {
   int status;                 /* RGBID_OK or RGBID_ERR_NAN (lost) */
   int new_odo_keyframe, new_integr_keyframe;
   int frame_index;
+  /* sequential odometry constraint (frame_index - 1 -> frame_index) the reference pushes to the keyframe manager as
+   * PoseConstraint::SEQ_ODO (src/visodo.cpp:2126-2156): relative transform and its propagated 6x6 covariance; the
+   * dummy constraint (identity, 100 I) when tracking was lost (:2068-2071) */
+  double seq_R[9], seq_t[3], seq_cov[36];
 } rgbid_frame_result;
+
+/* ---- keyframe hand-off to the back end (resetIntegrationKeyframe, src/visodo.cpp:1577-1672) ------------------------
+ * When a stream switches its integration keyframe, the OUTGOING keyframe is handed to the sink: its creation index and
+ * global pose, the SEQ_KF constraint from the previous keyframe with the covariance propagated through the
+ * odometry-keyframe chain, and host copies of its overlap mask, colours, fused inverse depth and normals (what the
+ * reference downloads into a Keyframe, :1639-1642).  The pointers are valid only during the callback, which runs inside
+ * rgbid_tracker_track on the calling thread. */
+enum { RGBID_SEQ_ODO = 0, RGBID_SEQ_KF = 1 };
+typedef struct rgbid_keyframe_handoff {
+  int stream;                  /* index in the batch */
+  int kf_index;                /* frame at which this keyframe was created (last_integrKF_index_) */
+  int frame_index;             /* frame that replaces it (global_time_) */
+  int rows, cols;
+  float fx, fy, cx, cy;
+  double R[9], t[3];           /* global pose of the keyframe */
+  double rel_R[9], rel_t[3];   /* SEQ_KF constraint kf_index -> frame_index ... */
+  double rel_cov[36];          /* ... and its covariance */
+  const uint8_t* overlap_mask; size_t overlap_mask_pitch;   /* rows x cols */
+  const uint8_t* colors;       /* rows x cols x 3, dense */
+  const float* depthinv; size_t depthinv_pitch;             /* rows x cols, fused */
+  const float* normals; size_t normals_pitch;               /* 3 rows x cols (x, y, z planes) */
+} rgbid_keyframe_handoff;
+typedef void (*rgbid_keyframe_sink)(void* user, const rgbid_keyframe_handoff* keyframe);
+/* cb == NULL removes the sink (then nothing is downloaded at a keyframe switch) */
+int rgbid_tracker_set_keyframe_sink(rgbid_tracker* trk, rgbid_keyframe_sink cb, void* user);
 
 int rgbid_tracker_create(rgbid_ctx* ctx, const rgbid_tracker_config* cfg, rgbid_tracker** out);
 int rgbid_tracker_destroy(rgbid_tracker* trk);

@@ -75,6 +75,22 @@ def backend(kind):
     return _CpuBackend() if kind == "cpu" else _RefBackend()
 
 
+def _skew(v):
+    return np.array([[0.0, -v[2], v[1]], [v[2], 0.0, -v[0]], [-v[1], v[0], 0.0]])
+
+
+def relative_constraint(R_last, t_last, cov_last, R_new, t_new, cov_new):
+    """Relative transform between two poses given in the same frame and its first-order covariance: the SEQ_ODO
+    constraint of src/visodo.cpp:2126-2146 and the SEQ_KF constraint of :1610-1629 (same formulas)."""
+    Rt = R_last.T
+    R, t = Rt @ R_new, Rt @ (t_new - t_last)
+    Jn, Jl = np.zeros((6, 6)), np.zeros((6, 6))
+    Jn[:3, :3], Jn[3:, 3:] = Rt, Rt
+    Jl[:3, :3], Jl[3:, 3:] = -Rt, -Rt
+    Jl[:3, 3:] = _skew(t) @ Rt
+    return R, t, Jl @ cov_last @ Jl.T + Jn @ cov_new @ Jn.T
+
+
 class OracleTracker:
     def __init__(self, rows, cols, intr, levels=3, iterations=(10, 5, 3), kind="cpu", motion_model=True,
                  visratio_odo=0.9, visratio_integr=0.7, delta_t=0.03333, mestimator=orc.STUDENT,
@@ -99,6 +115,20 @@ class OracleTracker:
         self.vel, self.omega = np.zeros(3), np.zeros(3)
         self.kf = None
         self.wstate = None
+        # delta_*_odo2integr_{last,next}_ and last_integrKF_index_ (src/visodo.cpp:1553-1670)
+        self.o2i_next = [np.eye(3), np.zeros(3), np.zeros((6, 6))]
+        self.o2i_last = [np.eye(3), np.zeros(3), np.zeros((6, 6))]
+        self.last_integrKF_index = 0
+
+    def _chain_compose(self):
+        """T_new = T_old * T_upd on the odometry-keyframe -> integration-keyframe chain: the common part of
+        resetOdometryKeyframe (:1553-1566) and resetIntegrationKeyframe (:1592-1605)."""
+        Rn, tn, Cn = self.o2i_next
+        J = np.zeros((6, 6))
+        J[:3, :3], J[3:, 3:] = Rn, Rn
+        t_new = Rn @ self.dt_
+        J[:3, 3:] = _skew(t_new)
+        self.o2i_next = [Rn @ self.dR, t_new + tn, Cn + J @ self.dcov @ J.T]
 
     def _proj(self, R, t, inverse):
         i = self.intr
@@ -139,7 +169,7 @@ class OracleTracker:
             res.update(R=np.eye(3), t=np.zeros(3), dR=np.eye(3), dt=np.zeros(3), cov=np.zeros((6, 6)),
                        new_odo_keyframe=1, new_integr_keyframe=1)
             return res
-        prevR, prevt = self.dR.copy(), self.dt_.copy()
+        prevR, prevt, prevcov = self.dR.copy(), self.dt_.copy(), self.dcov.copy()
         if self.global_time > 1 and self.motion_model and not self.lost:
             dRp, dtp = orc.exp_map(self.omega * float(self.dt), self.vel * float(self.dt))
             Ri, ti = prevR @ dRp, prevR @ dtp + prevt
@@ -171,11 +201,25 @@ class OracleTracker:
             res["visibility_odo"], res["visibility_integr"] = vis_odo, vis_int
             new_odo, new_int = vis_odo < self.vo, vis_int < self.vi
         res["new_odo_keyframe"], res["new_integr_keyframe"] = int(new_odo), int(new_int)
+        # sequential odometry constraint (:2126-2156) or the dummy one when lost (:2068-2071)
+        res["seq"] = relative_constraint(prevR, prevt, prevcov, self.dR, self.dt_, self.dcov) if ok else \
+            (np.eye(3), np.zeros(3), 100.0 * np.eye(6))
+        res["kf_handoff"] = None
         if new_odo:
+            self._chain_compose()
             self.R_odoKF, self.t_odoKF = self.R_est.copy(), self.t_est.copy()
             self.dR, self.dt_, self.dcov = np.eye(3), np.zeros(3), np.zeros((6, 6))
             self.kf = B.prepare_keyframe(W, I, self.levels, tracker=True)
         if new_int:
+            # resetIntegrationKeyframe (:1577-1672): the outgoing keyframe with its SEQ_KF constraint
+            self._chain_compose()
+            kR, kt, kcov = relative_constraint(*self.o2i_last, *self.o2i_next)
+            res["kf_handoff"] = dict(kf_index=self.last_integrKF_index, frame_index=self.global_time, R=self.R_intKF.copy(),
+                                     t=self.t_intKF.copy(), rel_R=kR, rel_t=kt, rel_cov=kcov, depthinv=B.copy(self.intW),
+                                     normals=B.copy(self.nmap))
+            self.last_integrKF_index = self.global_time
+            self.o2i_last = [self.dR.copy(), self.dt_.copy(), self.dcov.copy()]
+            self.o2i_next = [np.eye(3), np.zeros(3), np.zeros((6, 6))]
             self.R_intKF, self.t_intKF = self.R_est.copy(), self.t_est.copy()
             self._save_integration_kf(cur)
         else:

@@ -57,7 +57,21 @@ class FrameResult(C.Structure):
     _fields_ = [("R", C.c_double * 9), ("t", C.c_double * 3), ("dR", C.c_double * 9), ("dt", C.c_double * 3),
                 ("cov", C.c_double * 36), ("visibility_odo", C.c_float), ("visibility_integr", C.c_float),
                 ("chi_square", C.c_float), ("chi_test", C.c_float), ("ndof", C.c_float), ("status", C.c_int),
-                ("new_odo_keyframe", C.c_int), ("new_integr_keyframe", C.c_int), ("frame_index", C.c_int)]
+                ("new_odo_keyframe", C.c_int), ("new_integr_keyframe", C.c_int), ("frame_index", C.c_int),
+                ("seq_R", C.c_double * 9), ("seq_t", C.c_double * 3), ("seq_cov", C.c_double * 36)]
+
+
+class KeyframeHandoff(C.Structure):
+    _fields_ = [("stream", C.c_int), ("kf_index", C.c_int), ("frame_index", C.c_int), ("rows", C.c_int), ("cols", C.c_int),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("R", C.c_double * 9), ("t", C.c_double * 3), ("rel_R", C.c_double * 9), ("rel_t", C.c_double * 3),
+                ("rel_cov", C.c_double * 36),
+                ("overlap_mask", C.c_void_p), ("overlap_mask_pitch", C.c_size_t), ("colors", C.c_void_p),
+                ("depthinv", C.c_void_p), ("depthinv_pitch", C.c_size_t), ("normals", C.c_void_p),
+                ("normals_pitch", C.c_size_t)]
+
+
+KEYFRAME_SINK = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(KeyframeHandoff))
 
 
 P, SZ, I, F = C.c_void_p, C.c_size_t, C.c_int, C.c_float
@@ -112,6 +126,7 @@ PROTOTYPES = {
     "rgbid_tracker_reset": (I, [P]),
     "rgbid_tracker_track": (I, [P, P, P, I, C.POINTER(FrameResult)]),
     "rgbid_tracker_prefetch": (I, [P, P, P]),
+    "rgbid_tracker_set_keyframe_sink": (I, [P, P, P]),
     "rgbid_tracker_track_device": (I, [P, P, SZ, SZ, P, SZ, SZ, C.POINTER(FrameResult)]),
     "rgbid_tracker_keyframe_map": (I, [P, I, I, C.POINTER(P), C.POINTER(SZ)]),
     "rgbid_tracker_overlap_mask": (I, [P, I, C.POINTER(P), C.POINTER(SZ)]),

@@ -26,12 +26,79 @@ struct StreamState {
   double vel[3], omega[3];        // constant-velocity model state
   bool lost;
   int global_time, odoKF_count, integrKF_count;
+  // odometry-keyframe -> integration-keyframe chain (delta_*_odo2integr_{last,next}_, src/visodo.cpp:1553-1566, 1592-1670)
+  double o2i_next_R[9], o2i_next_t[3], o2i_next_cov[36];
+  double o2i_last_R[9], o2i_last_t[3], o2i_last_cov[36];
+  int last_integrKF_index;
 };
 
 void set_identity(double* R, double* t)
 {
   for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
   t[0] = t[1] = t[2] = 0.0;
+}
+
+// ---- 6x6 covariance propagation of the constraint chain (host, double) ---------------------------------------------
+// out += J C J^T
+void add_JCJt(const double* J, const double* C, double* out)
+{
+  double T[36];
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) {
+      double v = 0.0;
+      for (int k = 0; k < 6; ++k) v += J[6 * i + k] * C[6 * k + j];
+      T[6 * i + j] = v;
+    }
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) {
+      double v = 0.0;
+      for (int k = 0; k < 6; ++k) v += T[6 * i + k] * J[6 * j + k];
+      out[6 * i + j] += v;
+    }
+}
+
+void set_block3(double* J, int r0, int c0, const double* M, double sign = 1.0)
+{
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) J[6 * (r0 + i) + c0 + j] = sign * M[3 * i + j];
+}
+
+// T_new = T_old * T_upd on the odo->integration chain: the part resetOdometryKeyframe (src/visodo.cpp:1553-1566) and
+// resetIntegrationKeyframe (:1592-1605) have in common
+void chain_compose(StreamState& S)
+{
+  double J[36] = {0}, tnew[3], K[9], Rn[9];
+  set_block3(J, 0, 0, S.o2i_next_R);
+  set_block3(J, 3, 3, S.o2i_next_R);
+  mat3_vec(S.o2i_next_R, S.dt, tnew);
+  skew3(tnew, K);
+  set_block3(J, 0, 3, K);
+  add_JCJt(J, S.dcov, S.o2i_next_cov);
+  for (int k = 0; k < 3; ++k) S.o2i_next_t[k] = tnew[k] + S.o2i_next_t[k];
+  mat3_mul(S.o2i_next_R, S.dR, Rn);
+  memcpy(S.o2i_next_R, Rn, sizeof(Rn));
+}
+
+// Relative constraint between two poses expressed in the same frame, with first-order covariance
+// (src/visodo.cpp:2126-2146 for SEQ_ODO, :1610-1629 for SEQ_KF):
+//   R = R_last^T R_new, t = R_last^T (t_new - t_last),
+//   cov = dLast cov_last dLast^T + dNew cov_new dNew^T
+void relative_constraint(const double* R_last, const double* t_last, const double* cov_last, const double* R_new,
+                         const double* t_new, const double* cov_new, double* R, double* t, double* cov)
+{
+  double Rt[9], d[3], K[9], KR[9], Jn[36] = {0}, Jl[36] = {0};
+  mat3_transpose(R_last, Rt);
+  mat3_mul(Rt, R_new, R);
+  for (int k = 0; k < 3; ++k) d[k] = t_new[k] - t_last[k];
+  mat3_vec(Rt, d, t);
+  set_block3(Jn, 0, 0, Rt); set_block3(Jn, 3, 3, Rt);
+  set_block3(Jl, 0, 0, Rt, -1.0); set_block3(Jl, 3, 3, Rt, -1.0);
+  skew3(t, K);
+  mat3_mul(K, Rt, KR);
+  set_block3(Jl, 0, 3, KR);
+  for (int i = 0; i < 36; ++i) cov[i] = 0.0;
+  add_JCJt(Jl, cov_last, cov);
+  add_JCJt(Jn, cov_new, cov);
 }
 
 }  // namespace
@@ -50,6 +117,9 @@ struct rgbid_tracker {
   Proj* d_proj; Proj* h_proj;              // [4][batch]: odo cur->KF, odo KF->cur, integr cur->KF, integr KF->cur
   unsigned int* d_counts; unsigned int* h_counts;  // [batch][8]
   int* d_flags; int* h_flags;              // [3][batch]: new odo KF, new integration KF, fuse
+  // keyframe hand-off (rgbid_tracker_set_keyframe_sink): pinned host staging for one outgoing keyframe
+  rgbid_keyframe_sink sink; void* sink_user;
+  char* h_handoff; size_t handoff_bytes;
   // rgbid_tracker_prefetch: second raw-frame staging buffer, filled on a copy stream while the previous frame is tracked
   // (two buffers used alternately: frame k may still be read by its ingest kernel when frame k + 1 starts to arrive)
   cudaStream_t copy_stream; cudaEvent_t ev_copy[2];
@@ -136,6 +206,7 @@ int rgbid_tracker_create(rgbid_ctx* ctx, const rgbid_tracker_config* cfg, rgbid_
   if (t->cfg.max_integr_kf_count <= 0) t->cfg.max_integr_kf_count = 9999999;
   t->al = nullptr; t->d_arena = nullptr; t->d_proj = nullptr; t->h_proj = nullptr; t->d_counts = nullptr;
   t->h_counts = nullptr; t->d_flags = nullptr; t->h_flags = nullptr;
+  t->sink = nullptr; t->sink_user = nullptr; t->h_handoff = nullptr; t->handoff_bytes = 0;
   t->copy_stream = nullptr; t->pf_next = 0;
   for (int i = 0; i < 2; ++i) { t->ev_copy[i] = nullptr; t->d_prefetch[i] = nullptr; t->pf_depth[i] = t->pf_rgb[i] = nullptr; t->pf_valid[i] = false; }
   int rc = rgbid_aligner_create(ctx, &t->cfg.align, &t->al);
@@ -180,6 +251,7 @@ int rgbid_tracker_destroy(rgbid_tracker* t)
   if (t->copy_stream) { cudaStreamSynchronize(t->copy_stream); cudaStreamDestroy(t->copy_stream); }
   for (int i = 0; i < 2; ++i) { if (t->ev_copy[i]) cudaEventDestroy(t->ev_copy[i]); cudaFree(t->d_prefetch[i]); }
   cudaFree(t->d_arena); cudaFree(t->d_proj); cudaFree(t->d_counts); cudaFree(t->d_flags);
+  if (t->h_handoff) cudaFreeHost(t->h_handoff);
   if (t->h_proj) cudaFreeHost(t->h_proj);
   if (t->h_counts) cudaFreeHost(t->h_counts);
   if (t->h_flags) cudaFreeHost(t->h_flags);
@@ -195,6 +267,8 @@ int rgbid_tracker_reset(rgbid_tracker* t)
     memset(&s, 0, sizeof(s));
     set_identity(s.R_odoKF, s.t_odoKF); set_identity(s.R_est, s.t_est); set_identity(s.dR, s.dt);
     set_identity(s.R_intKF, s.t_intKF);
+    set_identity(s.o2i_next_R, s.o2i_next_t); set_identity(s.o2i_last_R, s.o2i_last_t);
+    s.last_integrKF_index = 0;
     s.lost = false; s.global_time = 0;
   }
   const rgbid_align_config& c = t->al->cfg;
@@ -238,6 +312,52 @@ int rgbid_tracker_overlap_mask(rgbid_tracker* t, int index, uint8_t** ptr, size_
 
 static int track_core(rgbid_tracker* t, const uint16_t* depth, const uint8_t* rgb, int from_host, size_t in_dpitch,
                       size_t in_dstride, size_t in_cpitch, size_t in_cstride, rgbid_frame_result* results);
+
+int rgbid_tracker_set_keyframe_sink(rgbid_tracker* t, rgbid_keyframe_sink cb, void* user)
+{
+  if (!t) return RGBID_ERR_ARG;
+  t->sink = cb; t->sink_user = user;
+  return RGBID_OK;
+}
+
+// Downloads the outgoing integration keyframe of stream b (before it is overwritten) and calls the sink.
+static int hand_off_keyframe(rgbid_tracker* t, int b, const double* rel_R, const double* rel_t, const double* rel_cov,
+                             int frame_index)
+{
+  const rgbid_align_config& c = t->al->cfg;
+  const StreamState& S = t->st[b];
+  cudaStream_t s = t->ctx->stream;
+  const size_t rows = c.rows, cols = c.cols;
+  const size_t mask_b = cols * rows, col_b = cols * rows * 3, map_b = cols * rows * sizeof(float);
+  const size_t off_col = align_up(mask_b, 256), off_w = off_col + align_up(col_b, 256), off_n = off_w + align_up(map_b, 256);
+  const size_t need = off_n + 3 * map_b;
+  if (t->handoff_bytes < need) {
+    if (t->h_handoff) cudaFreeHost(t->h_handoff);
+    t->h_handoff = nullptr; t->handoff_bytes = 0;
+    RGBID_CUDA_TRY(cudaMallocHost(&t->h_handoff, need));
+    t->handoff_bytes = need;
+  }
+  char* h = t->h_handoff;
+  RGBID_CUDA_TRY(cudaMemcpy2DAsync(h, cols, t->d_mask + t->mask_sstride * b, t->mask_pitch, cols, rows, cudaMemcpyDeviceToHost, s));
+  RGBID_CUDA_TRY(cudaMemcpyAsync(h + off_col, t->d_colors + t->colors_sstride * b, col_b, cudaMemcpyDeviceToHost, s));
+  RGBID_CUDA_TRY(cudaMemcpy2DAsync(h + off_w, cols * sizeof(float), (char*)t->intW.p + t->intW.sstride * b, t->intW.pitch,
+                                   cols * sizeof(float), rows, cudaMemcpyDeviceToHost, s));
+  RGBID_CUDA_TRY(cudaMemcpy2DAsync(h + off_n, cols * sizeof(float), (char*)t->nmap.p + t->nmap.sstride * b, t->nmap.pitch,
+                                   cols * sizeof(float), 3 * rows, cudaMemcpyDeviceToHost, s));
+  RGBID_CUDA_TRY(cudaStreamSynchronize(s));
+  rgbid_keyframe_handoff k;
+  memset(&k, 0, sizeof(k));
+  k.stream = b; k.kf_index = S.last_integrKF_index; k.frame_index = frame_index;
+  k.rows = c.rows; k.cols = c.cols; k.fx = c.fx; k.fy = c.fy; k.cx = c.cx; k.cy = c.cy;
+  memcpy(k.R, S.R_intKF, sizeof(k.R)); memcpy(k.t, S.t_intKF, sizeof(k.t));
+  memcpy(k.rel_R, rel_R, sizeof(k.rel_R)); memcpy(k.rel_t, rel_t, sizeof(k.rel_t)); memcpy(k.rel_cov, rel_cov, sizeof(k.rel_cov));
+  k.overlap_mask = (const uint8_t*)h; k.overlap_mask_pitch = cols;
+  k.colors = (const uint8_t*)(h + off_col);
+  k.depthinv = (const float*)(h + off_w); k.depthinv_pitch = cols * sizeof(float);
+  k.normals = (const float*)(h + off_n); k.normals_pitch = cols * sizeof(float);
+  t->sink(t->sink_user, &k);
+  return RGBID_OK;
+}
 
 int rgbid_tracker_prefetch(rgbid_tracker* t, const uint16_t* depth, const uint8_t* rgb)
 {
@@ -363,11 +483,12 @@ static int track_core(rgbid_tracker* t, const uint16_t* depth, const uint8_t* rg
   }
 
   // ---- estimateVisualOdometry (src/visodo.cpp:944-1479) -------------------------------------------------------
-  std::vector<double> prevR(9 * B), prevt(3 * B);
+  std::vector<double> prevR(9 * B), prevt(3 * B), prevcov(36 * B);
   for (int b = 0; b < B; ++b) {
     StreamState& S = t->st[b];
     memcpy(&prevR[9 * b], S.dR, sizeof(double) * 9);
     memcpy(&prevt[3 * b], S.dt, sizeof(double) * 3);
+    memcpy(&prevcov[36 * b], S.dcov, sizeof(double) * 36);
     double* Ri = al->h_init + 9 * b;
     double* ti = al->h_init + 9 * B + 3 * b;
     if (S.global_time > 1 && t->cfg.motion_model == RGBID_CONSTANT_VELOCITY && !S.lost) {
@@ -471,17 +592,39 @@ static int track_core(rgbid_tracker* t, const uint16_t* depth, const uint8_t* rg
     memcpy(r.dR, S.dR, sizeof(double) * 9); memcpy(r.dt, S.dt, sizeof(double) * 3);
     memcpy(r.cov, S.dcov, sizeof(double) * 36);
     r.new_odo_keyframe = new_odo; r.new_integr_keyframe = new_int;
+    if (r.status == RGBID_OK) {
+      // odometry-keyframe constraint (KF, i) -> sequential constraint (i - 1, i) (:2126-2156)
+      relative_constraint(&prevR[9 * b], &prevt[3 * b], &prevcov[36 * b], S.dR, S.dt, S.dcov, r.seq_R, r.seq_t, r.seq_cov);
+    } else {
+      // dummy constraint: zero motion, very high covariance (:2068-2071)
+      set_identity(r.seq_R, r.seq_t);
+      for (int i = 0; i < 36; ++i) r.seq_cov[i] = (i % 7 == 0) ? 100.0 : 0.0;
+    }
     if (new_odo) {
       // resetOdometryKeyframe (:1541-1575)
+      chain_compose(S);
       S.odoKF_count = 0;
       memcpy(S.R_odoKF, S.R_est, sizeof(double) * 9); memcpy(S.t_odoKF, S.t_est, sizeof(double) * 3);
       set_identity(S.dR, S.dt);
       memset(S.dcov, 0, sizeof(S.dcov));
     }
     if (new_int) {
-      // resetIntegrationKeyframe (:1577-1672): switch to the new keyframe
+      // resetIntegrationKeyframe (:1577-1672): close the chain, hand the outgoing keyframe over with its SEQ_KF
+      // constraint, switch to the new keyframe
+      chain_compose(S);
+      double kR[9], kt[3], kcov[36];
+      relative_constraint(S.o2i_last_R, S.o2i_last_t, S.o2i_last_cov, S.o2i_next_R, S.o2i_next_t, S.o2i_next_cov, kR, kt, kcov);
+      if (t->sink) {
+        int hrc = hand_off_keyframe(t, b, kR, kt, kcov, r.frame_index);
+        if (hrc != RGBID_OK) return hrc;
+      }
       S.integrKF_count = 0;
+      S.last_integrKF_index = r.frame_index;
       memcpy(S.R_intKF, S.R_est, sizeof(double) * 9); memcpy(S.t_intKF, S.t_est, sizeof(double) * 3);
+      memcpy(S.o2i_last_R, S.dR, sizeof(double) * 9); memcpy(S.o2i_last_t, S.dt, sizeof(double) * 3);
+      memcpy(S.o2i_last_cov, S.dcov, sizeof(double) * 36);
+      set_identity(S.o2i_next_R, S.o2i_next_t);
+      memset(S.o2i_next_cov, 0, sizeof(S.o2i_next_cov));
     }
     t->h_flags[0 * B + b] = new_odo; t->h_flags[1 * B + b] = new_int; t->h_flags[2 * B + b] = fuse;
     any_odo |= (new_odo != 0); any_int |= (new_int != 0); any_fuse |= (fuse != 0);

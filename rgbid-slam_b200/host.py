@@ -452,6 +452,32 @@ class Tracker:
         capi.check(self.lib.rgbid_tracker_track(self.h, pd, pc, host, self.results), "tracker_track")
         return self.results
 
+    def set_keyframe_sink(self, fn):
+        """fn(dict) is called inside track() for every outgoing integration keyframe (resetIntegrationKeyframe,
+        src/visodo.cpp:1577-1672): indices, global pose, SEQ_KF constraint + covariance, and numpy copies of the
+        overlap mask, colours, fused inverse depth and normals.  fn=None removes the sink."""
+        if fn is None:
+            self._sink = None
+            capi.check(self.lib.rgbid_tracker_set_keyframe_sink(self.h, None, None), "set_keyframe_sink")
+            return
+
+        def trampoline(_user, kp):
+            k = kp.contents
+            rows, cols = k.rows, k.cols
+
+            def arr(ptr, shape, dtype):
+                n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+                return np.frombuffer(C.string_at(ptr, n), dtype=dtype).reshape(shape).copy()
+
+            fn(dict(stream=k.stream, kf_index=k.kf_index, frame_index=k.frame_index, R=np.array(k.R[:]).reshape(3, 3),
+                    t=np.array(k.t[:]), rel_R=np.array(k.rel_R[:]).reshape(3, 3), rel_t=np.array(k.rel_t[:]),
+                    rel_cov=np.array(k.rel_cov[:]).reshape(6, 6),
+                    overlap_mask=arr(k.overlap_mask, (rows, cols), np.uint8), colors=arr(k.colors, (rows, cols, 3), np.uint8),
+                    depthinv=arr(k.depthinv, (rows, cols), np.float32), normals=arr(k.normals, (3 * rows, cols), np.float32)))
+
+        self._sink = capi.KEYFRAME_SINK(trampoline)  # keep the callback object alive
+        capi.check(self.lib.rgbid_tracker_set_keyframe_sink(self.h, C.cast(self._sink, C.c_void_p), None), "set_keyframe_sink")
+
     def prefetch(self, depth, rgb):
         """Start uploading the NEXT frame (CPU tensors / numpy arrays, ideally pinned) while the current one is tracked;
         the following track(depth, rgb) with the same buffers uses the uploaded copy."""
@@ -470,6 +496,12 @@ class Tracker:
         ms = _F(0)
         capi.check(self.lib.rgbid_aligner_time_build(self.aligner_handle, level, reps, C.byref(ms)), "aligner_time_build")
         return ms.value
+
+    def overlap_mask(self, index=0):
+        """Overlap mask of the integration keyframe of stream `index` (uint8, 1 = seen by the previous keyframe)."""
+        p, pitch = C.c_void_p(), C.c_size_t()
+        capi.check(self.lib.rgbid_tracker_overlap_mask(self.h, index, C.byref(p), C.byref(pitch)), "overlap_mask")
+        return _wrap_device(p.value, self.cfg.align.rows, self.cfg.align.cols, pitch.value, self.ctx.device, dtype=torch.uint8)
 
     def keyframe_map(self, which, index=0):
         p, pitch = C.c_void_p(), C.c_size_t()
