@@ -20,11 +20,11 @@
 
 #include "../../include/rgbid_b200/internal.hpp"
 #include "settings.hpp"
+#include "keyframe.hpp"
 
 namespace RGBID_SLAM {
 
-struct PixelRGB { unsigned char r, g, b; };  // include/types.h:88-91
-typedef DeviceArray2D<PixelRGB> View;
+typedef DeviceArray2D<PixelRGB> View;  // PixelRGB: keyframe.hpp
 typedef DeviceArray2D<unsigned short> DepthMap;
 
 /** Rigid transform, row-major: X_world = R X_cam + t */
@@ -146,6 +146,9 @@ class VisodoTracker {
     if (rc != RGBID_OK) throw std::runtime_error(std::string("rgbid_tracker_track: ") + rgbid_status_string(rc));
     last_ = r;
     lost_ = (r.status != RGBID_OK);
+    if (global_time_ > 0)  // SEQ_ODO constraint (or the dummy one when lost), src/visodo.cpp:2068-2071, 2147-2154
+      keyframe_buffers_.constraints_.push_back(PoseConstraint(global_time_ - 1, global_time_, PoseConstraint::SEQ_ODO, r.seq_R,
+                                                              r.seq_t, 1.f, r.seq_cov));
     Affine3 p;
     std::memcpy(p.R, r.R, sizeof(p.R));
     std::memcpy(p.t, r.t, sizeof(p.t));
@@ -165,6 +168,11 @@ class VisodoTracker {
   }
 
   const rgbid_frame_result& lastResult() const { return last_; }
+
+  /** What the reference pushes to keyframe_manager_ptr_ (buffer_keyframes_, constraints_): every outgoing integration
+      keyframe with its SEQ_KF constraint (resetIntegrationKeyframe, src/visodo.cpp:1577-1672) and one SEQ_ODO constraint
+      per frame.  The consumer (KeyframeManager) is out of scope; it would drain these. */
+  KeyframeBuffers keyframe_buffers_;
   rgbid_tracker* handle() { ensure_created(); return trk_; }
 
   void reset()
@@ -183,6 +191,14 @@ class VisodoTracker {
   int visodo_iterations_[RGBID_MAX_LEVELS];
 
  private:
+  static void keyframe_sink(void* user, const rgbid_keyframe_handoff* k)
+  {
+    VisodoTracker* self = (VisodoTracker*)user;
+    self->keyframe_buffers_.buffer_keyframes_.push_back(KeyframePtr(new Keyframe(*k)));
+    self->keyframe_buffers_.constraints_.push_back(PoseConstraint(k->kf_index, k->frame_index, PoseConstraint::SEQ_KF, k->rel_R,
+                                                                  k->rel_t, 1.f, k->rel_cov));
+  }
+
   void ensure_created()
   {
     if (trk_) return;
@@ -205,6 +221,7 @@ class VisodoTracker {
     c.delta_t = 0.03333f;  // computeInterframeTime in evaluation mode, src/visodo.cpp:1932
     int rc = rgbid_tracker_create(device::thread_context().ctx, &c, &trk_);
     if (rc != RGBID_OK) throw std::runtime_error(std::string("rgbid_tracker_create: ") + rgbid_status_string(rc));
+    rgbid_tracker_set_keyframe_sink(trk_, &VisodoTracker::keyframe_sink, this);
   }
 
   int rows_, cols_, levels_, optim_dim_, Mestimator_, motion_model_, sigma_estimator_, weighting_, warping_;

@@ -122,6 +122,17 @@ int main(int argc, char** argv)
       for (int i = 0; i < 3; ++i) fprintf(out, " %.17g", p.t[i]);
       fprintf(out, " %d %d\n", tracker.lastResult().new_odo_keyframe, tracker.lastResult().new_integr_keyframe);
     }
+    // hand-off containers (keyframe_manager_ptr_->buffer_keyframes_ / constraints_ in the reference)
+    const KeyframeBuffers& kb = tracker.keyframe_buffers_;
+    int n_seq_odo = 0, n_seq_kf = 0;
+    for (const PoseConstraint& pc : kb.constraints_) (pc.type_ == PoseConstraint::SEQ_ODO ? n_seq_odo : n_seq_kf)++;
+    fprintf(out, "handoff %d %d %d", (int)kb.buffer_keyframes_.size(), n_seq_odo, n_seq_kf);
+    for (const KeyframePtr& k : kb.buffer_keyframes_) {
+      double s = 0; int valid = 0;
+      for (float v : k->depthinv_) if (v == v) { s += v; ++valid; }
+      fprintf(out, " %d %d %.9g %d", k->id_, valid, s, (int)k->colors_[k->colors_.size() / 2].g);
+    }
+    fprintf(out, "\n");
   }
 
   // ---- 3. KeyframeAlign::alignKeyframes between frames 0 and 2 (src/loop_closer.cpp:319 calls it like this) ------

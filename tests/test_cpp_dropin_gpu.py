@@ -77,6 +77,13 @@ def test_cpp_dropin_surface(built, tmp_path):
         assert np.linalg.norm(np.array(pr[11:14]) - o["t"]) < 1e-4 and rot_angle(np.array(pr[2:11]).reshape(3, 3), o["R"]) < 1e-4
         assert int(pr[14]) == o["new_odo_keyframe"] and int(pr[15]) == o["new_integr_keyframe"]
 
+    # 2b. hand-off containers: one SEQ_ODO constraint per tracked frame, one keyframe + SEQ_KF per integration switch
+    ho = lines["handoff"]
+    n_int = sum(int(poses[k][15]) for k in range(1, n))
+    assert int(ho[0]) == n_int and int(ho[1]) == n - 1 and int(ho[2]) == n_int
+    if n_int:
+        assert int(ho[3]) == 0 and int(ho[4]) > 0.5 * rows * cols  # first outgoing keyframe was created at frame 0
+
     # 3. KeyframeAlign (grey image rounded to 8 bit, as the Keyframe container stores it)
     G = [np.floor(orc.intensity(rgb[j]) + 0.5).astype(np.uint8).astype(np.float32) for j in (0, 2)]
     W = [orc.depth_to_invdepth(depth[j]) for j in (0, 2)]
