@@ -287,6 +287,35 @@ typedef struct {
   double seq_R[9], seq_t[3], seq_cov[36];
 } rgbid_frame_result;
 
+/* ---- custom-calibration ingest and colour fusion / previews (f4) ------------------------------------
+ * One entry per reference bridge function; same argument meaning. */
+typedef struct rgbid_intr { float fx, fy, cx, cy, k1, k2, k3, k4, k5; } rgbid_intr;          /* Intr, src/internal.h:119-140 */
+typedef struct rgbid_depth_dist {                                                             /* DepthDist, :142-161 */
+  float c1, c0;
+  float q0[9], q1[9];
+  int xshift, yshift;
+} rgbid_depth_dist;
+/* undistortIntensity (src/internal.h:437, src/cuda/undistortion.cu:212-257) */
+int rgbid_undistort_intensity(rgbid_ctx* ctx, const float* src, size_t spitch, float* dst, size_t dpitch, int rows, int cols,
+                              const rgbid_intr* intr);
+/* undistortDepthInv (src/internal.h:440, undistortion.cu:260-310); the reference's src_corr scratch map is not needed */
+int rgbid_undistort_depthinv(rgbid_ctx* ctx, const float* src, size_t spitch, float* dst, size_t dpitch, int rows, int cols,
+                             const rgbid_intr* intr_depth, const rgbid_depth_dist* dp);
+/* registerDepthinv (src/internal.h:354, src/cuda/warping_registration.cu:720-800).  The 3 rows x 3 cols canvas
+ * (`intermediate` / `intermediate_as_int`) lives in the context's scratch.  dRc_proj = Kd dRc Kc^-1, t_dc_proj = Kd t_dc,
+ * cRd_proj = dRc_proj^-1 (row-major 3x3 / 3), as built in src/visodo.cpp:789-807. */
+int rgbid_register_depthinv(rgbid_ctx* ctx, const float* src, size_t spitch, float* dst, size_t dpitch, int rows, int cols,
+                            const float* dRc_proj, const float* t_dc_proj, const float* cRd_proj);
+/* integrateWarpedRGB (src/internal.h, warping_registration.cu:672-712, 1103-1129): depth_dst, colors_dst (rows x cols x 3
+ * uint8, pitch colors_pitch) and weight_dst are updated in place; all float maps share `pitch`. */
+int rgbid_integrate_warped_rgb(rgbid_ctx* ctx, const float* depth_warped, const float* r_warped, const float* g_warped,
+                               const float* b_warped, const float* weight_warped, float* depth_dst, uint8_t* colors_dst,
+                               size_t colors_pitch, float* weight_dst, size_t pitch, int rows, int cols);
+/* generateImage / generateImageRGB (src/internal.h:416-421, src/cuda/image_generator.cu): vmap / nmap are 3 rows x cols
+ * (x, y, z planes); rgb may be NULL (grey shading); light: position of the single light source; out: rows x cols x 3. */
+int rgbid_generate_image(rgbid_ctx* ctx, const float* vmap, const float* nmap, size_t map_pitch, const uint8_t* rgb,
+                         size_t rgb_pitch, const float* light_pos, uint8_t* out, size_t out_pitch, int rows, int cols);
+
 /* ---- keyframe hand-off to the back end (resetIntegrationKeyframe, src/visodo.cpp:1577-1672) ------------------------
  * When a stream switches its integration keyframe, the OUTGOING keyframe is handed to the sink: its creation index and
  * global pose, the SEQ_KF constraint from the previous keyframe with the covariance propagated through the

@@ -228,3 +228,49 @@ def align(cfg, kf, cur, R=None, t=None):
     torch.cuda.synchronize()
     l = lib()
     return _align_glue(cfg, kf, cur, R, t, fn=l.ref_align, ptr_of=lambda a: a.data_ptr())
+
+
+# ---- custom-calibration ingest, colour fusion, shaded previews -------------------------------------
+def _intr9(intr):
+    return np.array([intr[k] if k in intr else 0.0 for k in ("fx", "fy", "cx", "cy", "k1", "k2", "k3", "k4", "k5")],
+                    dtype=np.float32)
+
+
+def undistort_intensity(src, intr):
+    rows, cols = src.shape
+    out = torch.empty(rows, cols, device=src.device)
+    lib().ref_undistort_intensity(_dense(src), _dense(out), _sz(cols * 4), rows, cols, _np(_intr9(intr)))
+    return out
+
+
+def undistort_depthinv(src, intr, dp):
+    rows, cols = src.shape
+    out, scratch = torch.empty(rows, cols, device=src.device), torch.empty(rows, cols, device=src.device)
+    d = np.array([dp["c1"], dp["c0"]] + list(dp["q0"]) + list(dp["q1"]), dtype=np.float32)
+    lib().ref_undistort_depthinv(_dense(src), _dense(scratch), _dense(out), _sz(cols * 4), rows, cols, _np(_intr9(intr)),
+                                 _np(d), int(dp["xshift"]), int(dp["yshift"]))
+    return out
+
+
+def register_depthinv(src, dRc_proj, t_dc_proj, cRd_proj):
+    rows, cols = src.shape
+    out = torch.empty(rows, cols, device=src.device)
+    inter = torch.empty(3 * rows, 3 * cols, device=src.device)
+    inter_i = torch.empty(3 * rows, 3 * cols, dtype=torch.int32, device=src.device)
+    lib().ref_register_depthinv(_dense(src), _dense(inter), _dense(inter_i), _sz(3 * cols * 4), _dense(out), _sz(cols * 4),
+                                rows, cols, _np(_f32(dRc_proj)), _np(_f32(t_dc_proj)), _np(_f32(cRd_proj)))
+    return out
+
+
+def integrate_warped_rgb(dw, rw, gw, bw, ww, depth_dst, colors_dst, weight_dst):
+    rows, cols = dw.shape
+    lib().ref_integrate_warped_rgb(_dense(dw), _dense(rw), _dense(gw), _dense(bw), _dense(ww), _dense(depth_dst),
+                                   _dense(colors_dst), _sz(cols * 3), _dense(weight_dst), _sz(cols * 4), rows, cols)
+
+
+def generate_image(vmap, nmap, light, rgb=None):
+    rows, cols = vmap.shape[0] // 3, vmap.shape[1]
+    out = torch.empty(rows, cols, 3, dtype=torch.uint8, device=vmap.device)
+    lib().ref_generate_image(_dense(vmap), _dense(nmap), _sz(cols * 4), _dense(rgb) if rgb is not None else None,
+                             _sz(cols * 3), _np(_f32(light)), _dense(out), _sz(cols * 3), rows, cols)
+    return out

@@ -115,6 +115,57 @@ float ref_warp_invdepth_weighted(const float* src, const float* depth_prev, floa
   return warpInvDepthWithTrafo3DWeighted(s, d, p, w, mat33(Rp), make_float3(tp[0], tp[1], tp[2]), Intr(1, 1, 0, 0));
 }
 
+/* ---- custom-calibration ingest, colour fusion, shaded previews ---------------------------- */
+static inline Intr intr9(const float* k) { return Intr(k[0], k[1], k[2], k[3], k[4], k[5], k[6], k[7], k[8]); }
+
+float ref_undistort_intensity(const float* src, float* dst, size_t pitch, int rows, int cols, const float* intr)
+{
+  Map a = wrap(src, pitch, rows, cols), b = wrap(dst, pitch, rows, cols);
+  return undistortIntensity(a, b, intr9(intr));
+}
+
+/* dp: c1 c0 q0[9] q1[9] as floats, then xshift yshift as ints */
+float ref_undistort_depthinv(const float* src, float* scratch, float* dst, size_t pitch, int rows, int cols,
+                             const float* intr, const float* dp, int xshift, int yshift)
+{
+  Map a = wrap(src, pitch, rows, cols), c = wrap(scratch, pitch, rows, cols), b = wrap(dst, pitch, rows, cols);
+  DepthDist d(dp[0], dp[1], dp[2], dp[3], dp[4], dp[5], dp[6], dp[7], dp[8], dp[9], dp[10], dp[11], dp[12], dp[13], dp[14],
+              dp[15], dp[16], dp[17], dp[18], dp[19], xshift, yshift);
+  return undistortDepthInv(a, c, b, intr9(intr), d);
+}
+
+float ref_register_depthinv(const float* src, float* inter, int* inter_int, size_t ipitch, float* dst, size_t pitch,
+                            int rows, int cols, const float* dRc_proj, const float* t_dc_proj, const float* cRd_proj)
+{
+  Map a = wrap(src, pitch, rows, cols), b = wrap(dst, pitch, rows, cols);
+  Map im = wrap(inter, ipitch, 3 * rows, 3 * cols);
+  DeviceArray2D<int> ii(3 * rows, 3 * cols, (void*)inter_int, ipitch);
+  return registerDepthinv(a, im, ii, b, mat33(dRc_proj), make_float3(t_dc_proj[0], t_dc_proj[1], t_dc_proj[2]),
+                          mat33(cRd_proj));
+}
+
+float ref_integrate_warped_rgb(const float* dw, const float* rw, const float* gw, const float* bw, const float* ww,
+                               float* dd, unsigned char* colors, size_t cpitch, float* wd, size_t pitch, int rows, int cols)
+{
+  Map a = wrap(dw, pitch, rows, cols), r = wrap(rw, pitch, rows, cols), g = wrap(gw, pitch, rows, cols);
+  Map b = wrap(bw, pitch, rows, cols), w = wrap(ww, pitch, rows, cols), d = wrap(dd, pitch, rows, cols);
+  Map e = wrap(wd, pitch, rows, cols);
+  return integrateWarpedRGB(a, r, g, b, w, d, PtrStepSz<uchar3>(rows, cols, (uchar3*)colors, cpitch), e);
+}
+
+void ref_generate_image(const float* vmap, const float* nmap, size_t pitch, const unsigned char* rgb, size_t rgb_pitch,
+                        const float* light_pos, unsigned char* out, size_t out_pitch, int rows, int cols)
+{
+  Map v = wrap(vmap, pitch, 3 * rows, cols), n = wrap(nmap, pitch, 3 * rows, cols);
+  LightSource light;
+  light.number = 1;
+  light.pos[0] = make_float3(light_pos[0], light_pos[1], light_pos[2]);
+  PtrStepSz<uchar3> o(rows, cols, (uchar3*)out, out_pitch);
+  if (rgb) generateImageRGB(v, n, PtrStepSz<uchar3>(rows, cols, (uchar3*)rgb, rgb_pitch), light, o);
+  else generateImage(v, n, light, o);
+  sync();
+}
+
 float ref_integrate_warped_frame(const float* wsrc, const float* wweight, float* dst, float* dweight,
                                  size_t pitch, int rows, int cols)
 {

@@ -15,7 +15,7 @@ OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "librgbid_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-SOURCES = ["image_ops.cu", "warp_ops.cu", "scale_est.cu", "gn_system.cu", "api.cu", "aligner.cu", "tracker.cu"]
+SOURCES = ["image_ops.cu", "warp_ops.cu", "calib_ops.cu", "scale_est.cu", "gn_system.cu", "api.cu", "aligner.cu", "tracker.cu"]
 
 # numeric flags of the reference build (CMakeLists.txt:110) so that per-pixel float arithmetic is compiled
 # the same way as the reference's own kernels

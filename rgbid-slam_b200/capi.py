@@ -31,6 +31,15 @@ class SystemParams(C.Structure):
                 ("bias_int", C.c_float), ("nu_depthinv", C.c_float), ("nu_int", C.c_float)]
 
 
+class Intr(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("fx", "fy", "cx", "cy", "k1", "k2", "k3", "k4", "k5")]
+
+
+class DepthDist(C.Structure):
+    _fields_ = [("c1", C.c_float), ("c0", C.c_float), ("q0", C.c_float * 9), ("q1", C.c_float * 9), ("xshift", C.c_int),
+                ("yshift", C.c_int)]
+
+
 class AlignConfig(C.Structure):
     _fields_ = [("rows", C.c_int), ("cols", C.c_int), ("levels", C.c_int), ("finest_level", C.c_int),
                 ("iterations", C.c_int * MAX_LEVELS), ("batch", C.c_int), ("mode", C.c_int),
@@ -100,6 +109,11 @@ PROTOTYPES = {
     "rgbid_warp_invdepth_weighted": (I, [P, P, SZ, P, SZ, P, SZ, P, SZ, I, I, c_float_p, c_float_p]),
     "rgbid_integrate_warped_frame": (I, [P, P, SZ, P, SZ, P, SZ, P, SZ, I, I]),
     "rgbid_visibility_ratio": (I, [P, P, SZ, P, SZ, I, I, c_float_p, c_float_p, P, SZ, c_float_p]),
+    "rgbid_undistort_intensity": (I, [P, P, SZ, P, SZ, I, I, C.POINTER(Intr)]),
+    "rgbid_undistort_depthinv": (I, [P, P, SZ, P, SZ, I, I, C.POINTER(Intr), C.POINTER(DepthDist)]),
+    "rgbid_register_depthinv": (I, [P, P, SZ, P, SZ, I, I, c_float_p, c_float_p, c_float_p]),
+    "rgbid_integrate_warped_rgb": (I, [P, P, P, P, P, P, P, P, SZ, P, SZ, I, I]),
+    "rgbid_generate_image": (I, [P, P, P, SZ, P, SZ, c_float_p, P, SZ, I, I]),
     "rgbid_error_geometry": (I, [I, I, I, c_int_p, c_int_p, c_int_p]),
     "rgbid_compute_error": (I, [P, P, SZ, P, SZ, I, I, I, P, c_int_p]),
     "rgbid_sigma_nu_student": (I, [P, P, I, c_float_p, c_float_p, c_float_p, I]),

@@ -261,6 +261,58 @@ int rgbid_visibility_ratio(rgbid_ctx* ctx, const float* dsrc, size_t spitch, con
   return check_last(ctx);
 }
 
+// ---- custom-calibration ingest, colour fusion, previews (calib_ops.cu) ------------------------------------
+int rgbid_undistort_intensity(rgbid_ctx* ctx, const float* src, size_t spitch, float* dst, size_t dpitch, int rows, int cols,
+                              const rgbid_intr* intr)
+{
+  if (!ctx || !src || !dst || !intr || rows <= 0 || cols <= 0) return RGBID_ERR_ARG;
+  launch_undistort_intensity(ctx->L(), make_img(src, spitch, rows, cols), make_img(dst, dpitch, rows, cols), *intr);
+  return check_last(ctx);
+}
+
+int rgbid_undistort_depthinv(rgbid_ctx* ctx, const float* src, size_t spitch, float* dst, size_t dpitch, int rows, int cols,
+                             const rgbid_intr* intr, const rgbid_depth_dist* dp)
+{
+  if (!ctx || !src || !dst || !intr || !dp || rows <= 0 || cols <= 0) return RGBID_ERR_ARG;
+  launch_undistort_depthinv(ctx->L(), make_img(src, spitch, rows, cols), make_img(dst, dpitch, rows, cols), *intr, *dp);
+  return check_last(ctx);
+}
+
+int rgbid_register_depthinv(rgbid_ctx* ctx, const float* src, size_t spitch, float* dst, size_t dpitch, int rows, int cols,
+                            const float* dRc_proj, const float* t_dc_proj, const float* cRd_proj)
+{
+  if (!ctx || !src || !dst || !dRc_proj || !t_dc_proj || !cRd_proj || rows <= 0 || cols <= 0) return RGBID_ERR_ARG;
+  const int crows = 3 * rows, ccols = 3 * cols;  // src/visodo.cpp:623-624
+  const size_t cpitch = align_up((size_t)ccols * sizeof(int), 128);
+  int rc = ctx_reserve_device_stage(ctx, cpitch * crows);
+  if (rc != RGBID_OK) return rc;
+  launch_register_depthinv(ctx->L(), make_img(src, spitch, rows, cols), make_img(dst, dpitch, rows, cols), (int*)ctx->d_stage,
+                           cpitch, crows, ccols, dRc_proj, t_dc_proj, cRd_proj);
+  return check_last(ctx);
+}
+
+int rgbid_integrate_warped_rgb(rgbid_ctx* ctx, const float* depth_warped, const float* r_warped, const float* g_warped,
+                               const float* b_warped, const float* weight_warped, float* depth_dst, uint8_t* colors_dst,
+                               size_t colors_pitch, float* weight_dst, size_t pitch, int rows, int cols)
+{
+  if (!ctx || !depth_warped || !r_warped || !g_warped || !b_warped || !weight_warped || !depth_dst || !colors_dst ||
+      !weight_dst || rows <= 0 || cols <= 0)
+    return RGBID_ERR_ARG;
+  auto im = [&](const float* p) { return make_img(p, pitch, rows, cols); };
+  launch_integrate_rgb(ctx->L(), im(depth_warped), im(r_warped), im(g_warped), im(b_warped), im(weight_warped), im(depth_dst),
+                       colors_dst, colors_pitch, im(weight_dst));
+  return check_last(ctx);
+}
+
+int rgbid_generate_image(rgbid_ctx* ctx, const float* vmap, const float* nmap, size_t map_pitch, const uint8_t* rgb,
+                         size_t rgb_pitch, const float* light_pos, uint8_t* out, size_t out_pitch, int rows, int cols)
+{
+  if (!ctx || !vmap || !nmap || !light_pos || !out || rows <= 0 || cols <= 0) return RGBID_ERR_ARG;
+  launch_generate_image(ctx->L(), make_img(vmap, map_pitch, 3 * rows, cols), make_img(nmap, map_pitch, 3 * rows, cols), rgb,
+                        rgb_pitch, light_pos, out, out_pitch, rows, cols);
+  return check_last(ctx);
+}
+
 // ---- residual sampling / scale / chi-square -----------------------------------------------------------
 int rgbid_error_geometry(int rows, int cols, int min_nsamples, int* kept_rows, int* kept_cols, int* stride)
 {

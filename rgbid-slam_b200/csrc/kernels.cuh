@@ -52,6 +52,17 @@ void launch_visibility(const LaunchCtx& L, ImgB src, ImgB dst, const Proj* P_dev
                        unsigned int* counts, int count_offset, int count_stride, uint8_t* mask, size_t mpitch,
                        size_t mstride, int batch, const int* active = nullptr);
 
+// ---- calib_ops.cu ---------------------------------------------------------------------------------
+void launch_undistort_intensity(const LaunchCtx& L, ImgB src, ImgB dst, const rgbid_intr& intr);
+void launch_undistort_depthinv(const LaunchCtx& L, ImgB src, ImgB dst, const rgbid_intr& intr, const rgbid_depth_dist& dp);
+// canvas: int map of crows x ccols (the reference uses 3 rows x 3 cols) with pitch cpitch bytes, cleared inside
+void launch_register_depthinv(const LaunchCtx& L, ImgB src, ImgB dst, int* canvas, size_t cpitch, int crows, int ccols,
+                              const float* dRc_proj, const float* t_dc_proj, const float* cRd_proj);
+void launch_integrate_rgb(const LaunchCtx& L, ImgB dw, ImgB rw, ImgB gw, ImgB bw, ImgB ww, ImgB dd, uint8_t* colors,
+                          size_t cpitch, ImgB wd);
+void launch_generate_image(const LaunchCtx& L, ImgB vmap, ImgB nmap, const uint8_t* rgb, size_t rgb_pitch, const float* light,
+                           uint8_t* out, size_t out_pitch, int rows, int cols);
+
 // ---- scale_est.cu ---------------------------------------------------------------------------------
 void launch_compute_error(const LaunchCtx& L, ImgB im1, ImgB im0, float* error, int kept_rows, int kept_cols,
                           int stride);

@@ -154,6 +154,64 @@ class Context:
         self._leave()
         return out
 
+    # ---- custom-calibration ingest, colour fusion, previews -------------------------------------
+    @staticmethod
+    def _intr(intr):
+        return capi.Intr(*[float(intr.get(k, 0.0)) for k in ("fx", "fy", "cx", "cy", "k1", "k2", "k3", "k4", "k5")])
+
+    def undistort_intensity(self, src, intr):
+        rows, cols = src.shape
+        out = self.empty(rows, cols)
+        i = self._intr(intr)
+        self._enter()
+        capi.check(self.lib.rgbid_undistort_intensity(self.h, src.data_ptr(), _pitch(src), out.data_ptr(), _pitch(out), rows,
+                                                      cols, C.byref(i)), "undistort_intensity")
+        self._leave()
+        return out
+
+    def undistort_depthinv(self, src, intr, dp):
+        rows, cols = src.shape
+        out = self.empty(rows, cols)
+        i = self._intr(intr)
+        d = capi.DepthDist(float(dp["c1"]), float(dp["c0"]), (C.c_float * 9)(*dp["q0"]), (C.c_float * 9)(*dp["q1"]),
+                           int(dp["xshift"]), int(dp["yshift"]))
+        self._enter()
+        capi.check(self.lib.rgbid_undistort_depthinv(self.h, src.data_ptr(), _pitch(src), out.data_ptr(), _pitch(out), rows,
+                                                     cols, C.byref(i), C.byref(d)), "undistort_depthinv")
+        self._leave()
+        return out
+
+    def register_depthinv(self, src, dRc_proj, t_dc_proj, cRd_proj):
+        rows, cols = src.shape
+        out = self.empty(rows, cols)
+        a, t, b = (np.ascontiguousarray(np.reshape(m, -1), dtype=np.float32) for m in (dRc_proj, t_dc_proj, cRd_proj))
+        self._enter()
+        capi.check(self.lib.rgbid_register_depthinv(self.h, src.data_ptr(), _pitch(src), out.data_ptr(), _pitch(out), rows,
+                                                    cols, _fp(a), _fp(t), _fp(b)), "register_depthinv")
+        self._leave()
+        return out
+
+    def integrate_warped_rgb(self, dw, rw, gw, bw, ww, depth_dst, colors_dst, weight_dst):
+        rows, cols = dw.shape
+        self._enter()
+        capi.check(self.lib.rgbid_integrate_warped_rgb(self.h, dw.data_ptr(), rw.data_ptr(), gw.data_ptr(), bw.data_ptr(),
+                                                       ww.data_ptr(), depth_dst.data_ptr(), colors_dst.data_ptr(),
+                                                       colors_dst.stride(0), weight_dst.data_ptr(), _pitch(dw), rows, cols),
+                   "integrate_warped_rgb")
+        self._leave()
+
+    def generate_image(self, vmap, nmap, light, rgb=None):
+        rows, cols = vmap.shape[0] // 3, vmap.shape[1]
+        out = torch.empty(rows, cols, 3, dtype=torch.uint8, device=self.device)
+        l = np.ascontiguousarray(light, dtype=np.float32)
+        self._enter()
+        capi.check(self.lib.rgbid_generate_image(self.h, vmap.data_ptr(), nmap.data_ptr(), _pitch(vmap),
+                                                 rgb.data_ptr() if rgb is not None else None,
+                                                 rgb.stride(0) if rgb is not None else 0, _fp(l), out.data_ptr(), out.stride(0),
+                                                 rows, cols), "generate_image")
+        self._leave()
+        return out
+
     def _warp(self, fn, src, prev, Rp, tp, name):
         rows, cols = prev.shape
         out = self.empty(rows, cols)
