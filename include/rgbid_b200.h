@@ -306,6 +306,16 @@ int rgbid_undistort_depthinv(rgbid_ctx* ctx, const float* src, size_t spitch, fl
  * cRd_proj = dRc_proj^-1 (row-major 3x3 / 3), as built in src/visodo.cpp:789-807. */
 int rgbid_register_depthinv(rgbid_ctx* ctx, const float* src, size_t spitch, float* dst, size_t dpitch, int rows, int cols,
                             const float* dRc_proj, const float* t_dc_proj, const float* cRd_proj);
+/* prepareImagesCustomCalibration (src/visodo.cpp:775-823) inside the tracker: when set, every frame is ingested as
+ * intensity -> undistortIntensity(rgb), inverse depth -> undistortDepthInv(depth, dist) -> registerDepthinv with
+ * dRc_proj = Kd dRc Kc^-1, t_dc_proj = Kd t_dc (float, :789-807) instead of the plain conversion.  cal == NULL switches back.
+ * (config_data/calibration_custom.ini: [RGB_CALIBRATION], [DEPTH_CALIBRATION] custom_registration=1, [STEREO_DEPTH2RGB]) */
+typedef struct rgbid_custom_calibration {
+  rgbid_intr rgb, depth;
+  rgbid_depth_dist dist;
+  float dRc[9], t_dc[3];
+} rgbid_custom_calibration;
+int rgbid_tracker_set_custom_calibration(rgbid_tracker* trk, const rgbid_custom_calibration* cal);
 /* integrateWarpedRGB (src/internal.h, warping_registration.cu:672-712, 1103-1129): depth_dst, colors_dst (rows x cols x 3
  * uint8, pitch colors_pitch) and weight_dst are updated in place; all float maps share `pitch`. */
 int rgbid_integrate_warped_rgb(rgbid_ctx* ctx, const float* depth_warped, const float* r_warped, const float* g_warped,

@@ -87,6 +87,28 @@ struct Mat33 {
   float3 data[3];
 };
 
+/** Depth distortion model (src/internal.h:142-161) */
+struct DepthDist {
+  float c1, c0;
+  float q00, q01, q02, q03, q04, q05, q06, q07, q08;
+  float q10, q11, q12, q13, q14, q15, q16, q17, q18;
+  int xshift, yshift;
+  DepthDist() {}
+  DepthDist(float c1_, float c0_, float q00_ = 0.f, float q01_ = 0.f, float q02_ = 0.f, float q03_ = 0.f, float q04_ = 0.f,
+            float q05_ = 0.f, float q06_ = 0.f, float q07_ = 0.f, float q08_ = 0.f, float q10_ = 1.f, float q11_ = 0.f,
+            float q12_ = 0.f, float q13_ = 0.f, float q14_ = 0.f, float q15_ = 0.f, float q16_ = 0.f, float q17_ = 0.f,
+            float q18_ = 0.f, int xshift_ = 4, int yshift_ = 4)
+      : c1(c1_), c0(c0_), q00(q00_), q01(q01_), q02(q02_), q03(q03_), q04(q04_), q05(q05_), q06(q06_), q07(q07_), q08(q08_),
+        q10(q10_), q11(q11_), q12(q12_), q13(q13_), q14(q14_), q15(q15_), q16(q16_), q17(q17_), q18(q18_), xshift(xshift_),
+        yshift(yshift_) {}
+};
+
+/** Light source of the shaded previews (src/internal.h:173-177) */
+struct LightSource {
+  float3 pos[1];
+  int number;
+};
+
 // ---- per-thread context ---------------------------------------------------------------------------------
 struct ThreadContext {
   rgbid_ctx* ctx;
@@ -304,6 +326,86 @@ inline float integrateWarpedFrame(const DepthMapf& warped_depth_src, const Devic
                                      warped_weight_src.step(), depth_dst.ptr(), depth_dst.step(), weight_dst.ptr(),
                                      weight_dst.step(), depth_dst.rows(), depth_dst.cols()), "integrateWarpedFrame");
   return t.done();
+}
+
+// ---- custom-calibration ingest (src/internal.h:354, 437, 440), colour fusion, previews (:416-421) ---------------------
+inline rgbid_intr to_c(const Intr& i) { rgbid_intr r = {i.fx, i.fy, i.cx, i.cy, i.k1, i.k2, i.k3, i.k4, i.k5}; return r; }
+inline rgbid_depth_dist to_c(const DepthDist& d)
+{
+  rgbid_depth_dist r = {d.c1, d.c0, {d.q00, d.q01, d.q02, d.q03, d.q04, d.q05, d.q06, d.q07, d.q08},
+                        {d.q10, d.q11, d.q12, d.q13, d.q14, d.q15, d.q16, d.q17, d.q18}, d.xshift, d.yshift};
+  return r;
+}
+
+inline float undistortIntensity(IntensityMapf& src, IntensityMapf& dst, const Intr& intr_int, int numSMs = -1)
+{
+  (void)numSMs;
+  CallTimer t;
+  rgbid_intr i = to_c(intr_int);
+  check(rgbid_undistort_intensity(t.tc.ctx, src.ptr(), src.step(), dst.ptr(), dst.step(), src.rows(), src.cols(), &i),
+        "undistortIntensity");
+  return t.done();
+}
+
+inline float undistortDepthInv(const DepthMapf& src, DepthMapf& src_corr, DepthMapf& dst, const Intr& intr_depth,
+                               const DepthDist& dp, int numSMs = -1)
+{
+  (void)numSMs; (void)src_corr;  // the corrected intermediate map is never materialised (csrc/calib_ops.cu)
+  CallTimer t;
+  rgbid_intr i = to_c(intr_depth);
+  rgbid_depth_dist d = to_c(dp);
+  check(rgbid_undistort_depthinv(t.tc.ctx, src.ptr(), src.step(), dst.ptr(), dst.step(), src.rows(), src.cols(), &i, &d),
+        "undistortDepthInv");
+  return t.done();
+}
+
+inline float registerDepthinv(const DepthMapf& src, DepthMapf& intermediate, DeviceArray2D<int>& intermediate_as_int,
+                              DepthMapf& dst, const Mat33 dRc_proj, float3 t_dc_proj, const Mat33 cRd_proj, int numSMs = -1)
+{
+  (void)numSMs; (void)intermediate; (void)intermediate_as_int;  // the canvas lives in the context's scratch
+  CallTimer t;
+  float a[9], b[9], tt[3], zero[3];
+  to_arrays(dRc_proj, t_dc_proj, a, tt);
+  to_arrays(cRd_proj, t_dc_proj, b, zero);
+  check(rgbid_register_depthinv(t.tc.ctx, src.ptr(), src.step(), dst.ptr(), dst.step(), src.rows(), src.cols(), a, tt, b),
+        "registerDepthinv");
+  return t.done();
+}
+
+inline float integrateWarpedRGB(const DepthMapf& depth_warped_src, const IntensityMapf& r_warped_src,
+                                const IntensityMapf& g_warped_src, const IntensityMapf& b_warped_src,
+                                const DeviceArray2D<float>& weight_warped_src, DepthMapf& depth_dst, PtrStepSz<uchar3> colors_dst,
+                                DeviceArray2D<float>& weight_dst, int numSMs = -1)
+{
+  (void)numSMs;
+  CallTimer t;
+  const size_t p = depth_warped_src.step();
+  if (r_warped_src.step() != p || g_warped_src.step() != p || b_warped_src.step() != p || weight_warped_src.step() != p ||
+      depth_dst.step() != p || weight_dst.step() != p)
+    throw std::runtime_error("integrateWarpedRGB: pitch mismatch");
+  check(rgbid_integrate_warped_rgb(t.tc.ctx, depth_warped_src.ptr(), r_warped_src.ptr(), g_warped_src.ptr(), b_warped_src.ptr(),
+                                   weight_warped_src.ptr(), depth_dst.ptr(), (uint8_t*)colors_dst.data, colors_dst.step,
+                                   weight_dst.ptr(), p, depth_dst.rows(), depth_dst.cols()), "integrateWarpedRGB");
+  return t.done();
+}
+
+inline void generateImage(const MapArr& vmap, const MapArr& nmap, const LightSource& light, PtrStepSz<uchar3> dst)
+{
+  CallTimer t;
+  const float l[3] = {light.pos[0].x, light.pos[0].y, light.pos[0].z};
+  check(rgbid_generate_image(t.tc.ctx, vmap.ptr(), nmap.ptr(), vmap.step(), nullptr, 0, l, (uint8_t*)dst.data, dst.step,
+                             dst.rows, dst.cols), "generateImage");
+  t.done();
+}
+
+inline void generateImageRGB(const MapArr& vmap, const MapArr& nmap, const PtrStepSz<uchar3>& rgb, const LightSource& light,
+                             PtrStepSz<uchar3> dst)
+{
+  CallTimer t;
+  const float l[3] = {light.pos[0].x, light.pos[0].y, light.pos[0].z};
+  check(rgbid_generate_image(t.tc.ctx, vmap.ptr(), nmap.ptr(), vmap.step(), (const uint8_t*)rgb.data, rgb.step, l,
+                             (uint8_t*)dst.data, dst.step, dst.rows, dst.cols), "generateImageRGB");
+  t.done();
 }
 
 inline float getVisibilityRatio(const DepthMapf& depth_src, const DepthMapf& depth_dst, Mat33 rotation, float3 translation,

@@ -40,6 +40,10 @@ class DepthDist(C.Structure):
                 ("yshift", C.c_int)]
 
 
+class CustomCalibration(C.Structure):
+    _fields_ = [("rgb", Intr), ("depth", Intr), ("dist", DepthDist), ("dRc", C.c_float * 9), ("t_dc", C.c_float * 3)]
+
+
 class AlignConfig(C.Structure):
     _fields_ = [("rows", C.c_int), ("cols", C.c_int), ("levels", C.c_int), ("finest_level", C.c_int),
                 ("iterations", C.c_int * MAX_LEVELS), ("batch", C.c_int), ("mode", C.c_int),
@@ -141,6 +145,7 @@ PROTOTYPES = {
     "rgbid_tracker_track": (I, [P, P, P, I, C.POINTER(FrameResult)]),
     "rgbid_tracker_prefetch": (I, [P, P, P]),
     "rgbid_tracker_set_keyframe_sink": (I, [P, P, P]),
+    "rgbid_tracker_set_custom_calibration": (I, [P, C.POINTER(CustomCalibration)]),
     "rgbid_tracker_track_device": (I, [P, P, SZ, SZ, P, SZ, SZ, C.POINTER(FrameResult)]),
     "rgbid_tracker_keyframe_map": (I, [P, I, I, C.POINTER(P), C.POINTER(SZ)]),
     "rgbid_tracker_overlap_mask": (I, [P, I, C.POINTER(P), C.POINTER(SZ)]),

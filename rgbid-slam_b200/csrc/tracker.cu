@@ -117,6 +117,11 @@ struct rgbid_tracker {
   Proj* d_proj; Proj* h_proj;              // [4][batch]: odo cur->KF, odo KF->cur, integr cur->KF, integr KF->cur
   unsigned int* d_counts; unsigned int* h_counts;  // [batch][8]
   int* d_flags; int* h_flags;              // [3][batch]: new odo KF, new integration KF, fuse
+  // custom calibration (rgbid_tracker_set_custom_calibration): parameters, projective matrices, one stream of scratch
+  bool custom_on;
+  rgbid_custom_calibration custom;
+  float dRc_proj[9], t_dc_proj[3], cRd_proj[9];
+  char* d_custom; ImgB cW, cI, cPre; int* d_canvas; size_t canvas_pitch;
   // keyframe hand-off (rgbid_tracker_set_keyframe_sink): pinned host staging for one outgoing keyframe
   rgbid_keyframe_sink sink; void* sink_user;
   char* h_handoff; size_t handoff_bytes;
@@ -206,6 +211,7 @@ int rgbid_tracker_create(rgbid_ctx* ctx, const rgbid_tracker_config* cfg, rgbid_
   if (t->cfg.max_integr_kf_count <= 0) t->cfg.max_integr_kf_count = 9999999;
   t->al = nullptr; t->d_arena = nullptr; t->d_proj = nullptr; t->h_proj = nullptr; t->d_counts = nullptr;
   t->h_counts = nullptr; t->d_flags = nullptr; t->h_flags = nullptr;
+  t->custom_on = false; t->d_custom = nullptr; t->d_canvas = nullptr;
   t->sink = nullptr; t->sink_user = nullptr; t->h_handoff = nullptr; t->handoff_bytes = 0;
   t->copy_stream = nullptr; t->pf_next = 0;
   for (int i = 0; i < 2; ++i) { t->ev_copy[i] = nullptr; t->d_prefetch[i] = nullptr; t->pf_depth[i] = t->pf_rgb[i] = nullptr; t->pf_valid[i] = false; }
@@ -251,6 +257,7 @@ int rgbid_tracker_destroy(rgbid_tracker* t)
   if (t->copy_stream) { cudaStreamSynchronize(t->copy_stream); cudaStreamDestroy(t->copy_stream); }
   for (int i = 0; i < 2; ++i) { if (t->ev_copy[i]) cudaEventDestroy(t->ev_copy[i]); cudaFree(t->d_prefetch[i]); }
   cudaFree(t->d_arena); cudaFree(t->d_proj); cudaFree(t->d_counts); cudaFree(t->d_flags);
+  cudaFree(t->d_custom);
   if (t->h_handoff) cudaFreeHost(t->h_handoff);
   if (t->h_proj) cudaFreeHost(t->h_proj);
   if (t->h_counts) cudaFreeHost(t->h_counts);
@@ -312,6 +319,44 @@ int rgbid_tracker_overlap_mask(rgbid_tracker* t, int index, uint8_t** ptr, size_
 
 static int track_core(rgbid_tracker* t, const uint16_t* depth, const uint8_t* rgb, int from_host, size_t in_dpitch,
                       size_t in_dstride, size_t in_cpitch, size_t in_cstride, rgbid_frame_result* results);
+
+int rgbid_tracker_set_custom_calibration(rgbid_tracker* t, const rgbid_custom_calibration* cal)
+{
+  if (!t) return RGBID_ERR_ARG;
+  if (!cal) { t->custom_on = false; return RGBID_OK; }
+  const rgbid_align_config& c = t->al->cfg;
+  if (!t->d_custom) {
+    const LevelGeom& g = t->al->geom[0];
+    t->canvas_pitch = align_up((size_t)3 * c.cols * sizeof(int), 128);
+    const size_t maps = 3 * g.sstride, canvas = t->canvas_pitch * 3 * c.rows;
+    RGBID_CUDA_TRY(cudaMalloc(&t->d_custom, maps + canvas));
+    t->cW = make_img((float*)t->d_custom, g.pitch, c.rows, c.cols, 0);
+    t->cI = make_img((float*)(t->d_custom + g.sstride), g.pitch, c.rows, c.cols, 0);
+    t->cPre = make_img((float*)(t->d_custom + 2 * g.sstride), g.pitch, c.rows, c.cols, 0);
+    t->d_canvas = (int*)(t->d_custom + maps);
+  }
+  t->custom = *cal;
+  // dRc_proj = Kd dRc Kc^-1, t_dc_proj = Kd t_dc, cRd_proj = dRc_proj^-1 in float (src/visodo.cpp:792-801)
+  const rgbid_intr& kc = cal->rgb;
+  const rgbid_intr& kd = cal->depth;
+  const float Kd[9] = {kd.fx, 0.f, kd.cx, 0.f, kd.fy, kd.cy, 0.f, 0.f, 1.f};
+  const float Kci[9] = {1.f / kc.fx, 0.f, -kc.cx / kc.fx, 0.f, 1.f / kc.fy, -kc.cy / kc.fy, 0.f, 0.f, 1.f};
+  float T[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) T[3 * i + j] = Kd[3 * i] * cal->dRc[j] + Kd[3 * i + 1] * cal->dRc[3 + j] + Kd[3 * i + 2] * cal->dRc[6 + j];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) t->dRc_proj[3 * i + j] = T[3 * i] * Kci[j] + T[3 * i + 1] * Kci[3 + j] + T[3 * i + 2] * Kci[6 + j];
+  for (int i = 0; i < 3; ++i) t->t_dc_proj[i] = Kd[3 * i] * cal->t_dc[0] + Kd[3 * i + 1] * cal->t_dc[1] + Kd[3 * i + 2] * cal->t_dc[2];
+  const float* M = t->dRc_proj;
+  const float c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
+  const float id = 1.f / (M[0] * c00 + M[1] * c01 + M[2] * c02);
+  float* I = t->cRd_proj;
+  I[0] = c00 * id; I[1] = (M[2] * M[7] - M[1] * M[8]) * id; I[2] = (M[1] * M[5] - M[2] * M[4]) * id;
+  I[3] = c01 * id; I[4] = (M[0] * M[8] - M[2] * M[6]) * id; I[5] = (M[2] * M[3] - M[0] * M[5]) * id;
+  I[6] = c02 * id; I[7] = (M[1] * M[6] - M[0] * M[7]) * id; I[8] = (M[0] * M[4] - M[1] * M[3]) * id;
+  t->custom_on = true;
+  return RGBID_OK;
+}
 
 int rgbid_tracker_set_keyframe_sink(rgbid_tracker* t, rgbid_keyframe_sink cb, void* user)
 {
@@ -454,8 +499,21 @@ static int track_core(rgbid_tracker* t, const uint16_t* depth, const uint8_t* rg
     }
     d_depth = al->d_depth_raw; d_rgb = al->d_rgb_raw; dstride = raw_depth; cstride = raw_rgb;
   }
-  launch_ingest(L, d_depth, dpitch, dstride, d_rgb, cpitch, cstride, al->maps[MAP_W_CUR][0],
-                al->maps[MAP_I_CUR][0], B, c.factor_depth);
+  if (!t->custom_on) {
+    launch_ingest(L, d_depth, dpitch, dstride, d_rgb, cpitch, cstride, al->maps[MAP_W_CUR][0],
+                  al->maps[MAP_I_CUR][0], B, c.factor_depth);
+  } else {
+    // prepareImagesCustomCalibration (src/visodo.cpp:775-823), stream by stream through one set of scratch maps
+    const int crows = 3 * rows, ccols = 3 * cols;
+    for (int b = 0; b < B; ++b) {
+      launch_ingest(L, (const uint16_t*)((const char*)d_depth + dstride * b), dpitch, 0, d_rgb + cstride * b, cpitch, 0, t->cW,
+                    t->cI, 1, c.factor_depth);
+      launch_undistort_intensity(L, t->cI, al->view(MAP_I_CUR, 0, b), t->custom.rgb);
+      launch_undistort_depthinv(L, t->cW, t->cPre, t->custom.depth, t->custom.dist);
+      launch_register_depthinv(L, t->cPre, al->view(MAP_W_CUR, 0, b), t->d_canvas, t->canvas_pitch, crows, ccols, t->dRc_proj,
+                               t->t_dc_proj, t->cRd_proj);
+    }
+  }
   aligner_current_pyramid(al, 0, B);
 
   // ---- first frame: everything becomes a keyframe (src/visodo.cpp:1994-2045) ---------------------------------

@@ -510,6 +510,20 @@ class Tracker:
         capi.check(self.lib.rgbid_tracker_track(self.h, pd, pc, host, self.results), "tracker_track")
         return self.results
 
+    def set_custom_calibration(self, rgb_intr, depth_intr, dist, dRc, t_dc):
+        """Ingest every frame through the reference's custom-calibration path (prepareImagesCustomCalibration,
+        src/visodo.cpp:775-823); dicts as in Context.undistort_*; None for rgb_intr switches it off."""
+        if rgb_intr is None:
+            capi.check(self.lib.rgbid_tracker_set_custom_calibration(self.h, None), "set_custom_calibration")
+            return
+        cal = capi.CustomCalibration()
+        cal.rgb, cal.depth = Context._intr(rgb_intr), Context._intr(depth_intr)
+        cal.dist = capi.DepthDist(float(dist["c1"]), float(dist["c0"]), (C.c_float * 9)(*dist["q0"]), (C.c_float * 9)(*dist["q1"]),
+                                  int(dist["xshift"]), int(dist["yshift"]))
+        cal.dRc = (C.c_float * 9)(*np.reshape(dRc, -1).tolist())
+        cal.t_dc = (C.c_float * 3)(*np.reshape(t_dc, -1).tolist())
+        capi.check(self.lib.rgbid_tracker_set_custom_calibration(self.h, C.byref(cal)), "set_custom_calibration")
+
     def set_keyframe_sink(self, fn):
         """fn(dict) is called inside track() for every outgoing integration keyframe (resetIntegrationKeyframe,
         src/visodo.cpp:1577-1672): indices, global pose, SEQ_KF constraint + covariance, and numpy copies of the

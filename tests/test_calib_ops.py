@@ -125,3 +125,42 @@ def test_colour_fusion_and_previews_vs_oracle_and_reference(ctx):
         refk.integrate_warped_rgb(cu(dw), cu(chans[0]), cu(chans[1]), cu(chans[2]), cu(ww), r_d, r_c, r_w)
         assert np.array_equal(g_d.cpu().numpy(), r_d.cpu().numpy(), equal_nan=True)
         assert np.array_equal(g_c.cpu().numpy(), r_c.cpu().numpy()) and np.array_equal(g_w.cpu().numpy(), r_w.cpu().numpy())
+
+
+@pytest.mark.gpu
+def test_tracker_with_custom_calibration(ctx):
+    """prepareImagesCustomCalibration inside the tracker (rgbid_tracker_set_custom_calibration): the current-frame
+    maps must be exactly what the three bridge ops produce one after the other, and tracking must run on them."""
+    import ctypes as C
+    from rgbid_slam_b200 import capi, host
+    rows, cols, n = 240, 320, 4
+    seq = synth.make_sequence(seed=21, n_frames=n, rows=rows, cols=cols, noise=True)
+    s = 0.5  # the calibration file is for 640 x 480
+    rgb_i = {k: (v * s if k in ("fx", "fy", "cx", "cy") else v) for k, v in RGB_INTR.items()}
+    dep_i = {k: (v * s if k in ("fx", "fy", "cx", "cy") else v) for k, v in DEPTH_INTR.items()}
+    acfg = host.make_align_config(rows, cols, 3, capi.MODE_TRACKER, batch=2, fx=rgb_i["fx"], fy=rgb_i["fy"], cx=rgb_i["cx"],
+                                  cy=rgb_i["cy"])
+    trk = host.Tracker(ctx, host.make_tracker_config(acfg))
+    trk.set_custom_calibration(rgb_i, dep_i, DEPTH_DIST, DRC, T_DC)
+    for k in range(n):
+        d, c = seq["depth"][k].cuda(), seq["rgb"][k].cuda()
+        res = trk.track(torch.stack([d, d]).contiguous(), torch.stack([c, c]).contiguous())
+        assert res[0].status == 0 and res[1].status == 0
+    # maps of the last frame, stream 1
+    p, pitch = C.c_void_p(), C.c_size_t()
+    got = {}
+    for name, which in (("W", 6), ("I", 7)):  # MAP_W_CUR, MAP_I_CUR (csrc/aligner.hpp)
+        capi.check(trk.lib.rgbid_aligner_map(trk.aligner_handle, which, 0, 1, C.byref(p), C.byref(pitch)), "aligner_map")
+        got[name] = host._wrap_device(p.value, rows, cols, pitch.value, ctx.device)
+    W = ctx.convert_depth_to_invdepth(seq["depth"][n - 1].cuda())
+    I = ctx.compute_intensity(seq["rgb"][n - 1].cuda())
+    K = lambda i: np.array([[i["fx"], 0, i["cx"]], [0, i["fy"], i["cy"]], [0, 0, 1]], dtype=np.float32)
+    dRc_proj = (K(dep_i) @ DRC @ np.linalg.inv(K(rgb_i))).astype(np.float32)
+    want_I = ctx.undistort_intensity(I, rgb_i)
+    want_W = ctx.register_depthinv(ctx.undistort_depthinv(W, dep_i, DEPTH_DIST), dRc_proj, (K(dep_i) @ T_DC).astype(np.float32),
+                                   np.linalg.inv(dRc_proj).astype(np.float32))
+    assert torch.equal(torch.nan_to_num(got["I"], nan=-1.0), torch.nan_to_num(want_I, nan=-1.0))
+    assert agree(got["W"].cpu().numpy(), want_W.cpu().numpy(), rel=1e-5, frac=0.999)  # K^-1 products differ in the last bit
+    assert float(torch.isnan(got["W"]).float().mean()) < 0.3
+    trk.set_custom_calibration(None, None, None, None, None)
+    trk.close()
