@@ -120,6 +120,33 @@ class VisodoTracker {
     if (c.getEntry("cx", e)) cx_ = (float)atof(e.getValue().c_str());
     if (c.getEntry("cy", e)) cy_ = (float)atof(e.getValue().c_str());
     if (c.getEntry("factor_depth", e)) factor_depth_ = (float)atof(e.getValue().c_str());
+    if (c.getEntry("kd", e)) {  // RGB distortion k1..k5 (src/visodo.cpp:160-168)
+      std::stringstream ss(e.getValue());
+      ss >> custom_.rgb.k1 >> custom_.rgb.k2 >> custom_.rgb.k3 >> custom_.rgb.k4 >> custom_.rgb.k5;
+    }
+    // [DEPTH_CALIBRATION] + [STEREO_DEPTH2RGB]: the custom registration path (src/visodo.cpp:183-318)
+    Section d;
+    if (settings.getSection("DEPTH_CALIBRATION", d)) {
+      if (d.getEntry("custom_registration", e)) { std::stringstream ss(e.getValue()); ss >> custom_registration_; }
+      if (d.getEntry("fx", e)) custom_.depth.fx = (float)atof(e.getValue().c_str());
+      if (d.getEntry("fy", e)) custom_.depth.fy = (float)atof(e.getValue().c_str());
+      if (d.getEntry("cx", e)) custom_.depth.cx = (float)atof(e.getValue().c_str());
+      if (d.getEntry("cy", e)) custom_.depth.cy = (float)atof(e.getValue().c_str());
+      if (d.getEntry("kd", e)) {
+        std::stringstream ss(e.getValue());
+        ss >> custom_.depth.k1 >> custom_.depth.k2 >> custom_.depth.k3 >> custom_.depth.k4 >> custom_.depth.k5;
+      }
+      if (d.getEntry("c0", e)) { std::stringstream ss(e.getValue()); ss >> custom_.dist.c0; }
+      if (d.getEntry("c1", e)) { std::stringstream ss(e.getValue()); ss >> custom_.dist.c1; }
+      if (d.getEntry("q0", e)) { std::stringstream ss(e.getValue()); for (int i = 0; i < 9; ++i) ss >> custom_.dist.q0[i]; }
+      if (d.getEntry("q1", e)) { std::stringstream ss(e.getValue()); for (int i = 0; i < 9; ++i) ss >> custom_.dist.q1[i]; }
+    }
+    if (settings.getSection("STEREO_DEPTH2RGB", d)) {
+      if (d.getEntry("dRc", e)) { std::stringstream ss(e.getValue()); for (int i = 0; i < 9; ++i) ss >> custom_.dRc[i]; }
+      if (d.getEntry("t_dc", e)) { std::stringstream ss(e.getValue()); for (int i = 0; i < 3; ++i) ss >> custom_.t_dc[i]; }
+    }
+    custom_.rgb.fx = fx_; custom_.rgb.fy = fy_; custom_.rgb.cx = cx_; custom_.rgb.cy = cy_;
+    if (trk_) apply_custom_calibration();
   }
 
   void setRGBIntrinsics(float fx, float fy, float cx = -1, float cy = -1, float = 0.f, float = 0.f, float = 0.f,
@@ -191,6 +218,12 @@ class VisodoTracker {
   int visodo_iterations_[RGBID_MAX_LEVELS];
 
  private:
+  void apply_custom_calibration()
+  {
+    int rc = rgbid_tracker_set_custom_calibration(trk_, custom_registration_ ? &custom_ : nullptr);
+    if (rc != RGBID_OK) throw std::runtime_error(std::string("rgbid_tracker_set_custom_calibration: ") + rgbid_status_string(rc));
+  }
+
   static void keyframe_sink(void* user, const rgbid_keyframe_handoff* k)
   {
     VisodoTracker* self = (VisodoTracker*)user;
@@ -222,8 +255,19 @@ class VisodoTracker {
     int rc = rgbid_tracker_create(device::thread_context().ctx, &c, &trk_);
     if (rc != RGBID_OK) throw std::runtime_error(std::string("rgbid_tracker_create: ") + rgbid_status_string(rc));
     rgbid_tracker_set_keyframe_sink(trk_, &VisodoTracker::keyframe_sink, this);
+    apply_custom_calibration();
   }
 
+  int custom_registration_ = 0;  // src/visodo.cpp:63
+  rgbid_custom_calibration custom_ = default_custom_calibration();
+  static rgbid_custom_calibration default_custom_calibration()
+  {
+    rgbid_custom_calibration c;
+    std::memset(&c, 0, sizeof(c));
+    c.dist.c1 = 1.f; c.dist.q1[0] = 0.f; c.dist.xshift = 4; c.dist.yshift = 4;  // DepthDist defaults, src/internal.h:150-155
+    c.dRc[0] = c.dRc[4] = c.dRc[8] = 1.f;                                       // dRc_ = I, t_dc_ = 0 (src/visodo.cpp:59-60)
+    return c;
+  }
   int rows_, cols_, levels_, optim_dim_, Mestimator_, motion_model_, sigma_estimator_, weighting_, warping_;
   int max_odoKF_count_, finest_level_, termination_;
   float visibility_ratio_odo_threshold_;

@@ -56,3 +56,39 @@ def test_app_on_tum_sequence(built, tmp_path):
                        capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
     assert r.returncode == 0, r.stdout + r.stderr
     assert os.path.exists(tmp_path / "rgbd_dataset_synth_poses.txt")
+
+
+def test_app_with_custom_calibration_file(built, tmp_path):
+    """config_data/calibration_custom.ini dialect ([RGB_CALIBRATION], [DEPTH_CALIBRATION] custom_registration=1,
+    [STEREO_DEPTH2RGB] with a multi-line dRc): the driver must take the custom-calibration ingest path and keep tracking."""
+    rows, cols, n = 240, 320, 5
+    seq = synth.make_sequence(seed=12, n_frames=n, rows=rows, cols=cols, noise=True)
+    folder = str(tmp_path / "rgbd_dataset_custom")
+    synth.write_tum_sequence(seq, folder)
+    i = seq["intr"]
+    calib = tmp_path / "calibration_custom.ini"
+    calib.write_text(
+        "[RGB_CALIBRATION]\nfx=%r\nfy=%r\ncx=%r\ncy=%r\nkd=-0.01630   0.0   0.0   0.0  0.0\n\n"
+        "[DEPTH_CALIBRATION]\ncustom_registration=1\nfx=%r\nfy=%r\ncx=%r\ncy=%r\nkd=-0.02711   0.0   0.0   0.0  0.0\n"
+        "c1 = 0.98954\nc0 = -1.2618e-03\n"
+        "q0 =  7.0023e-03   1.0844e-02  -6.0580e-01   1.2602e+00  -2.3050e-03   1.6084e-02   2.1441e-02  -1.8073e-02  -3.6722e-02\n"
+        "q1 =  -6.7052e-03  -1.9692e-03   5.5808e-01  -1.2327e+00   1.2714e-02  -2.0804e-02  -7.5163e-03   3.1985e-02   4.8632e-02\n\n"
+        "[STEREO_DEPTH2RGB]\ndRc=\n0.9999    0.0143    0.0060\n-0.0143    0.9999   -0.0018\n-0.0060    0.0017    1.0000\n"
+        "t_dc=0.0263595 -0.0000973  0.0002853\n"
+        % (i["fx"], i["fy"], i["cx"], i["cy"], i["fx"] * 1.06, i["fy"] * 1.06, i["cx"] + 1.4, i["cy"] + 1.2))
+    log = tmp_path / "poses.txt"
+    r = subprocess.run([APP, "-eval", folder + "/", "-match_file", "matches.txt", "-calib", str(calib), "-o", str(log)],
+                       capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "frames %d" % n in r.stdout and "lost 0" in r.stdout
+    plain = tmp_path / "plain.ini"
+    plain.write_text("[CALIBRATION]\nfx=%r\nfy=%r\ncx=%r\ncy=%r\n" % (i["fx"], i["fy"], i["cx"], i["cy"]))
+    log2 = tmp_path / "poses_plain.txt"
+    r2 = subprocess.run([APP, "-eval", folder + "/", "-match_file", "matches.txt", "-calib", str(plain), "-o", str(log2)],
+                        capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert r2.returncode == 0
+    a = np.array([[float(v) for v in ln.split()] for ln in log.read_text().splitlines()])
+    b = np.array([[float(v) for v in ln.split()] for ln in log2.read_text().splitlines()])
+    assert a.shape == b.shape == (n, 8)
+    assert np.abs(a[1:, 1:4] - b[1:, 1:4]).max() > 1e-6   # a different camera model was really used ...
+    assert np.abs(a[:, 1:4] - b[:, 1:4]).max() < 0.05     # ... on the same motion
