@@ -16,7 +16,7 @@ namespace rgbid {
 namespace cg = cooperative_groups;
 
 constexpr int kScaleCluster = 8;    // CTAs per frame pair (portable cluster size limit)
-constexpr int kScaleThreads = 512;  // threads per CTA
+constexpr int kScaleThreads = 512;  // threads per CTA (256 measured the same: a round is bound by its ~550 instructions per thread, see profiles/README.md)
 constexpr int kScaleVals = 12;      // reduced values per round (6 per residual slot)
 
 // C(nu) = -psi(nu/2) + ln(nu/2) + f + 1 + psi((nu+1)/2) - ln((nu+1)/2)   (sigmaFuncs.cu:966), float arithmetic
@@ -232,7 +232,7 @@ __device__ __forceinline__ void slot_advance(ScaleSlot& s, const double* tot)
 
 struct ScaleShared {
   double warp_part[kScaleThreads / 32][kScaleVals];
-  double xchg[2][kScaleVals];  // this CTA's totals, double-buffered across rounds (read by peers via DSMEM)
+  double gath[2][kScaleCluster][kScaleVals];  // every CTA's totals, pushed by the peers through DSMEM; double-buffered
   double total[kScaleVals];
 };
 
@@ -262,27 +262,27 @@ __device__ __forceinline__ void scale_rounds(cg::cluster_group& cluster, ScaleSh
       double v = 0.0;
 #pragma unroll
       for (int w = 0; w < kScaleThreads / 32; ++w) v += sh.warp_part[w][tid];
-      sh.xchg[parity][tid] = v;
+      // push this CTA's total into every CTA of the cluster (remote shared-memory stores: fire and forget, completed
+      // by the cluster barrier), instead of every CTA pulling eight remote values after the barrier
+      const unsigned me = cluster.block_rank();
+#pragma unroll
+      for (int r = 0; r < kScaleCluster; ++r) cluster.map_shared_rank(&sh.gath[parity][me][0], r)[tid] = v;
     }
     cluster.sync();
     if (tid < kScaleVals) {
-      // all remote reads in flight at once (a DSMEM load is a few hundred ns; issued one after the other they
-      // were most of a round), then the fixed-order sum
-      double part[kScaleCluster];
-#pragma unroll
-      for (int r = 0; r < kScaleCluster; ++r) part[r] = cluster.map_shared_rank(&sh.xchg[parity][0], r)[tid];
       double v = 0.0;
 #pragma unroll
-      for (int r = 0; r < kScaleCluster; ++r) v += part[r];
+      for (int r = 0; r < kScaleCluster; ++r) v += sh.gath[parity][r][tid];  // fixed order: identical in every CTA
       sh.total[tid] = v;
     }
     __syncthreads();
     slot_advance(s0, &sh.total[0]);
     slot_advance(s1, &sh.total[6]);
     parity ^= 1;
-    __syncthreads();  // total[] / warp_part[] are rewritten next round
+    // no barrier here: total[] is rewritten only after the next round's barriers, warp_part[] after this round's
+    // readers have passed the cluster barrier, and gath[] is double-buffered (a CTA is at most one round ahead)
   }
-  // peers may still be reading this CTA's xchg through DSMEM: do not exit before they are done
+  // peers may still be writing into this CTA's shared memory: do not exit before everybody is done
   cluster.sync();
 }
 
