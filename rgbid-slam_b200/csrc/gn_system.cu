@@ -455,13 +455,16 @@ __device__ __forceinline__ void accumulate_scalar(float* acc, float s, const flo
   }
 }
 
-template <bool TRACKER, bool CHI>
+// CHIM: 0 no chi^2 sums, 1 chi^2 with the M-estimator chosen at run time, 2 chi^2 specialised for Student (the default)
+template <bool TRACKER, int CHIM>
 __global__ void __launch_bounds__(kBuildThreads, 2)
     gn_build_fast_kernel(const GnLevelMaps M, const GnParams P, const FastGeom G, GnState* __restrict__ states,
                          const ScaleState* __restrict__ scales, double* __restrict__ partials, int partial_stride,
                          unsigned int* __restrict__ counters, rgbid_iter_trace* __restrict__ trace)
 {
+  constexpr bool CHI = (CHIM != 0);
   constexpr int NACC = CHI ? kAccChi : kAcc;
+  const int chi_mest = (CHIM == 2) ? (int)RGBID_STUDENT : P.chi_mestimator;
   extern __shared__ __align__(128) unsigned char ring[];
   __shared__ BuildShared sh;
   __shared__ __align__(8) unsigned long long bars[kBuildWarps * (kStagesW + kStagesL)];
@@ -710,7 +713,7 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
         // sigmaFuncs.cu:137-150, 541-611) with the reference scales 5 / 0.0025
         if (P.chi_mestimator >= 0) {
           const float cd = (w1[k] - w0[k]) / 0.0025f;
-          if (!(isnan(cd) || isinf(cd))) { chi[2] += chi_rho_dev(cd, P.chi_mestimator); chi[3] += 1.f; }
+          if (!(isnan(cd) || isinf(cd))) { chi[2] += chi_rho_dev(cd, chi_mest); chi[3] += 1.f; }
         }
       }
 #if RGBID_ACC2
@@ -759,7 +762,7 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
       if (CHI) {
         if (P.chi_mestimator >= 0) {
           const float ci = (i1v - i0[k]) / 5.f;
-          if (!(isnan(ci) || isinf(ci))) { chi[0] += chi_rho_dev(ci, P.chi_mestimator); chi[1] += 1.f; }
+          if (!(isnan(ci) || isinf(ci))) { chi[0] += chi_rho_dev(ci, chi_mest); chi[1] += 1.f; }
         }
       }
 #if RGBID_ACC2
@@ -1006,17 +1009,20 @@ void launch_gn_build(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P
     dim3 grid(gx, P.batch);
     static bool configured = false;
     if (!configured) {
-      cudaFuncSetAttribute(gn_build_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
-      cudaFuncSetAttribute(gn_build_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
-      cudaFuncSetAttribute(gn_build_fast_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
-      cudaFuncSetAttribute(gn_build_fast_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
+      cudaFuncSetAttribute(gn_build_fast_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
+      cudaFuncSetAttribute(gn_build_fast_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
+      cudaFuncSetAttribute(gn_build_fast_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
+      cudaFuncSetAttribute(gn_build_fast_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
+      cudaFuncSetAttribute(gn_build_fast_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
+      cudaFuncSetAttribute(gn_build_fast_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
       configured = true;
     }
     const bool tracker = (P.mode == RGBID_MODE_TRACKER);
+    const int chim = !chi ? 0 : (P.chi_mestimator == RGBID_STUDENT ? 2 : 1);
 #define RGBID_FAST_LAUNCH(T, C) \
     gn_build_fast_kernel<T, C><<<grid, kBuildThreads, kFastSmemBytes, L.stream>>>(M, P, G, states, scales, partials, partial_stride, counters, trace)
-    if (tracker) { if (chi) RGBID_FAST_LAUNCH(true, true); else RGBID_FAST_LAUNCH(true, false); }
-    else { if (chi) RGBID_FAST_LAUNCH(false, true); else RGBID_FAST_LAUNCH(false, false); }
+    if (tracker) { if (chim == 0) RGBID_FAST_LAUNCH(true, 0); else if (chim == 1) RGBID_FAST_LAUNCH(true, 1); else RGBID_FAST_LAUNCH(true, 2); }
+    else { if (chim == 0) RGBID_FAST_LAUNCH(false, 0); else if (chim == 1) RGBID_FAST_LAUNCH(false, 1); else RGBID_FAST_LAUNCH(false, 2); }
 #undef RGBID_FAST_LAUNCH
     ++*L.launches;
     return;

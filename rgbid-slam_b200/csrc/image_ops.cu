@@ -365,6 +365,81 @@ __global__ void nmap_gradients_kernel(ImgB depth_inv, ImgB gx_, ImgB gy_, ImgB n
   nmap.row(b, v)[u] = nx_out;
 }
 
+// 4 pixels per thread.  The x plane is always written (value or NaN); the y / z planes only where the reference
+// writes them, with one float4 store when all four pixels qualify.
+__global__ void __launch_bounds__(BX* BY) vmap_vec_kernel(ImgB depth_inv, ImgB vmap, float fx_inv, float fy_inv, float cx,
+                                                           float cy, const int* __restrict__ active)
+{
+  const int b = blockIdx.z;
+  RGBID_ACTIVE_GUARD(b);
+  const int u0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x), v = blockIdx.y * blockDim.y + threadIdx.y;
+  const int rows = depth_inv.rows;
+  if (u0 >= depth_inv.cols || v >= rows) return;
+  float w[4], vx[4], vy[4], vz[4];
+  *(float4*)w = *(const float4*)(depth_inv.row(b, v) + u0);
+  bool ok[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float z = 1.f / w[k];
+    ok[k] = !isnan(z);
+    vx[k] = ok[k] ? z * (__int2float_rn(u0 + k) - cx) * fx_inv : qnanf();
+    vy[k] = z * (__int2float_rn(v) - cy) * fy_inv;
+    vz[k] = z;
+  }
+  *(float4*)(vmap.row(b, v) + u0) = *(float4*)vx;
+  if (ok[0] && ok[1] && ok[2] && ok[3]) {
+    *(float4*)(vmap.row(b, v + rows) + u0) = *(float4*)vy;
+    *(float4*)(vmap.row(b, v + 2 * rows) + u0) = *(float4*)vz;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (ok[k]) { vmap.row(b, v + rows)[u0 + k] = vy[k]; vmap.row(b, v + 2 * rows)[u0 + k] = vz[k]; }
+  }
+}
+
+__global__ void __launch_bounds__(BX* BY) nmap_gradients_vec_kernel(ImgB depth_inv, ImgB gx_, ImgB gy_, ImgB nmap, float fx,
+                                                                     float fy, float cx, float cy,
+                                                                     const int* __restrict__ active)
+{
+  const int b = blockIdx.z;
+  RGBID_ACTIVE_GUARD(b);
+  const int u0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x), v = blockIdx.y * blockDim.y + threadIdx.y;
+  const int rows = depth_inv.rows;
+  if (u0 >= depth_inv.cols || v >= rows) return;
+  float w4[4], gx4[4], gy4[4], ox[4], oy[4], oz[4];
+  *(float4*)w4 = *(const float4*)(depth_inv.row(b, v) + u0);
+  *(float4*)gx4 = *(const float4*)(gx_.row(b, v) + u0);
+  *(float4*)gy4 = *(const float4*)(gy_.row(b, v) + u0);
+  bool ok[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int u = u0 + k;
+    const float w = w4[k], gx = gx4[k], gy = gy4[k];
+    ox[k] = qnanf(); oy[k] = 0.f; oz[k] = 0.f; ok[k] = false;
+    if (!(isnan(w) || isnan(gx) || isnan(gy))) {
+      float nx = gx * fx, ny = gy * fy;
+      float nz = gx * (cx - __int2float_rn(u)) + gy * (cy - __int2float_rn(v)) + w;
+      float rn = rsqrtf(nx * nx + ny * ny + nz * nz);
+      nx *= rn; ny *= rn; nz *= rn;
+      float z = 1.f / w;
+      float vx = z * (__int2float_rn(u) - cx) * (1.f / fx);
+      float vy = z * (__int2float_rn(v) - cy) * (1.f / fy);
+      float rv = rsqrtf(vx * vx + vy * vy + z * z);
+      float d = (vx * rv) * nx + (vy * rv) * ny + (z * rv) * nz;
+      if (d > 0.1f) { ox[k] = nx; oy[k] = ny; oz[k] = nz; ok[k] = true; }  // grazing-angle cut (maps.cu:170)
+    }
+  }
+  *(float4*)(nmap.row(b, v) + u0) = *(float4*)ox;
+  if (ok[0] && ok[1] && ok[2] && ok[3]) {
+    *(float4*)(nmap.row(b, v + rows) + u0) = *(float4*)oy;
+    *(float4*)(nmap.row(b, v + 2 * rows) + u0) = *(float4*)oz;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (ok[k]) { nmap.row(b, v + rows)[u0 + k] = oy[k]; nmap.row(b, v + 2 * rows)[u0 + k] = oz[k]; }
+  }
+}
+
 inline bool aligned(const void* p, size_t a) { return ((uintptr_t)p % a) == 0; }
 
 }  // namespace
@@ -480,16 +555,26 @@ void launch_fill_u8(const LaunchCtx& L, uint8_t* dst, size_t pitch, size_t sstri
 void launch_vmap(const LaunchCtx& L, ImgB depth_inv, ImgB vmap, float fx, float fy, float cx, float cy, int batch,
                  const int* active)
 {
-  vmap_kernel<<<grid2d(depth_inv.cols, depth_inv.rows, batch), dim3(BX, BY), 0, L.stream>>>(
-      depth_inv, vmap, 1.f / fx, 1.f / fy, cx, cy, active);
+  auto v16 = [](const ImgB& m) { return aligned(m.p, 16) && m.pitch % 16 == 0 && m.sstride % 16 == 0; };
+  if (depth_inv.cols % 4 == 0 && v16(depth_inv) && v16(vmap))
+    vmap_vec_kernel<<<grid2d(depth_inv.cols / 4, depth_inv.rows, batch), dim3(BX, BY), 0, L.stream>>>(
+        depth_inv, vmap, 1.f / fx, 1.f / fy, cx, cy, active);
+  else
+    vmap_kernel<<<grid2d(depth_inv.cols, depth_inv.rows, batch), dim3(BX, BY), 0, L.stream>>>(
+        depth_inv, vmap, 1.f / fx, 1.f / fy, cx, cy, active);
   ++*L.launches;
 }
 
 void launch_nmap_gradients(const LaunchCtx& L, ImgB depth_inv, ImgB gx, ImgB gy, ImgB nmap, float fx, float fy,
                            float cx, float cy, int batch, const int* active)
 {
-  nmap_gradients_kernel<<<grid2d(depth_inv.cols, depth_inv.rows, batch), dim3(BX, BY), 0, L.stream>>>(
-      depth_inv, gx, gy, nmap, fx, fy, cx, cy, active);
+  auto v16 = [](const ImgB& m) { return aligned(m.p, 16) && m.pitch % 16 == 0 && m.sstride % 16 == 0; };
+  if (depth_inv.cols % 4 == 0 && v16(depth_inv) && v16(gx) && v16(gy) && v16(nmap))
+    nmap_gradients_vec_kernel<<<grid2d(depth_inv.cols / 4, depth_inv.rows, batch), dim3(BX, BY), 0, L.stream>>>(
+        depth_inv, gx, gy, nmap, fx, fy, cx, cy, active);
+  else
+    nmap_gradients_kernel<<<grid2d(depth_inv.cols, depth_inv.rows, batch), dim3(BX, BY), 0, L.stream>>>(
+        depth_inv, gx, gy, nmap, fx, fy, cx, cy, active);
   ++*L.launches;
 }
 

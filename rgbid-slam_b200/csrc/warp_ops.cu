@@ -159,6 +159,46 @@ __global__ void __launch_bounds__(BX* BY) warp_integrate_kernel(ImgB cur, ImgB k
   }
 }
 
+// 4 pixels per thread: float4 loads of the three keyframe maps, the transform staged in shared memory once per CTA,
+// float4 write-back of whatever changed (a thread owns its four pixels, so rewriting unchanged lanes is harmless).
+__global__ void __launch_bounds__(256) warp_integrate_vec_kernel(ImgB cur, ImgB kf, ImgB kf_weight, ImgB wstate,
+                                                                 const Proj* __restrict__ P_dev,
+                                                                 const int* __restrict__ active)
+{
+  const int b = blockIdx.y;
+  if (active != nullptr && active[b] == 0) return;
+  __shared__ Proj sP;
+  if (threadIdx.x < 12) ((float*)&sP)[threadIdx.x] = ((const float*)&P_dev[b])[threadIdx.x];
+  __syncthreads();
+  const Proj P = sP;
+  const int qpr = kf.cols >> 2, total = qpr * kf.rows;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+    const int y = q / qpr, x0 = (q - y * qpr) * 4;
+    float wk[4], kw[4], wsv[4];
+    *(float4*)wk = *(const float4*)(kf.row(b, y) + x0);
+    *(float4*)kw = *(const float4*)(kf_weight.row(b, y) + x0);
+    *(float4*)wsv = *(const float4*)(wstate.row(b, y) + x0);
+    bool ch_state = false, ch_kf = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float wgt;
+      bool has;
+      const float ws = warp_weighted_pixel(P, x0 + k, y, wk[k], cur.row(b, 0), cur.pitch, cur.cols, cur.rows, wgt, has);
+      if (has) { wsv[k] = wgt; ch_state = true; }
+      if (isnan(ws)) continue;
+      if (!has) wgt = wsv[k];
+      const float wk0 = wk[k], kw0 = kw[k];
+      integrate_pixel(ws, wgt, wk[k], kw[k]);
+      if (!(wk[k] == wk0) || !(kw[k] == kw0)) ch_kf = true;
+    }
+    if (ch_state) *(float4*)(wstate.row(b, y) + x0) = *(float4*)wsv;
+    if (ch_kf) {
+      *(float4*)(kf.row(b, y) + x0) = *(float4*)wk;
+      *(float4*)(kf_weight.row(b, y) + x0) = *(float4*)kw;
+    }
+  }
+}
+
 // K9 + K10: partialVisibility(WithOverlapMask)Kernel + finalVisibilityReductionKernel
 // (warping_registration.cu:297-461).  Counts are exact integers (the reference sums 1.f in float, which
 // is exact below 2^24), reduced with a warp ballot and one integer atomic per warp.
@@ -288,8 +328,17 @@ void launch_integrate(const LaunchCtx& L, ImgB wsrc, ImgB wweight, ImgB dst, Img
 void launch_warp_integrate(const LaunchCtx& L, ImgB cur, ImgB kf, ImgB kf_weight, ImgB wstate, const Proj* P_dev,
                            int batch, const int* active)
 {
-  warp_integrate_kernel<<<grid2d(kf.cols, kf.rows, batch), dim3(BX, BY), 0, L.stream>>>(cur, kf, kf_weight, wstate,
-                                                                                       P_dev, active);
+  auto v16 = [](const ImgB& m) { return ((uintptr_t)m.p % 16 == 0) && m.pitch % 16 == 0 && m.sstride % 16 == 0; };
+  if (kf.cols % 4 == 0 && v16(kf) && v16(kf_weight) && v16(wstate) && P_dev != nullptr) {
+    const int total = (kf.cols / 4) * kf.rows;
+    int gx = (total + 255) / 256;
+    const int cap = (L.num_sms * 8 + batch - 1) / batch;
+    if (gx > cap) gx = cap;
+    warp_integrate_vec_kernel<<<dim3(gx, batch), 256, 0, L.stream>>>(cur, kf, kf_weight, wstate, P_dev, active);
+  } else {
+    warp_integrate_kernel<<<grid2d(kf.cols, kf.rows, batch), dim3(BX, BY), 0, L.stream>>>(cur, kf, kf_weight, wstate,
+                                                                                         P_dev, active);
+  }
   ++*L.launches;
 }
 
