@@ -248,10 +248,11 @@ def run_b200(args, world, rank, local):
                     "upload": "next frame prefetched on a copy stream (rgbid_tracker_prefetch)"
                               if not os.environ.get("RGBID_BENCH_NO_PREFETCH") else "inside rgbid_tracker_track"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "gn_build_kernel<4,false> level 0 (fused warp+residual+JtJ)",
+            "roofline": {"bound": "hbm", "kernel": "gn_build_fast_kernel<tracker> level 0 (fused warp+residual+JtJ, TMA-staged)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes,
-                         "ms_per_launch": ms_build, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback"},
+                         "ms_per_launch": ms_build, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
+                         "note": "FP32-FMA-pipe bound (about 141 FMA-pipe instructions per pixel, 9 flop/B): see profiles/README.md"},
             "lost_streams": lost,
         }
         if not args.no_cpu_baseline:
