@@ -7,6 +7,7 @@
 // maintenance (keyframe refresh launches are predicated per stream on the device).  The host synchronises
 // twice per frame (pose read-back, covisibility read-back) to take the keyframe decisions in double
 // precision exactly like the reference's host code.
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <new>
@@ -182,6 +183,20 @@ __global__ void __launch_bounds__(256) prefetch_copy_kernel(uint4* __restrict__ 
     dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
   }
   for (; i < n16; i += stride) dst[i] = src[i];
+}
+
+// The tracker's small per-frame control uploads (initial guesses, transforms, keyframe flags: a few KB from pinned host
+// memory) go through this one-CTA zero-copy kernel instead of cudaMemcpyAsync, so they never queue behind the bulk
+// upload of the next frame on the host->device copy engine.
+__global__ void __launch_bounds__(256) control_upload_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, int n32)
+{
+  for (int i = threadIdx.x; i < n32; i += blockDim.x) dst[i] = src[i];
+}
+
+void upload_control(const LaunchCtx& L, void* dst, const void* src_pinned, size_t bytes)
+{
+  control_upload_kernel<<<1, 256, 0, L.stream>>>((uint32_t*)dst, (const uint32_t*)src_pinned, (int)(bytes / 4));
+  ++*L.launches;
 }
 
 bool host_pointer_is_device_readable(const void* p)
@@ -424,15 +439,22 @@ int rgbid_tracker_prefetch(rgbid_tracker* t, const uint16_t* depth, const uint8_
   t->pf_next ^= 1;
   char* dd = t->d_prefetch[slot];
   char* dc = t->d_prefetch[slot] + raw_depth * B;
+  // Bulk upload on the copy engine: it overlaps the tracking of the current frame without touching an SM (the system
+  // kernel is sized to fill every register file, so any co-resident copy kernel CTA pushes one of its CTAs into a second
+  // wave; measured with a zero-copy upload kernel: +0.5 .. 0.8 ms per step).  The tracker's own control uploads do not
+  // use the copy engine (upload_control), so they are not stuck behind these 49 MB.
+  static const bool zero_copy = [] { const char* e = getenv("RGBID_PREFETCH_KERNEL"); return e && e[0] == '1'; }();
   const bool dense = (raw_depth == dsz && raw_rgb == csz) && (dsz * B) % 16 == 0 && (csz * B) % 16 == 0 &&
                      ((uintptr_t)depth % 16 == 0) && ((uintptr_t)rgb % 16 == 0);
-  if (dense && host_pointer_is_device_readable(depth) && host_pointer_is_device_readable(rgb)) {
-    const int ctas = 24;  // enough loads in flight to fill the link, few enough to leave the SMs to the tracker
+  if (zero_copy && dense && host_pointer_is_device_readable(depth) && host_pointer_is_device_readable(rgb)) {
+    static const int ctas = [] { const char* e = getenv("RGBID_PREFETCH_CTAS"); int v = e ? atoi(e) : 0; return v > 0 ? v : 4; }();
     prefetch_copy_kernel<<<ctas, 256, 0, t->copy_stream>>>((uint4*)dd, (const uint4*)depth, dsz * B / 16);
     prefetch_copy_kernel<<<ctas, 256, 0, t->copy_stream>>>((uint4*)dc, (const uint4*)rgb, csz * B / 16);
     t->ctx->launches += 2;
+  } else if (raw_depth == dsz && raw_rgb == csz) {
+    RGBID_CUDA_TRY(cudaMemcpyAsync(dd, depth, dsz * B, cudaMemcpyHostToDevice, t->copy_stream));
+    RGBID_CUDA_TRY(cudaMemcpyAsync(dc, rgb, csz * B, cudaMemcpyHostToDevice, t->copy_stream));
   } else {
-    // pageable host memory: per-image copies through the copy engine
     for (int b = 0; b < B; ++b) {
       RGBID_CUDA_TRY(cudaMemcpyAsync(dd + raw_depth * b, (const char*)depth + dsz * b, dsz, cudaMemcpyHostToDevice, t->copy_stream));
       RGBID_CUDA_TRY(cudaMemcpyAsync(dc + raw_rgb * b, rgb + csz * b, csz, cudaMemcpyHostToDevice, t->copy_stream));
@@ -563,7 +585,7 @@ static int track_core(rgbid_tracker* t, const uint16_t* depth, const uint8_t* rg
       memcpy(ti, S.dt, sizeof(double) * 3);
     }
   }
-  RGBID_CUDA_TRY(cudaMemcpyAsync(al->d_init, al->h_init, sizeof(double) * 12 * B, cudaMemcpyHostToDevice, s));
+  upload_control(L, al->d_init, al->h_init, sizeof(double) * 12 * B);
   int rc = aligner_enqueue_device_init(al);
   if (rc != RGBID_OK) return rc;
   RGBID_CUDA_TRY(cudaMemcpyAsync(al->h_states, al->d_states, sizeof(GnState) * B, cudaMemcpyDeviceToHost, s));
@@ -612,7 +634,7 @@ static int track_core(rgbid_tracker* t, const uint16_t* depth, const uint8_t* rg
     to_proj(dRi, dti, c, &t->h_proj[2 * B + b]);
     to_proj_inverse(dRi, dti, c, &t->h_proj[3 * B + b]);
   }
-  RGBID_CUDA_TRY(cudaMemcpyAsync(t->d_proj, t->h_proj, sizeof(Proj) * 4 * B, cudaMemcpyHostToDevice, s));
+  upload_control(L, t->d_proj, t->h_proj, sizeof(Proj) * 4 * B);
   RGBID_CUDA_TRY(cudaMemsetAsync(t->d_counts, 0, sizeof(unsigned int) * 8 * B, s));
   Proj dummy;
   memset(&dummy, 0, sizeof(dummy));
@@ -688,7 +710,7 @@ static int track_core(rgbid_tracker* t, const uint16_t* depth, const uint8_t* rg
     any_odo |= (new_odo != 0); any_int |= (new_int != 0); any_fuse |= (fuse != 0);
     S.global_time++;
   }
-  RGBID_CUDA_TRY(cudaMemcpyAsync(t->d_flags, t->h_flags, sizeof(int) * 3 * B, cudaMemcpyHostToDevice, s));
+  upload_control(L, t->d_flags, t->h_flags, sizeof(int) * 3 * B);
   if (any_odo) {
     // saveCurrentImagesAsOdoKeyframes (:826-878), predicated per stream
     aligner_copy_current_to_keyframe(al, 0, B, t->d_flags + 0 * B);

@@ -35,3 +35,15 @@ print("track device     %.3f ms" % wall(only_track_dev, 2));
 print("track host       %.3f ms" % wall(track_host, 2))
 trk.prefetch(hd[k[0]], hc[k[0]])
 print("track prefetched %.3f ms" % wall(track_prefetched, 3))
+
+# does an unrelated, concurrent host->device copy slow the tracker down?
+side = torch.cuda.Stream()
+dst_d, dst_c = torch.empty_like(depth[0]), torch.empty_like(rgb[0])
+def track_dev_with_unrelated_copy():
+    with torch.cuda.stream(side):
+        dst_d.copy_(hd[5], non_blocking=True); dst_c.copy_(hc[5], non_blocking=True)
+    trk.track(depth[k[0]], rgb[k[0]]); k[0] += 1
+k[0] = 3
+print("track device + unrelated H2D on another stream %.3f ms" % wall(track_dev_with_unrelated_copy, 3))
+k[0] = 3
+print("track device (again)   %.3f ms" % wall(only_track_dev, 3))
