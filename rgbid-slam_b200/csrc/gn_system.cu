@@ -457,7 +457,7 @@ __device__ __forceinline__ void accumulate_scalar(float* acc, float s, const flo
 
 // CHIM: 0 no chi^2 sums, 1 chi^2 with the M-estimator chosen at run time, 2 chi^2 specialised for Student (the default)
 template <bool TRACKER, int CHIM>
-__global__ void __launch_bounds__(kBuildThreads, 2)
+__global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
     gn_build_fast_kernel(const GnLevelMaps M, const GnParams P, const FastGeom G, GnState* __restrict__ states,
                          const ScaleState* __restrict__ scales, double* __restrict__ partials, int partial_stride,
                          unsigned int* __restrict__ counters, rgbid_iter_trace* __restrict__ trace)
@@ -1005,8 +1005,8 @@ void launch_gn_build(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P
     G.nchunks = (G.npx + kChunkPx - 1) / kChunkPx;
     G.colsf = (float)P.cols; G.inv_cols = 1.f / (float)P.cols;
     G.inv_hx = 2.f / (float)P.cols; G.inv_hy = 2.f / (float)P.rows;
-    // one balanced wave of 2 CTAs / SM over all pairs; a pair never gets more CTAs than it has 8-chunk groups
-    int cap = (2 * L.num_sms) / (P.batch_total > 0 ? P.batch_total : P.batch);
+    // one balanced wave of kBuildMinBlocks CTAs / SM over all pairs; a pair never gets more CTAs than it has 8-chunk groups
+    int cap = (kBuildMinBlocks * L.num_sms) / (P.batch_total > 0 ? P.batch_total : P.batch);
     if (cap < 1) cap = 1;
     if (cap > L.num_sms) cap = L.num_sms;
     int gx = (G.nchunks + kBuildWarps - 1) / kBuildWarps;
