@@ -39,7 +39,7 @@ ALGO_BYTES_PER_PX = 32  # 6 keyframe maps + 2 current-frame maps, fp32 (SURVEY.m
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=int(os.environ.get("RGBID_BENCH_STREAMS", "32")),
@@ -75,7 +75,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.02)
 
     def stop(self):
         self._stop_evt.set()
