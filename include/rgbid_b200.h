@@ -363,7 +363,8 @@ int rgbid_tracker_track(rgbid_tracker* trk, const uint16_t* depth, const uint8_t
  * on a copy stream and return immediately.  A following rgbid_tracker_track(trk, depth, rgb, 1, ...) with the same two
  * pointers uses the uploaded copy instead of copying again, so the upload overlaps the tracking of the current frame
  * (the reference uploads and tracks strictly one after the other, tools/RGBID_SLAMapp.cpp:163-214).  One frame may be
- * in flight; the host buffers must stay valid and unchanged until that track call returns. */
+ * in flight; the host buffers must stay valid and unchanged until that track call returns.  A prefetched frame is used by
+ * the current or the next track call only; after that it is dropped and the frame is copied inside the call as usual. */
 int rgbid_tracker_prefetch(rgbid_tracker* trk, const uint16_t* depth, const uint8_t* rgb);
 /* Same with pitched DEVICE buffers (what VisodoTracker::depth_ / rgb24_ are: DeviceArray2D, include/visodo.h:118-119):
  * row pitch and per-stream stride in bytes (stride is ignored when batch == 1). */

@@ -131,6 +131,7 @@ struct rgbid_tracker {
   cudaStream_t copy_stream; cudaEvent_t ev_copy[2];
   char* d_prefetch[2];                     // [batch] depth, then [batch] rgb (same layout as the aligner's raw staging)
   const void* pf_depth[2]; const void* pf_rgb[2]; bool pf_valid[2]; int pf_next;
+  long long pf_issued_at[2], track_calls;  // a prefetched frame is good for the current or the next track call only
 };
 
 namespace {
@@ -228,7 +229,7 @@ int rgbid_tracker_create(rgbid_ctx* ctx, const rgbid_tracker_config* cfg, rgbid_
   t->h_counts = nullptr; t->d_flags = nullptr; t->h_flags = nullptr;
   t->custom_on = false; t->d_custom = nullptr; t->d_canvas = nullptr;
   t->sink = nullptr; t->sink_user = nullptr; t->h_handoff = nullptr; t->handoff_bytes = 0;
-  t->copy_stream = nullptr; t->pf_next = 0;
+  t->copy_stream = nullptr; t->pf_next = 0; t->track_calls = 0; t->pf_issued_at[0] = t->pf_issued_at[1] = 0;
   for (int i = 0; i < 2; ++i) { t->ev_copy[i] = nullptr; t->d_prefetch[i] = nullptr; t->pf_depth[i] = t->pf_rgb[i] = nullptr; t->pf_valid[i] = false; }
   int rc = rgbid_aligner_create(ctx, &t->cfg.align, &t->al);
   if (rc != RGBID_OK) { delete t; return rc; }
@@ -461,7 +462,7 @@ int rgbid_tracker_prefetch(rgbid_tracker* t, const uint16_t* depth, const uint8_
     }
   }
   RGBID_CUDA_TRY(cudaEventRecord(t->ev_copy[slot], t->copy_stream));
-  t->pf_depth[slot] = depth; t->pf_rgb[slot] = rgb; t->pf_valid[slot] = true;
+  t->pf_depth[slot] = depth; t->pf_rgb[slot] = rgb; t->pf_valid[slot] = true; t->pf_issued_at[slot] = t->track_calls;
   return RGBID_OK;
 }
 
@@ -497,8 +498,12 @@ static int track_core(rgbid_tracker* t, const uint16_t* depth, const uint8_t* rg
   const uint8_t* d_rgb = rgb;
   size_t dstride = in_dstride, cstride = in_cstride, dpitch = in_dpitch, cpitch = in_cpitch;
   int pf = -1;
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 2; ++i) {
+    // expired: prefetched more than one track call ago (the caller may have refilled that host buffer since)
+    if (t->pf_valid[i] && t->track_calls - t->pf_issued_at[i] > 1) t->pf_valid[i] = false;
     if (from_host && t->pf_valid[i] && t->pf_depth[i] == (const void*)depth && t->pf_rgb[i] == (const void*)rgb) pf = i;
+  }
+  ++t->track_calls;
   if (pf >= 0) {
     // this frame was uploaded by rgbid_tracker_prefetch while the previous one was being tracked
     dpitch = (size_t)cols * 2; cpitch = (size_t)cols * 3;

@@ -253,3 +253,25 @@ def test_tracker_prefetch_is_the_same_tracker(ctx):
         poses.append(out)
     for (Ra, ta, ka), (Rb, tb, kb) in zip(*poses):
         assert np.array_equal(Ra, Rb) and np.array_equal(ta, tb) and ka == kb
+
+
+def test_stale_prefetch_is_dropped(ctx):
+    """A prefetched frame is good for the current or the next track call only: a host buffer that was prefetched,
+    not tracked, refilled and tracked later must be read again."""
+    rows, cols, n = 240, 320, 4
+    seq = synth.make_sequence(seed=78, n_frames=n, rows=rows, cols=cols, noise=True)
+    acfg = host.make_align_config(rows, cols, 3, capi.MODE_TRACKER, batch=1, **seq["intr"])
+    frames = [(seq["depth"][k][None].contiguous().pin_memory(), seq["rgb"][k][None].contiguous().pin_memory()) for k in range(n)]
+    trk = host.Tracker(ctx, host.make_tracker_config(acfg))
+    want = [np.array(trk.track(*frames[k])[0].t[:]) for k in range(n)]
+    trk.close()
+    trk = host.Tracker(ctx, host.make_tracker_config(acfg))
+    sd, sc = frames[1][0].clone().pin_memory(), frames[1][1].clone().pin_memory()
+    trk.track(*frames[0])
+    trk.prefetch(sd, sc)          # frame 1's bytes are uploaded ...
+    trk.track(*frames[1])         # ... but another buffer is tracked (twice)
+    trk.track(*frames[2])
+    sd.copy_(frames[3][0]); sc.copy_(frames[3][1])
+    got = np.array(trk.track(sd, sc)[0].t[:])  # the refilled buffer must be read again, not served from the old upload
+    trk.close()
+    assert np.array_equal(got, want[3])
