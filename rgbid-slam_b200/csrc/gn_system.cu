@@ -400,8 +400,7 @@ constexpr int kFastSmemBytes = kBuildWarps * kWarpRingBytes;                    
 struct FastGeom {
   int npx;        // rows * cols
   int nchunks;    // ceil(npx / 128)
-  float colsf, inv_cols;
-  float inv_hx, inv_hy;  // 2 / cols, 2 / rows
+  float colsf, rowsf, inv_cols;
 };
 
 // the 27 sums in the reference's order from the 15 packed accumulators (see accumulate_packed)
@@ -579,10 +578,11 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
   const unsigned char* ringW_p = ring + (size_t)wid * kWarpRingBytes + (size_t)lane * 16;
   const unsigned char* ringL_p = ringW_p + kStagesW * kChunkBytes;
   auto lds_w0 = [&](int i, float* w0) { *(float4*)w0 = *(const float4*)(ringW_p + (size_t)(i % kStagesW) * kChunkBytes); };
-  // 0 <= xt < cols && 0 <= yt < rows as max(|2 xt / cols - 1|, |2 yt / rows - 1|) < 1 (false for the NaN coordinates
-  // of an invalid geometry); returned as 0 / NaN so that it can be added to the sample later
+  // floor(xt) in [0, cols) && floor(yt) in [0, rows) (warping_registration.cu:490-491) as four float compares -- exact,
+  // false for the NaN coordinates of an invalid geometry, and on the ALU pipe (this kernel is bound by the FMA pipe);
+  // returned as 0 / NaN so that it can be added to the sample later
   auto in_image_nan = [&](float xt, float yt) {
-    return (fmaxf(fabsf(fmaf(xt, G.inv_hx, -1.f)), fabsf(fmaf(yt, G.inv_hy, -1.f))) < 1.f) ? 0.f : qnanf();
+    return (xt >= 0.f && xt < G.colsf && yt >= 0.f && yt < G.rowsf) ? 0.f : qnanf();
   };
   // S2: first projection (geometry = keyframe inverse depth) of chunk i and its gather(s)
   auto gather = [&](int i, float* w2, float* wcs, float* i1, float* pinf) {
@@ -1003,8 +1003,7 @@ void launch_gn_build(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P
     FastGeom G;
     G.npx = P.rows * P.cols;
     G.nchunks = (G.npx + kChunkPx - 1) / kChunkPx;
-    G.colsf = (float)P.cols; G.inv_cols = 1.f / (float)P.cols;
-    G.inv_hx = 2.f / (float)P.cols; G.inv_hy = 2.f / (float)P.rows;
+    G.colsf = (float)P.cols; G.rowsf = (float)P.rows; G.inv_cols = 1.f / (float)P.cols;
     // one balanced wave of kBuildMinBlocks CTAs / SM over all pairs; a pair never gets more CTAs than it has 8-chunk groups
     int cap = (kBuildMinBlocks * L.num_sms) / (P.batch_total > 0 ? P.batch_total : P.batch);
     if (cap < 1) cap = 1;
