@@ -234,6 +234,7 @@ struct ScaleShared {
   double warp_part[kScaleThreads / 32][kScaleVals];
   double gath[2][kScaleCluster][kScaleVals];  // every CTA's totals, pushed by the peers through DSMEM; double-buffered
   double total[kScaleVals];
+  ScaleSlot slots[2];  // state after this round's control flow, published by the first warp
 };
 
 // Runs all rounds for the two slots.  samples0/1: this CTA's slice of each residual vector (shared or global
@@ -251,11 +252,26 @@ __device__ __forceinline__ void scale_rounds(cg::cluster_group& cluster, ScaleSh
     for (int k = 0; k < kScaleVals; ++k) acc[k] = 0.f;
     if (s0.phase != PH_DONE) slot_accumulate_all(s0, samples0, n_local, acc);
     if (s1.phase != PH_DONE) slot_accumulate_all(s1, samples1, n_local, acc + 6);
-    // float inside the warp (<= ~10 samples per lane; the reference sums in float throughout), double above
+    // float inside the warp (<= ~10 samples per lane; the reference sums in float throughout), double above.
+    // The 12 sums are reduced together: after the exchange with lane ^ 16 a lane keeps only half of the values, then a
+    // quarter, ... -- 8 + 4 + 2 + 1 + 1 = 16 shuffles instead of 12 x 5; lane l ends with the total of value (l >> 1) & 15.
+    {
+      float v[16];
 #pragma unroll
-    for (int k = 0; k < kScaleVals; ++k) {
-      float v = warp_sum(acc[k]);
-      if (lane == 0) sh.warp_part[wid][k] = (double)v;
+      for (int k = 0; k < 16; ++k) v[k] = (k < kScaleVals) ? acc[k] : 0.f;
+#pragma unroll
+      for (int h = 8, m = 16; h >= 1; h >>= 1, m >>= 1) {
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+          const float send = up ? v[i] : v[i + h];
+          const float keep = up ? v[i + h] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
+      }
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+      const int idx = (lane >> 1) & 15;
+      if (!(lane & 1) && idx < kScaleVals) sh.warp_part[wid][idx] = (double)v[0];
     }
     __syncthreads();
     if (tid < kScaleVals) {
@@ -269,18 +285,25 @@ __device__ __forceinline__ void scale_rounds(cg::cluster_group& cluster, ScaleSh
       for (int r = 0; r < kScaleCluster; ++r) cluster.map_shared_rank(&sh.gath[parity][me][0], r)[tid] = v;
     }
     cluster.sync();
-    if (tid < kScaleVals) {
-      double v = 0.0;
+    // the host control flow runs in the first warp only (every CTA of the cluster: identical inputs, identical
+    // decisions); the other warps pick up the new state after the barrier they need anyway
+    if (wid == 0) {
+      if (lane < kScaleVals) {
+        double v = 0.0;
 #pragma unroll
-      for (int r = 0; r < kScaleCluster; ++r) v += sh.gath[parity][r][tid];  // fixed order: identical in every CTA
-      sh.total[tid] = v;
+        for (int r = 0; r < kScaleCluster; ++r) v += sh.gath[parity][r][lane];  // fixed order: identical in every CTA
+        sh.total[lane] = v;
+      }
+      __syncwarp();
+      slot_advance(s0, &sh.total[0]);
+      slot_advance(s1, &sh.total[6]);
+      if (lane == 0) { sh.slots[0] = s0; sh.slots[1] = s1; }
     }
     __syncthreads();
-    slot_advance(s0, &sh.total[0]);
-    slot_advance(s1, &sh.total[6]);
+    if (wid != 0) { s0 = sh.slots[0]; s1 = sh.slots[1]; }
     parity ^= 1;
-    // no barrier here: total[] is rewritten only after the next round's barriers, warp_part[] after this round's
-    // readers have passed the cluster barrier, and gath[] is double-buffered (a CTA is at most one round ahead)
+    // no barrier here: total[] and slots[] are rewritten only after the next round's barriers, warp_part[] after this
+    // round's readers have passed the cluster barrier, and gath[] is double-buffered (a CTA is at most one round ahead)
   }
   // peers may still be writing into this CTA's shared memory: do not exit before everybody is done
   cluster.sync();
