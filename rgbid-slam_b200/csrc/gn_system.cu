@@ -844,7 +844,7 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
 // Sampling geometry of computeErrorGridStride (sigmaFuncs.cu:711-747): sample (s y, s x) -> index y*kept_cols+x.
 // ------------------------------------------------------------------------------------------------------------
 template <bool TEX>
-__global__ void __cluster_dims__(kScaleCluster, 1, 1) __launch_bounds__(kScaleThreads)
+__global__ void __cluster_dims__(kScaleCluster, 1, 1) __launch_bounds__(kScaleThreads, 2)
     gn_scale_kernel(const GnLevelMaps M, const GnParams P, const GnState* __restrict__ states,
                     ScaleState* __restrict__ scales)
 {

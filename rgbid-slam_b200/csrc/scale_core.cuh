@@ -6,9 +6,12 @@
 // runs inside ONE kernel: an 8-CTA cluster owns the residual samples of one frame pair (both residual
 // types), keeps them in shared memory, and performs one cluster-wide reduction per round through
 // distributed shared memory; the control flow (convergence test, bisection) is evaluated redundantly and
-// identically by every thread, so no host round trip is needed.
+// identically by two warps of every CTA (one per residual type), so no host round trip is needed.
 #pragma once
 #include <cooperative_groups.h>
+#if RGBID_SCALE_PROBE
+#include <cstdio>  // -DRGBID_SCALE_PROBE=1: per-segment clock counts of the rounds, tools/scale_round_probe.py
+#endif
 #include "kernels.cuh"
 
 namespace rgbid {
@@ -16,7 +19,7 @@ namespace rgbid {
 namespace cg = cooperative_groups;
 
 constexpr int kScaleCluster = 8;    // CTAs per frame pair (portable cluster size limit)
-constexpr int kScaleThreads = 512;  // threads per CTA (256 measured the same: a round is bound by its ~550 instructions per thread, see profiles/README.md)
+constexpr int kScaleThreads = 512;  // threads per CTA (256 measured the same: the per-SM instruction total of a round does not change, see profiles/README.md)
 constexpr int kScaleVals = 12;      // reduced values per round (6 per residual slot)
 
 // C(nu) = -psi(nu/2) + ln(nu/2) + f + 1 + psi((nu+1)/2) - ln((nu+1)/2)   (sigmaFuncs.cu:966), float arithmetic
@@ -183,6 +186,17 @@ __device__ __forceinline__ void slot_accumulate_all(const ScaleSlot& s, const fl
   }
 }
 
+// Fixed-order sum of N doubles read through `at(i)` as four interleaved partial sums: a dependent chain of N / 4 + 2
+// additions instead of N (a double add is ~35 clk of latency here and one thread per value is doing this).
+template <int N, class F>
+__device__ __forceinline__ double sum4(F at)
+{
+  double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; i += 4) { q0 += at(i); q1 += at(i + 1); q2 += at(i + 2); q3 += at(i + 3); }
+  return (q0 + q1) + (q2 + q3);
+}
+
 // Host-side control flow of computeSigmaAndNuStudent / computeSigmaPdf / computeNuStudent, advanced by
 // one round given the cluster-wide totals tot[0..5] of this slot.
 __device__ __forceinline__ void slot_advance(ScaleSlot& s, const double* tot)
@@ -234,7 +248,7 @@ struct ScaleShared {
   double warp_part[kScaleThreads / 32][kScaleVals];
   double gath[2][kScaleCluster][kScaleVals];  // every CTA's totals, pushed by the peers through DSMEM; double-buffered
   double total[kScaleVals];
-  ScaleSlot slots[2];  // state after this round's control flow, published by the first warp
+  ScaleSlot slots[2];  // the two slots' state, advanced by warps 0 and 1 after every round
 };
 
 // Runs all rounds for the two slots.  samples0/1: this CTA's slice of each residual vector (shared or global
@@ -244,14 +258,37 @@ __device__ __forceinline__ void scale_rounds(cg::cluster_group& cluster, ScaleSh
 {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   int parity = 0;
+#if RGBID_SCALE_PROBE
+  long long seg[7] = {0, 0, 0, 0, 0, 0, 0};
+  int rounds_done = 0;
+#define PROBE(k) { long long now = clock64(); seg[k] += now - tprev; tprev = now; }
+#else
+#define PROBE(k)
+#endif
+  // The full state of the two slots lives in shared memory (it is only needed by the two warps that run the control
+  // flow); every thread keeps just the fields the sample loops read.
+  if (tid == 0) { sh.slots[0] = s0; sh.slots[1] = s1; }
+  __syncthreads();
+  ScaleSlot v0, v1;
+  auto load_view = [](ScaleSlot& v, const ScaleSlot& src) {
+    v.phase = src.phase; v.op = src.op; v.mest = src.mest; v.lsq = src.lsq;
+    v.bias = src.bias; v.sigma = src.sigma; v.nu_new = src.nu_new;
+  };
+  load_view(v0, sh.slots[0]);
+  load_view(v1, sh.slots[1]);
   // bounded: <= 10 IRLS + 1 + 5 bisection rounds per slot (they advance concurrently)
   for (int round = 0; round < 20; ++round) {
-    if (s0.phase == PH_DONE && s1.phase == PH_DONE) break;
+    if (v0.phase == PH_DONE && v1.phase == PH_DONE) break;
+#if RGBID_SCALE_PROBE
+    long long tprev = clock64();
+    ++rounds_done;
+#endif
     float acc[kScaleVals];
 #pragma unroll
     for (int k = 0; k < kScaleVals; ++k) acc[k] = 0.f;
-    if (s0.phase != PH_DONE) slot_accumulate_all(s0, samples0, n_local, acc);
-    if (s1.phase != PH_DONE) slot_accumulate_all(s1, samples1, n_local, acc + 6);
+    if (v0.phase != PH_DONE) slot_accumulate_all(v0, samples0, n_local, acc);
+    if (v1.phase != PH_DONE) slot_accumulate_all(v1, samples1, n_local, acc + 6);
+    PROBE(0)
     // float inside the warp (<= ~10 samples per lane; the reference sums in float throughout), double above.
     // The 12 sums are reduced together: after the exchange with lane ^ 16 a lane keeps only half of the values, then a
     // quarter, ... -- 8 + 4 + 2 + 1 + 1 = 16 shuffles instead of 12 x 5; lane l ends with the total of value (l >> 1) & 15.
@@ -273,40 +310,51 @@ __device__ __forceinline__ void scale_rounds(cg::cluster_group& cluster, ScaleSh
       const int idx = (lane >> 1) & 15;
       if (!(lane & 1) && idx < kScaleVals) sh.warp_part[wid][idx] = (double)v[0];
     }
+    PROBE(1)
     __syncthreads();
+    PROBE(2)
     if (tid < kScaleVals) {
-      double v = 0.0;
-#pragma unroll
-      for (int w = 0; w < kScaleThreads / 32; ++w) v += sh.warp_part[w][tid];
+      const double v = sum4<kScaleThreads / 32>([&](int w) { return sh.warp_part[w][tid]; });
       // push this CTA's total into every CTA of the cluster (remote shared-memory stores: fire and forget, completed
       // by the cluster barrier), instead of every CTA pulling eight remote values after the barrier
       const unsigned me = cluster.block_rank();
 #pragma unroll
       for (int r = 0; r < kScaleCluster; ++r) cluster.map_shared_rank(&sh.gath[parity][me][0], r)[tid] = v;
     }
+    PROBE(3)
     cluster.sync();
-    // the host control flow runs in the first warp only (every CTA of the cluster: identical inputs, identical
-    // decisions); the other warps pick up the new state after the barrier they need anyway
-    if (wid == 0) {
-      if (lane < kScaleVals) {
-        double v = 0.0;
-#pragma unroll
-        for (int r = 0; r < kScaleCluster; ++r) v += sh.gath[parity][r][lane];  // fixed order: identical in every CTA
-        sh.total[lane] = v;
+    PROBE(4)
+    // the host control flow runs in two warps only, one per residual slot (in every CTA of the cluster: identical
+    // inputs, identical decisions); the other warps pick up the new state after the barrier they need anyway
+    if (wid < 2) {
+      if (lane < 6) {
+        const int k = 6 * wid + lane;  // fixed order: identical in every CTA
+        sh.total[k] = sum4<kScaleCluster>([&](int r) { return sh.gath[parity][r][k]; });
       }
       __syncwarp();
-      slot_advance(s0, &sh.total[0]);
-      slot_advance(s1, &sh.total[6]);
-      if (lane == 0) { sh.slots[0] = s0; sh.slots[1] = s1; }
+      ScaleSlot st = sh.slots[wid];
+      slot_advance(st, &sh.total[6 * wid]);
+      __syncwarp();
+      if (lane == 0) sh.slots[wid] = st;
     }
+    PROBE(5)
     __syncthreads();
-    if (wid != 0) { s0 = sh.slots[0]; s1 = sh.slots[1]; }
+    PROBE(6)
+    load_view(v0, sh.slots[0]);
+    load_view(v1, sh.slots[1]);
     parity ^= 1;
     // no barrier here: total[] and slots[] are rewritten only after the next round's barriers, warp_part[] after this
     // round's readers have passed the cluster barrier, and gath[] is double-buffered (a CTA is at most one round ahead)
   }
   // peers may still be writing into this CTA's shared memory: do not exit before everybody is done
   cluster.sync();
+  s0 = sh.slots[0];
+  s1 = sh.slots[1];
+#if RGBID_SCALE_PROBE
+  if ((blockIdx.x == 0 || blockIdx.x == 131) && (tid == 0 || tid == 200))
+    printf("probe cta %d tid %d n_local %d rounds %d | samples %lld reduce %lld sync1 %lld sum+push %lld cluster %lld advance %lld sync2 %lld\n",
+           blockIdx.x, tid, n_local, rounds_done, seg[0], seg[1], seg[2], seg[3], seg[4], seg[5], seg[6]);
+#endif
 }
 
 }  // namespace rgbid
