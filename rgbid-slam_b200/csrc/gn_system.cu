@@ -955,14 +955,13 @@ void launch_gn_scale(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P
   const int n = P.kept_rows * P.kept_cols;
   const int chunk = (n + kScaleCluster - 1) / kScaleCluster;
   size_t smem = (size_t)2 * chunk * sizeof(float);
-  static bool table_ready = false;
-  if (!table_ready) { upload_nu_table(); table_ready = true; }
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(gn_scale_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(gn_scale_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  static PerDevice table, smem_limit;
+  table.once([] { upload_nu_table(); });
+  if (smem > 48 * 1024)
+    smem_limit.at_least(smem, [](size_t bytes) {
+      cudaFuncSetAttribute(gn_scale_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+      cudaFuncSetAttribute(gn_scale_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    });
   if (M.texW != nullptr && M.texI != nullptr)
     gn_scale_kernel<true><<<kScaleCluster * P.batch, kScaleThreads, smem, L.stream>>>(M, P, states, scales);
   else
@@ -1011,16 +1010,15 @@ void launch_gn_build(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P
     int gx = (G.nchunks + kBuildWarps - 1) / kBuildWarps;
     if (gx > cap) gx = cap;
     dim3 grid(gx, P.batch);
-    static bool configured = false;
-    if (!configured) {
+    static PerDevice configured;
+    configured.once([] {
       cudaFuncSetAttribute(gn_build_fast_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
       cudaFuncSetAttribute(gn_build_fast_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
       cudaFuncSetAttribute(gn_build_fast_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
       cudaFuncSetAttribute(gn_build_fast_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
       cudaFuncSetAttribute(gn_build_fast_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
       cudaFuncSetAttribute(gn_build_fast_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
-      configured = true;
-    }
+    });
     const bool tracker = (P.mode == RGBID_MODE_TRACKER);
     const int chim = !chi ? 0 : (P.chi_mestimator == RGBID_STUDENT ? 2 : 1);
 #define RGBID_FAST_LAUNCH(T, C) \

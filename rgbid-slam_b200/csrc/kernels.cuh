@@ -1,5 +1,6 @@
 // kernels.cuh -- internal launchers (C++ linkage) shared by the C-ABI layer.
 #pragma once
+#include <mutex>
 #include "common.cuh"
 
 namespace rgbid {
@@ -9,6 +10,34 @@ struct LaunchCtx {
   cudaStream_t stream;
   long long* launches;
   int num_sms;
+};
+
+// One-time set-up that lives in a device's context (constant tables, kernel attributes) has to happen once per DEVICE
+// the process uses, not once per process, and two host threads may get here together (the tracker and the keyframe
+// aligner call concurrently).  `once(f)` runs f the first time it is called with a given device current.
+class PerDevice {
+ public:
+  template <class F>
+  void once(F&& f)
+  {
+    std::lock_guard<std::mutex> guard(mu_);
+    const unsigned long long bit = 1ull << (current() & 63);
+    if (!(done_ & bit)) { f(); done_ |= bit; }
+  }
+  // grow-only variant: runs f(value) whenever `value` exceeds what this device has been configured for
+  template <class F>
+  void at_least(size_t value, F&& f)
+  {
+    std::lock_guard<std::mutex> guard(mu_);
+    size_t& have = level_[current() & 63];
+    if (value > have) { f(value); have = value; }
+  }
+
+ private:
+  static int current() { int dev = 0; cudaGetDevice(&dev); return dev; }
+  std::mutex mu_;
+  unsigned long long done_ = 0;
+  size_t level_[64] = {};
 };
 
 // ---- image_ops.cu ---------------------------------------------------------------------------------

@@ -90,8 +90,8 @@ void launch_compute_error(const LaunchCtx& L, ImgB im1, ImgB im0, float* error, 
 void launch_scale_from_errors(const LaunchCtx& L, const float* err0, const float* err1, int n, int op, int mest,
                               float bias0, float sigma0, float bias1, float sigma1, ScaleState* out)
 {
-  static bool table_ready = false;
-  if (!table_ready) { upload_nu_table(); table_ready = true; }
+  static PerDevice table;
+  table.once([] { upload_nu_table(); });
   scale_from_errors_kernel<<<kScaleCluster, kScaleThreads, 0, L.stream>>>(err0, err1, n, op, mest, bias0, sigma0,
                                                                           bias1, sigma1, out);
   ++*L.launches;
