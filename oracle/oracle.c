@@ -1022,10 +1022,15 @@ int orc_align(const orc_align_config* C, const orc_pyramids* P, double* R, doubl
   memset(A, 0, sizeof(A));
   int rows0 = C->rows, cols0 = C->cols;
   long maxpix = (long)rows0 * cols0;
-  float* W1 = (float*)malloc(sizeof(float) * maxpix);
-  float* I1 = (float*)malloc(sizeof(float) * maxpix);
+  float* W1buf = (float*)malloc(sizeof(float) * maxpix);
+  float* I1buf = (float*)malloc(sizeof(float) * maxpix);
   float* eI = (float*)malloc(sizeof(float) * maxpix);
   float* eW = (float*)malloc(sizeof(float) * maxpix);
+  /* WARP_ORDER = warpFirst (tracker only, src/visodo.cpp:1078-1105): second pair of buffers for the per-iteration
+   * pyramid of the warped maps */
+  const int warp_first = C->warp_first && C->mode == ORC_MODE_TRACKER;
+  float* W2 = warp_first ? (float*)malloc(sizeof(float) * maxpix) : NULL;
+  float* I2 = warp_first ? (float*)malloc(sizeof(float) * maxpix) : NULL;
   int status = 0;
 
   for (int level = C->levels - 1; level >= C->finest_level && !status; --level) {
@@ -1034,12 +1039,30 @@ int orc_align(const orc_align_config* C, const orc_pyramids* P, double* R, doubl
     level_intr(C, level, &fx, &fy, &cx, &cy);
     for (int iter = 0; iter < C->iterations[level]; ++iter) {
       float Rp[9], tp[3];
-      orc_projective_inverse_pose(R, t, fx, fy, cx, cy, Rp, tp);
-      orc_warp_invdepth(P->W_cur[level], P->W_kf[level], W1, rows, cols, Rp, tp);
-      /* tracker warps intensity with the just-warped iD as geometry (visodo.cpp:1121-1126);
-       * KeyframeAlign uses the keyframe iD (keyframe_align.cpp:239) */
-      orc_warp_intensity(P->I_cur[level], C->mode == ORC_MODE_TRACKER ? W1 : P->W_kf[level], I1, rows,
-                         cols, Rp, tp);
+      float *W1 = W1buf, *I1 = I1buf;
+      if (warp_first && level > 0) {
+        /* "expensive warping": warp at level 0 with the level-0 calibration, then build the pyramid of the
+         * warped maps down to this level, every iteration (visodo.cpp:1078-1105) */
+        float fx0, fy0, cx0, cy0;
+        level_intr(C, 0, &fx0, &fy0, &cx0, &cy0);
+        orc_projective_inverse_pose(R, t, fx0, fy0, cx0, cy0, Rp, tp);
+        orc_warp_invdepth(P->W_cur[0], P->W_kf[0], W1, rows0, cols0, Rp, tp);
+        orc_warp_intensity(P->I_cur[0], W1, I1, rows0, cols0, Rp, tp);
+        float *Wn = W2, *In = I2;
+        for (int i = 1; i <= level; ++i) {
+          orc_pyr_down(I1, rows0 >> (i - 1), cols0 >> (i - 1), In);
+          orc_pyr_down(W1, rows0 >> (i - 1), cols0 >> (i - 1), Wn);
+          float* sw = W1; W1 = Wn; Wn = sw;
+          sw = I1; I1 = In; In = sw;
+        }
+      } else {
+        orc_projective_inverse_pose(R, t, fx, fy, cx, cy, Rp, tp);
+        orc_warp_invdepth(P->W_cur[level], P->W_kf[level], W1, rows, cols, Rp, tp);
+        /* tracker warps intensity with the just-warped iD as geometry (visodo.cpp:1121-1126);
+         * KeyframeAlign uses the keyframe iD (keyframe_align.cpp:239) */
+        orc_warp_intensity(P->I_cur[level], C->mode == ORC_MODE_TRACKER ? W1 : P->W_kf[level], I1, rows,
+                           cols, Rp, tp);
+      }
       orc_system_params S;
       memset(&S, 0, sizeof(S));
       S.fx = fx; S.fy = fy; S.cx = cx; S.cy = cy;
@@ -1088,7 +1111,8 @@ int orc_align(const orc_align_config* C, const orc_pyramids* P, double* R, doubl
     /* lost: cov = 100 I (visodo.cpp:1269) */
     if (cov36) for (int i = 0; i < 36; ++i) cov36[i] = (i % 7 == 0) ? 100.0 : 0.0;
   } else if (C->mode == ORC_MODE_TRACKER) {
-    /* covariance pass, visodo.cpp:1283-1415 */
+    /* covariance pass, visodo.cpp:1283-1415 (warps at the finest level in both warp orders) */
+    float *W1 = W1buf, *I1 = I1buf;
     int level = C->finest_level;
     int rows = rows0 >> level, cols = cols0 >> level;
     float fx, fy, cx, cy, Rp[9], tp[3];
@@ -1117,6 +1141,6 @@ int orc_align(const orc_align_config* C, const orc_pyramids* P, double* R, doubl
     if (cov36) orc_inverse6(A, cov36); /* keyframe_align.cpp:339-350: last iteration's A */
   }
   if (n_trace) *n_trace = nt;
-  free(W1); free(I1); free(eI); free(eW);
+  free(W1buf); free(I1buf); free(eI); free(eW); free(W2); free(I2);
   return status;
 }

@@ -36,6 +36,7 @@ typedef struct {
   int sigma_estimator; /* tracker only */
   int nsamples;        /* 10000 tracker, 19200 align */
   float fx, fy, cx, cy; /* level-0 intrinsics */
+  int warp_first;      /* tracker only: WARP_ORDER = warpFirst (src/visodo.cpp:1078-1105); 0 = pyrFirst */
 } orc_align_config;
 
 typedef struct {

@@ -295,10 +295,26 @@ int ref_align(const orc_align_config* C, const orc_pyramids* P, double* R, doubl
     Map Wc = wrap(P->W_cur[level], pitch, rows, cols), Ic = wrap(P->I_cur[level], pitch, rows, cols);
     for (int iter = 0; iter < C->iterations[level]; ++iter) {
       float Rp[9], tp[3];
+      if (C->warp_first && C->mode == ORC_MODE_TRACKER && level > 0) {
+        /* WARP_ORDER = warpFirst, src/visodo.cpp:1078-1105: warp at level 0, pyramid of the warped maps */
+        size_t pitch0 = (size_t)C->cols * sizeof(float);
+        Intr intr0(C->fx, C->fy, C->cx, C->cy);
+        Map Wkf0 = wrap(P->W_kf[0], pitch0, C->rows, C->cols);
+        Map Wc0 = wrap(P->W_cur[0], pitch0, C->rows, C->cols), Ic0 = wrap(P->I_cur[0], pitch0, C->rows, C->cols);
+        orc_projective_inverse_pose(R, t, intr0.fx, intr0.fy, intr0.cx, intr0.cy, Rp, tp);
+        Mat33 dR0 = mat33(Rp); float3 dt0 = make_float3(tp[0], tp[1], tp[2]);
+        warpInvDepthWithTrafo3D(Wc0, W1[0], Wkf0, dR0, dt0, intr0);
+        warpIntensityWithTrafo3DInvDepth(Ic0, I1[0], W1[0], dR0, dt0, intr0);
+        for (int i = 1; i <= level; ++i) {
+          pyrDownIntensity(I1[i - 1], I1[i]);
+          pyrDownDepth(W1[i - 1], W1[i]);
+        }
+      } else {
       orc_projective_inverse_pose(R, t, intr.fx, intr.fy, intr.cx, intr.cy, Rp, tp);
       Mat33 dR = mat33(Rp); float3 dt = make_float3(tp[0], tp[1], tp[2]);
       warpInvDepthWithTrafo3D(Wc, W1[level], Wkf, dR, dt, intr, numSMs);
       warpIntensityWithTrafo3DInvDepth(Ic, I1[level], C->mode == ORC_MODE_TRACKER ? W1[level] : Wkf, dR, dt, intr, numSMs);
+      }
       float sigma_int = 5.f, sigma_w = 0.0025f, bias_int = 0.f, bias_w = 0.f, nu_int = 5.f, nu_w = 5.f;
       if (C->mode == ORC_MODE_TRACKER) {
         if (C->sigma_estimator == ORC_SIGMA_PDF) {

@@ -152,6 +152,34 @@ def test_alignment_recovers_known_motion(mode, levels, its):
     assert A[0, 5] == s[5] and b[0] == s[6] and A[1, 1] == s[7] and A[5, 5] == s[25] and b[5] == s[26] and np.array_equal(A, A.T)
 
 
+def test_warp_first_order_of_the_tracker():
+    """WARP_ORDER = warpFirst (src/visodo.cpp:1078-1105): warp at level 0, then the pyramid of the warped maps, every
+    iteration.  Same as pyrFirst when only level 0 iterates; a different (but equally convergent) path otherwise."""
+    P = pair_maps(seed=20261019, rows=240, cols=320, noise=True)
+    i = P["intr"]
+    kf, cur = orc.prepare_keyframe(P["WA"], P["IA"], 3, True), orc.prepare_current(P["WB"], P["IB"], 3)
+
+    def run(its, warp_first):
+        cfg = orc.make_config(240, 320, 3, orc.MODE_TRACKER, its, i["fx"], i["fy"], i["cx"], i["cy"], warp_first=warp_first)
+        return orc.align(cfg, kf, cur)
+
+    a, b = run([4, 0, 0], 0), run([4, 0, 0], 1)
+    # (not bit-equal: the oracle's OpenMP reductions do not fix the summation order between runs)
+    assert np.allclose(a["R"], b["R"], atol=1e-9) and np.allclose(a["t"], b["t"], atol=1e-9)
+    assert np.allclose(a["cov"], b["cov"], rtol=1e-6)
+    pf, wf = run([10, 5, 3], 0), run([10, 5, 3], 1)
+    assert wf["status"] == 0 and len(wf["trace"]) == 18
+    assert np.linalg.norm(wf["t"] - P["t_ab"]) < 5e-4 and rot_angle(wf["R"], P["R_ab"]) < 5e-4
+    # the first iteration (level 2) already sees different warped maps: pyrDown(warp(.)) != warp(pyrDown(.))
+    assert not np.array_equal(pf["trace"][0]["sums27"], wf["trace"][0]["sums27"])
+    assert np.allclose(pf["trace"][0]["sums27"][[0, 7, 13]], wf["trace"][0]["sums27"][[0, 7, 13]], rtol=0.2)
+    # KeyframeAlign has no such option (src/keyframe_align.cpp:178-350): the flag is ignored there
+    ca = orc.make_config(240, 320, 3, orc.MODE_ALIGN, [3, 3, 3], i["fx"], i["fy"], i["cx"], i["cy"], warp_first=1)
+    cb = orc.make_config(240, 320, 3, orc.MODE_ALIGN, [3, 3, 3], i["fx"], i["fy"], i["cx"], i["cy"], warp_first=0)
+    kfa = orc.prepare_keyframe(P["WA"], P["IA"], 3, False)
+    assert np.allclose(orc.align(ca, kfa, cur)["t"], orc.align(cb, kfa, cur)["t"], atol=1e-9)
+
+
 def test_alignment_reports_lost_on_empty_input():
     nan = np.full((60, 80), np.nan, dtype=np.float32)
     cfg = orc.make_config(60, 80, 2, orc.MODE_TRACKER, [2, 2], 100, 100, 40, 30)
