@@ -200,6 +200,9 @@ typedef struct {
   float fx, fy, cx, cy; /* level-0 intrinsics */
   float factor_depth;
   int with_fusion;  /* tracker: allocate integration-keyframe buffers */
+  int warp_first;   /* tracker: 1 = WARP_ORDER warpFirst (src/visodo.cpp:1078-1105: above level 0 every iteration warps
+                     * at level 0 and rebuilds the pyramid of the warped maps), 0 = pyrFirst (the shipped
+                     * config_data/visodoRGBDconfig.ini).  NOT the reference's enum value: a zeroed config is pyrFirst. */
 } rgbid_align_config;
 
 typedef struct {

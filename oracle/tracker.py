@@ -94,12 +94,12 @@ def relative_constraint(R_last, t_last, cov_last, R_new, t_new, cov_new):
 class OracleTracker:
     def __init__(self, rows, cols, intr, levels=3, iterations=(10, 5, 3), kind="cpu", motion_model=True,
                  visratio_odo=0.9, visratio_integr=0.7, delta_t=0.03333, mestimator=orc.STUDENT,
-                 sigma_estimator=orc.SIGMA_PDF, nsamples=10000, factor_depth=1.0):
+                 sigma_estimator=orc.SIGMA_PDF, nsamples=10000, factor_depth=1.0, warp_first=0):
         self.B = backend(kind)
         self.rows, self.cols, self.intr, self.levels = rows, cols, intr, levels
         self.cfg = orc.make_config(rows, cols, levels, orc.MODE_TRACKER, list(iterations), intr["fx"], intr["fy"],
                                    intr["cx"], intr["cy"], mestimator=mestimator, sigma_estimator=sigma_estimator,
-                                   nsamples=nsamples)
+                                   nsamples=nsamples, warp_first=warp_first)
         self.motion_model, self.vo, self.vi = motion_model, visratio_odo, visratio_integr
         self.dt = np.float32(delta_t)
         self.factor_depth = factor_depth

@@ -49,7 +49,7 @@ class AlignConfig(C.Structure):
                 ("iterations", C.c_int * MAX_LEVELS), ("batch", C.c_int), ("mode", C.c_int),
                 ("mestimator", C.c_int), ("weighting", C.c_int), ("sigma_estimator", C.c_int),
                 ("nsamples", C.c_int), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float),
-                ("cy", C.c_float), ("factor_depth", C.c_float), ("with_fusion", C.c_int)]
+                ("cy", C.c_float), ("factor_depth", C.c_float), ("with_fusion", C.c_int), ("warp_first", C.c_int)]
 
 
 class IterTrace(C.Structure):

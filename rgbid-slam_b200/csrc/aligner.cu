@@ -119,6 +119,7 @@ static void record_chain(rgbid_aligner* al, LaunchCtx L, int first, int count, c
   const rgbid_align_config& c = al->cfg;
   const bool tracker = (c.mode == RGBID_MODE_TRACKER);
   const bool estimate_scale = tracker ? (c.sigma_estimator == RGBID_SIGMA_PDF) : true;
+  const bool warp_first = tracker && c.warp_first;  // KeyframeAlign has no such option (src/keyframe_align.cpp:178-350)
   int done = 0;
   for (int level = c.levels - 1; level >= c.finest_level; --level) {
     for (int it = 0; it < c.iterations[level]; ++it) {
@@ -138,6 +139,22 @@ static void record_chain(rgbid_aligner* al, LaunchCtx L, int first, int count, c
       // KeyframeAlign: covariance = inverse of the LAST iteration's A (keyframe_align.cpp:339-350)
       P.compute_cov = (!tracker && done == al->niters) ? 1 : 0;
       GnLevelMaps M = level_maps(al, level, false);
+      if (warp_first && level > 0) {
+        // WARP_ORDER = warpFirst (src/visodo.cpp:1078-1105): every iteration warps the current frame at level 0 with the
+        // current pose and rebuilds the pyramid of the warped maps down to this level; the scale and system kernels
+        // then read those maps pixel for pixel.  At level 0 the two warp orders are the same computation.
+        const int B = c.batch;
+        launch_warp_pair(L, al->maps[MAP_W_CUR][0], al->maps[MAP_I_CUR][0], al->use_tex ? al->d_tex : nullptr,
+                         al->use_tex ? al->d_tex + B : nullptr, al->maps[MAP_W_KF][0], al->d_states,
+                         al->maps[MAP_W_WARP][0], al->maps[MAP_I_WARP][0], first, count);
+        for (int l = 1; l <= level; ++l)
+          launch_pyr_down2(L, sub(al->maps[MAP_I_WARP][l - 1], first), sub(al->maps[MAP_I_WARP][l], first),
+                           sub(al->maps[MAP_W_WARP][l - 1], first), sub(al->maps[MAP_W_WARP][l], first), count);
+        M.Wc = al->maps[MAP_W_WARP][level]; M.Ic = al->maps[MAP_I_WARP][level];
+        M.texW = nullptr; M.texI = nullptr; M.tex_border = 0;
+        P.prewarped = 1;
+      }
+      if (warp_first) P.next_level = -1;  // the level-0 projection is needed whatever level iterates next
       if (estimate_scale) launch_gn_scale(L, M, P, al->d_states, al->d_scales);
       if (!signalled) { cudaEventRecord(after_first_launch, L.stream); signalled = true; }
       launch_gn_build(L, M, P, al->d_states, al->d_scales, al->d_partials, 32, al->d_counters, al->d_trace);
@@ -218,7 +235,7 @@ int rgbid_aligner_create(rgbid_ctx* ctx, const rgbid_align_config* cfg, rgbid_al
     g.pitch = align_up((size_t)g.cols * sizeof(float), 128);
     g.sstride = align_up(g.pitch * g.rows, 512);  // texture base alignment
     rgbid_error_geometry(g.rows, g.cols, al->cfg.nsamples, &g.kept_rows, &g.kept_cols, &g.sample_stride);
-    int nmaps = tracker ? (int)MAP_COUNT : 8;
+    int nmaps = tracker ? (al->cfg.warp_first ? (int)MAP_COUNT : (int)MAP_W_WARP) : 8;
     total += (size_t)nmaps * g.sstride * B;
   }
   size_t raw_depth = align_up((size_t)cfg->rows * cfg->cols * 2, 256), raw_rgb = align_up((size_t)cfg->rows * cfg->cols * 3, 256);
@@ -230,7 +247,7 @@ int rgbid_aligner_create(rgbid_ctx* ctx, const rgbid_align_config* cfg, rgbid_al
   size_t off = 0;
   for (int l = 0; l < cfg->levels; ++l) {
     const LevelGeom& g = al->geom[l];
-    int nmaps = tracker ? (int)MAP_COUNT : 8;
+    int nmaps = tracker ? (al->cfg.warp_first ? (int)MAP_COUNT : (int)MAP_W_WARP) : 8;
     for (int m = 0; m < nmaps; ++m) {
       al->maps[m][l] = make_img((float*)(al->d_arena + off), g.pitch, g.rows, g.cols, g.sstride);
       off += g.sstride * B;

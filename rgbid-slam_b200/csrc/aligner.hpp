@@ -9,6 +9,7 @@ enum MapId {
   MAP_W_KF = 0, MAP_I_KF, MAP_GWX, MAP_GWY, MAP_GIX, MAP_GIY, MAP_W_CUR, MAP_I_CUR,
   MAP_CGWX, MAP_CGWY, MAP_CGIX, MAP_CGIY,  // covariance-only (bilateral-filtered) gradients, tracker mode
   MAP_WF, MAP_IF,                          // bilateral-filtered keyframe pyramid (scratch), tracker mode
+  MAP_W_WARP, MAP_I_WARP,                  // WARP_ORDER = warpFirst: per-iteration pyramid of the warped current frame
   MAP_COUNT
 };
 

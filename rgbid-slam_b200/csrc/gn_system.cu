@@ -331,7 +331,14 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
       gix[0] = __ldg(M.gIx.row(b, y) + x0); giy[0] = __ldg(M.gIy.row(b, y) + x0);
     }
     float w1[VEC], i1[VEC];
-    if (TEX) {
+    if (P.prewarped) {  // uniform
+      // WARP_ORDER = warpFirst above level 0: Wc / Ic hold pyrDown^level(warp_0(current frame)), src/visodo.cpp:1078-1105
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        w1[k] = __ldg(M.Wc.row(b, y) + x0 + k);
+        i1[k] = __ldg(M.Ic.row(b, y) + x0 + k);
+      }
+    } else if (TEX) {
       // all inverse-depth fetches of this thread in flight, then all intensity fetches
       WarpCoord wc[VEC];
       float fetched[VEC];
@@ -364,19 +371,21 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
 // ------------------------------------------------------------------------------------------------------------
 // gn_build_fast_kernel: the shipped configuration (Student-t weights, INDEPENDENT weighting, texture gathers, flat
 // keyframe maps) of gn_build_kernel, rebuilt around the measured limits of the B200 SM (tools/ubench/pipes.cu):
-// FP32 FMA-pipe instructions issue at ~0.9 / clk / SMSP, ALU-pipe instructions (compares, selects, min/max,
-// integer) at half that, so the kernel is bound by instruction issue long before DRAM unless the per-pixel
-// instruction count is cut.  What it does differently from the generic kernel:
-//   * the six keyframe maps arrive through the TMA engine: each warp owns a ring of kFastStages x 6 x 512 B
-//     shared-memory slots, one lane issues 1-D bulk copies (cp.async.bulk, SASS UBLKCP) two chunks ahead and the
-//     warp waits on an mbarrier -- no CTA-wide barrier in the loop, no staging registers, DRAM latency hidden;
+// an FP32 FMA-pipe instruction on three distinct registers issues at ~0.7 / clk / SMSP and the path needs ~140 of them
+// per pixel, so the kernel is bound by the FMA pipe before DRAM (profiles/README.md).  What it does differently from
+// the generic kernel:
+//   * the six keyframe maps arrive through the TMA engine: each warp owns two rings of shared-memory slots (W0:
+//     kStagesW x 512 B, the five other maps: kStagesL x 2560 B), one elected lane issues 1-D bulk copies
+//     (cp.async.bulk, SASS UBLKCP) several chunks ahead and the warp waits on an mbarrier -- no CTA-wide barrier in
+//     the loop, no staging registers, DRAM latency hidden;
+//   * the texture gathers of chunk i + 1 / i + 2 are issued while the constraints of chunk i are accumulated
+//     (software pipeline, unrolled by two so that no register set has to be copied);
 //   * the projection is factored as  K R K^-1 (x, y, 1)^T / w + K t : the pixel-dependent part is computed once and
 //     reused by the second projection of tracker mode (2 FMAs per coordinate instead of 5);
 //   * the inverse-depth texture uses border addressing (0 outside), so "outside the image" falls out of the
-//     reference's own `res > 0` test and only the intensity fetch needs an explicit in-image test, done as two
-//     |fma| < 1 compares; validity is carried by NaN propagation into the weight and ONE compare per constraint;
-//   * the 2 x 27 accumulations are predicated packed FMAs (fma.rn.f32x2, SASS FFMA2): 15 + 3 issue slots per
-//     constraint instead of 27 + 6, free operand swaps / broadcasts.
+//     reference's own `res > 0` test and only the intensity fetch needs an explicit in-image test (four compares on
+//     the ALU pipe); validity is carried by NaN propagation into the weight and ONE compare per constraint;
+//   * the 2 x 27 accumulations are FMAs predicated on that compare (no selects, no sanitising of the rows).
 // Arithmetic differs from the generic kernel only in rounding (same formulas re-associated); the parity tests
 // hold both against the oracle and the reference's own kernels.
 // ------------------------------------------------------------------------------------------------------------
@@ -878,7 +887,8 @@ __global__ void __cluster_dims__(kScaleCluster, 1, 1) __launch_bounds__(kScaleTh
     const int x = s * xs, y = s * ys;
     float w0 = __ldg(M.W0.row(b, y) + x), i0 = __ldg(M.I0.row(b, y) + x);
     float w1, i1;
-    warp_pixel<TEX>(proj, x, y, w0, cur, P.cols, P.rows, geom_is_warped, w1, i1);
+    if (P.prewarped) { w1 = __ldg(M.Wc.row(b, y) + x); i1 = __ldg(M.Ic.row(b, y) + x); }  // uniform; see gn_build_kernel
+    else warp_pixel<TEX>(proj, x, y, w0, cur, P.cols, P.rows, geom_is_warped, w1, i1);
     samp_int[il] = i1 - i0;
     samp_dep[il] = w1 - w0;
   }
@@ -993,7 +1003,7 @@ void launch_gn_build(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P
   // nu = 5 of computeWeight(STUDENT): the same expression), INDEPENDENT weighting.
   static const bool no_fast = [] { const char* e = getenv("RGBID_NO_FAST"); return e && e[0] == '1'; }();
   const size_t flat = (size_t)P.cols * sizeof(float);
-  const bool fast = !no_fast && vec && tex && M.tex_border && P.weighting == RGBID_INDEPENDENT &&
+  const bool fast = !no_fast && !P.prewarped && vec && tex && M.tex_border && P.weighting == RGBID_INDEPENDENT &&
                     (P.student_nu || P.mestimator == RGBID_STUDENT) && M.W0.pitch == flat && M.I0.pitch == flat &&
                     M.gWx.pitch == flat && M.gWy.pitch == flat && M.gIx.pitch == flat && M.gIy.pitch == flat &&
                     (long long)P.rows * P.cols <= 2500000ll && padded(M.W0, P) && padded(M.I0, P) && padded(M.gWx, P) &&

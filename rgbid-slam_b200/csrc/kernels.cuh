@@ -70,6 +70,13 @@ void launch_warp_intensity(const LaunchCtx& L, ImgB src, ImgB prev, ImgB dst, co
 // batched weighted warp (+ optional fused integration): per-stream Proj read from device memory
 void launch_warp_invdepth_weighted(const LaunchCtx& L, ImgB src, ImgB prev, ImgB dst, ImgB weight, const Proj* P_dev,
                                    Proj P_host, int batch, const int* active = nullptr);
+// batched K4 + K5 of tracker mode in one pass (warped inverse depth, then intensity warped with it as geometry), per-
+// stream projection read from the device-resident Gauss-Newton state (states[first + b].proj[0]); texW / texI: one
+// texture object per stream over src_w (point, border) / src_i (linear, clamp), or null for the software sampler
+struct GnState;
+void launch_warp_pair(const LaunchCtx& L, ImgB src_w, ImgB src_i, const cudaTextureObject_t* texW,
+                      const cudaTextureObject_t* texI, ImgB kf_w, const GnState* states, ImgB dst_w, ImgB dst_i,
+                      int first, int batch);
 void launch_integrate(const LaunchCtx& L, ImgB wsrc, ImgB wweight, ImgB dst, ImgB dweight, int batch,
                       const int* active = nullptr);
 // fused K6 + K7: warp current inverse depth into the keyframe and fuse it in the same pass
@@ -153,6 +160,8 @@ struct GnParams {
   int next_level;               // level of the launch that consumes the updated pose (-1: refresh proj[] of all levels)
   int first;                    // first frame pair of this launch (the batch may be launched in groups, see aligner.cu)
   int batch_total;              // pairs of the whole batch (grid sizing); 0: same as batch
+  int prewarped;                // 1: M.Wc / M.Ic already are the current frame warped into the keyframe view at this
+                                //    level (WARP_ORDER = warpFirst, see aligner.cu): read them pixel for pixel
 };
 
 // fused warp + sample + residual -> IRLS sigma / nu (8-CTA cluster per pair)

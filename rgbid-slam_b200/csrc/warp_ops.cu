@@ -54,6 +54,34 @@ __global__ void __launch_bounds__(BX* BY) warp_intensity_kernel(ImgB src, ImgB p
   dst.row(0, y)[x] = out;
 }
 
+// K4 + K5 of the tracker for a batch of streams in one pass, at the maps' own level, with the projection of the
+// device-resident Gauss-Newton state: the per-iteration level-0 warp of WARP_ORDER = warpFirst
+// (src/visodo.cpp:1087-1098).  Writes NaN where the reference's two kernels do.
+template <bool TEX>
+__global__ void __launch_bounds__(BX* BY)
+    warp_pair_kernel(ImgB src_w, ImgB src_i, const cudaTextureObject_t* __restrict__ texW,
+                     const cudaTextureObject_t* __restrict__ texI, ImgB kf_w, const GnState* __restrict__ states,
+                     ImgB dst_w, ImgB dst_i, int first)
+{
+  const int b = blockIdx.z + first;
+  const GnState& st = states[b];
+  if (st.status != RGBID_OK) return;  // uniform over the CTA: lost pairs are skipped by every kernel of the schedule
+  __shared__ Proj s_proj;
+  const int tid = threadIdx.y * BX + threadIdx.x;
+  if (tid < 12) ((float*)&s_proj)[tid] = ((const float*)&st.proj[0])[tid];
+  __syncthreads();
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= dst_w.cols || y >= dst_w.rows) return;
+  CurFrame cur;
+  cur.Wc = src_w.row(b, 0); cur.Ic = src_i.row(b, 0);
+  cur.wpitch = src_w.pitch; cur.ipitch = src_i.pitch;
+  cur.texW = TEX ? texW[b] : 0; cur.texI = TEX ? texI[b] : 0;
+  float w1, i1;
+  warp_pixel<TEX>(s_proj, x, y, kf_w.row(b, y)[x], cur, src_w.cols, src_w.rows, true, w1, i1);
+  dst_w.row(b, y)[x] = w1;
+  dst_i.row(b, y)[x] = i1;
+}
+
 // Shared body of K6 (trafo3DKernelInvDepthWeightedGridStride, warping_registration.cu:549-594):
 // returns the warped inverse depth (NaN if rejected) and, through weight / has_weight, the fusion weight
 // (1 - w2 tz)^4 / v1z^2 when it is positive.
@@ -314,6 +342,18 @@ void launch_warp_invdepth_weighted(const LaunchCtx& L, ImgB src, ImgB prev, ImgB
 {
   warp_invdepth_weighted_kernel<<<grid2d(dst.cols, dst.rows, batch), dim3(BX, BY), 0, L.stream>>>(
       src, prev, dst, weight, P_dev, P_host, active);
+  ++*L.launches;
+}
+
+void launch_warp_pair(const LaunchCtx& L, ImgB src_w, ImgB src_i, const cudaTextureObject_t* texW,
+                      const cudaTextureObject_t* texI, ImgB kf_w, const GnState* states, ImgB dst_w, ImgB dst_i,
+                      int first, int batch)
+{
+  const dim3 grid = grid2d(dst_w.cols, dst_w.rows, batch), block(BX, BY);
+  if (texW != nullptr && texI != nullptr)
+    warp_pair_kernel<true><<<grid, block, 0, L.stream>>>(src_w, src_i, texW, texI, kf_w, states, dst_w, dst_i, first);
+  else
+    warp_pair_kernel<false><<<grid, block, 0, L.stream>>>(src_w, src_i, texW, texI, kf_w, states, dst_w, dst_i, first);
   ++*L.launches;
 }
 

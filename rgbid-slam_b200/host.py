@@ -322,7 +322,7 @@ class Context:
 
 def make_align_config(rows, cols, levels, mode, batch=1, fx=525.0, fy=525.0, cx=319.5, cy=239.5, iterations=None,
                       finest_level=0, mestimator=capi.STUDENT, weighting=capi.INDEPENDENT,
-                      sigma_estimator=capi.SIGMA_PDF, nsamples=None, factor_depth=1.0):
+                      sigma_estimator=capi.SIGMA_PDF, nsamples=None, factor_depth=1.0, warp_first=0):
     cfg = capi.AlignConfig()
     cfg.rows, cfg.cols, cfg.levels, cfg.finest_level = rows, cols, levels, finest_level
     its = iterations if iterations is not None else default_iterations(levels, mode)
@@ -334,6 +334,7 @@ def make_align_config(rows, cols, levels, mode, batch=1, fx=525.0, fy=525.0, cx=
     cfg.fx, cfg.fy, cfg.cx, cfg.cy = fx, fy, cx, cy
     cfg.factor_depth = factor_depth
     cfg.with_fusion = 0
+    cfg.warp_first = int(warp_first)  # tracker: WARP_ORDER = warpFirst (src/visodo.cpp:1078-1105); 0 = pyrFirst
     return cfg
 
 

@@ -54,9 +54,6 @@ class VisodoTracker {
         Nsamples_(Nsamples), trk_(nullptr), lost_(false), global_time_(0)
   {
     if (optim_dim != 6) throw std::invalid_argument("only the 6-DoF optimisation of the reference is implemented");
-    if (warping != device::PYR_FIRST)
-      std::cerr << "VisodoTracker: WARP_ORDER warpFirst is not implemented on this path; using pyrFirst "
-                   "(the shipped configuration, config_data/visodoRGBDconfig.ini:9)" << std::endl;
     if (termination != device::ALL_ITERS)
       std::cerr << "VisodoTracker: CHI_SQUARED early termination is not implemented; using ALL_ITERS (the default)" << std::endl;
     setRGBIntrinsics(device::FOCAL_LENGTH, device::FOCAL_LENGTH, device::CENTER_X, device::CENTER_Y);
@@ -247,6 +244,7 @@ class VisodoTracker {
     c.align.nsamples = Nsamples_;
     c.align.fx = fx_; c.align.fy = fy_; c.align.cx = cx_; c.align.cy = cy_;
     c.align.factor_depth = factor_depth_;
+    c.align.warp_first = (warping_ == device::WARP_FIRST) ? 1 : 0;  // src/visodo.cpp:1078
     c.motion_model = motion_model_;
     c.visratio_odo = visibility_ratio_odo_threshold_; c.visratio_integr = visibility_ratio_integr_threshold_;
     c.max_odo_kf_count = max_odoKF_count_; c.max_integr_kf_count = max_integrKF_count_;
