@@ -128,9 +128,10 @@ int main(int argc, char** argv)
       std::cout << "Can't read the first frame of " << eval_folder << std::endl;
       return 1;
     }
-    // the reference's tracker defaults (tools/RGBID_SLAMapp.cpp:82-96) at the size of the sequence
+    // the reference's tracker defaults (`new VisodoTracker`, tools/RGBID_SLAMapp.cpp:82, include/visodo.h:54-70) at the
+    // size of the sequence; note WARP_ORDER: the code default is warpFirst, config_data/visodoRGBDconfig.ini says pyrFirst
     VisodoTracker visodo(6, device::STUDENT, device::CONSTANT_VELOCITY, device::SIGMA_PDF, device::INDEPENDENT,
-                         device::PYR_FIRST, device::DEFAULT_ODO_KF_COUNT, 0, device::ALL_ITERS, device::DEFAULT_VISRATIO_ODO,
+                         device::DEFAULT_WARPING, device::DEFAULT_ODO_KF_COUNT, 0, device::ALL_ITERS, device::DEFAULT_VISRATIO_ODO,
                          device::NO_FILTERS, device::DEFAULT_VISRATIO_INTEGR, device::DEFAULT_INTEGR_KF_COUNT, 10000,
                          rows, cols);
     visodo.setRGBIntrinsics(525.f, 525.f, 319.5f, 239.5f);  // Evaluation::fx .. cy, tools/evaluation.cpp:61-64

@@ -40,7 +40,7 @@ class VisodoTracker {
 
   VisodoTracker(int optim_dim = 6, int Mestimator = device::DEFAULT_MESTIMATOR,
                 int motion_model = device::DEFAULT_MOTION_MODEL, int sigma_estimator = device::SIGMA_PDF,
-                int weighting = device::DEFAULT_WEIGHTING, int warping = device::PYR_FIRST,
+                int weighting = device::DEFAULT_WEIGHTING, int warping = device::WARP_FIRST,  // include/visodo.h:59
                 int max_odoKF_count = device::DEFAULT_ODO_KF_COUNT, int finest_level = 0,
                 int termination = device::DEFAULT_TERMINATION, float visratio_odo = device::DEFAULT_VISRATIO_ODO,
                 int image_filtering = device::DEFAULT_IMAGE_FILTERING, float visratio_integr = device::DEFAULT_VISRATIO_INTEGR,
