@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--cols", type=int, default=640)
     ap.add_argument("--levels", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--warp-order", default="pyrFirst", choices=["pyrFirst", "warpFirst"],
+                    help="WARP_ORDER of the tracker; the headline metric is quoted on the reference's shipped pyrFirst")
     ap.add_argument("--ref-streams", type=int, default=2, help="streams per step for --impl reference")
     return ap.parse_args()
 
@@ -143,7 +145,8 @@ def run_b200(args, world, rank, local):
     depth, rgb, intr = make_frames(args, stream_ids, n_frames, device)
     ctx = host.Context(local)
     its = host.default_iterations(args.levels, capi.MODE_TRACKER)
-    acfg = host.make_align_config(args.rows, args.cols, args.levels, capi.MODE_TRACKER, batch=S, iterations=its, **intr)
+    acfg = host.make_align_config(args.rows, args.cols, args.levels, capi.MODE_TRACKER, batch=S, iterations=its,
+                                  warp_first=int(args.warp_order == "warpFirst"), **intr)
     trk = host.Tracker(ctx, host.make_tracker_config(acfg))
 
     gather = None
@@ -242,7 +245,7 @@ def run_b200(args, world, rank, local):
             "config": {"workload": "tum_synth_640x480_4lvl_tracker" if (args.rows, args.cols, args.levels) == (480, 640, 4)
                        else "tum_synth_%dx%d_%dlvl_tracker" % (args.cols, args.rows, args.levels),
                        "streams_per_gpu": S, "frames_per_step": S * world, "iterations": its,
-                       "sigma_estimator": "sigmaML", "m_estimator": "Student", "warp_order": "pyrFirst",
+                       "sigma_estimator": "sigmaML", "m_estimator": "Student", "warp_order": args.warp_order,
                        "l2_policy": "inputs larger than L2: %.0f MB of pyramids touched per step, new frames every step"
                                     % (S * 39.0)},
             "clocks": clocks,
