@@ -19,6 +19,9 @@
  *
  * Images are dense row-major float32 [rows][cols]; NaN marks an invalid pixel.
  */
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include "oracle.h"
 
 #include <math.h>
@@ -38,6 +41,25 @@
 static int g_tex_frac_mode = ORC_TEX_FRAC_ROUND;
 
 void orc_set_tex_frac_mode(int mode) { g_tex_frac_mode = mode; }
+
+/* Thread count of the row-parallel loops (bench.py reports the baseline on all host cores and on one) */
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
+int orc_max_threads(void)
+{
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
 
 static inline float qnan(void) { return nanf(""); }
 static inline int imin(int a, int b) { return a < b ? a : b; }

@@ -124,6 +124,9 @@ void orc_projective_inverse_pose(const double* R, const double* t, float fx, flo
                                  float cy, float* Rp, float* tp);
 int orc_gn_update(const double* A36, const double* b6, double* R, double* t, double* x_out);
 
+void orc_set_num_threads(int n); /* OpenMP threads of the row-parallel loops (no-op without OpenMP) */
+int orc_max_threads(void);
+
 int orc_align(const orc_align_config* C, const orc_pyramids* P, double* R, double* t, double* cov36,
               orc_iter_trace* trace, int trace_cap, int* n_trace, orc_frame_stats* stats);
 
