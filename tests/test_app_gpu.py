@@ -52,7 +52,8 @@ def test_app_on_tum_sequence(built, tmp_path):
         assert np.linalg.norm(t - o["t"]) < 1e-4 and rot_angle(quat_to_R(q), o["R"]) < 1e-4
 
     # default log name: "<dataset>_poses.txt" in the working directory (tools/RGBID_SLAMapp.cpp:414-428)
-    r = subprocess.run([APP, "-eval", folder + "/", "-match_file", "matches.txt", "-calib", str(calib), "-n", "2"],
+    r = subprocess.run([APP, "-eval", folder + "/", "-match_file", "matches.txt", "-calib", str(calib), "-config", str(config),
+                        "-n", "2"],
                        capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
     assert r.returncode == 0, r.stdout + r.stderr
     assert os.path.exists(tmp_path / "rgbd_dataset_synth_poses.txt")
@@ -76,15 +77,21 @@ def test_app_with_custom_calibration_file(built, tmp_path):
         "[STEREO_DEPTH2RGB]\ndRc=\n0.9999    0.0143    0.0060\n-0.0143    0.9999   -0.0018\n-0.0060    0.0017    1.0000\n"
         "t_dc=0.0263595 -0.0000973  0.0002853\n"
         % (i["fx"], i["fy"], i["cx"], i["cy"], i["fx"] * 1.06, i["fy"] * 1.06, i["cx"] + 1.4, i["cy"] + 1.2))
+    # the [VISODO] section of the reference's shipped config_data/visodoRGBDconfig.ini (without -config the tracker runs
+    # with the code default WARP_ORDER = warpFirst, like the reference's app)
+    config = tmp_path / "visodo.ini"
+    config.write_text("[VISODO]\nM_ESTIMATOR = Student\nSIGMA_ESTIMATOR = sigmaML\nWARP_ORDER = pyrFirst\nIMAGE_FILTERING = none\n")
     log = tmp_path / "poses.txt"
-    r = subprocess.run([APP, "-eval", folder + "/", "-match_file", "matches.txt", "-calib", str(calib), "-o", str(log)],
+    r = subprocess.run([APP, "-eval", folder + "/", "-match_file", "matches.txt", "-calib", str(calib), "-config", str(config),
+                        "-o", str(log)],
                        capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
     assert r.returncode == 0, r.stdout + r.stderr
     assert "frames %d" % n in r.stdout and "lost 0" in r.stdout
     plain = tmp_path / "plain.ini"
     plain.write_text("[CALIBRATION]\nfx=%r\nfy=%r\ncx=%r\ncy=%r\n" % (i["fx"], i["fy"], i["cx"], i["cy"]))
     log2 = tmp_path / "poses_plain.txt"
-    r2 = subprocess.run([APP, "-eval", folder + "/", "-match_file", "matches.txt", "-calib", str(plain), "-o", str(log2)],
+    r2 = subprocess.run([APP, "-eval", folder + "/", "-match_file", "matches.txt", "-calib", str(plain), "-config", str(config),
+                         "-o", str(log2)],
                         capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
     assert r2.returncode == 0
     a = np.array([[float(v) for v in ln.split()] for ln in log.read_text().splitlines()])
