@@ -34,6 +34,49 @@ def test_library_exports_every_declared_symbol(built):
     assert b"argument" in lib.rgbid_status_string(-2)
 
 
+def _c_layout(header, include_dir, pairs, tmp_path):
+    """sizeof / offsetof of every mirrored struct as the C compiler sees them."""
+    import subprocess
+    src = ["#include <stdio.h>", "#include <stddef.h>", '#include "%s"' % header, "int main(void) {"]
+    for cname, cls in pairs:
+        src.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for f in cls._fields_:
+            src.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, f[0], cname, f[0]))
+    src.append("return 0; }")
+    c, exe = tmp_path / "layout.c", tmp_path / "layout"
+    c.write_text("\n".join(src))
+    r = subprocess.run(["gcc", "-I", include_dir, str(c), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr  # a field named in the ctypes mirror does not exist in the header
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    return {k: int(v) for k, v in (ln.split() for ln in out.splitlines())}
+
+
+def _check_layout(got, pairs):
+    for cname, cls in pairs:
+        assert got[cname] == C.sizeof(cls), (cname, got[cname], C.sizeof(cls))
+        for f in cls._fields_:
+            assert got["%s.%s" % (cname, f[0])] == getattr(cls, f[0]).offset, (cname, f[0])
+
+
+def test_ctypes_mirrors_have_the_layout_of_the_header(tmp_path):
+    """include/rgbid_b200.h is plain C: every struct of the boundary, field by field, against rgbid-slam_b200/capi.py."""
+    from rgbid_slam_b200 import capi
+    pairs = [("rgbid_system_params", capi.SystemParams), ("rgbid_intr", capi.Intr), ("rgbid_depth_dist", capi.DepthDist),
+             ("rgbid_custom_calibration", capi.CustomCalibration), ("rgbid_align_config", capi.AlignConfig),
+             ("rgbid_iter_trace", capi.IterTrace), ("rgbid_tracker_config", capi.TrackerConfig),
+             ("rgbid_frame_result", capi.FrameResult), ("rgbid_keyframe_handoff", capi.KeyframeHandoff)]
+    _check_layout(_c_layout("rgbid_b200.h", os.path.join(ROOT, "include"), pairs, tmp_path), pairs)
+    # a zeroed configuration is the reference's shipped one (pyrFirst), not enum value 0 of the reference (WARP_FIRST)
+    assert capi.AlignConfig().warp_first == 0
+
+
+def test_oracle_ctypes_mirrors_have_the_layout_of_its_header(tmp_path):
+    import oracle as orc
+    pairs = [("orc_system_params", orc.SystemParams), ("orc_align_config", orc.AlignConfig), ("orc_pyramids", orc.Pyramids),
+             ("orc_iter_trace", orc.IterTrace), ("orc_frame_stats", orc.FrameStats)]
+    _check_layout(_c_layout("oracle.h", os.path.join(ROOT, "oracle"), pairs, tmp_path), pairs)
+
+
 def test_every_entry_point_cites_the_reference():
     src = open(os.path.join(ROOT, "include", "rgbid_b200.h")).read()
     assert src.count("src/internal.h:") >= 20 and "src/visodo.cpp:" in src and "src/keyframe_align.cpp:" in src
