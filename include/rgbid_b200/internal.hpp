@@ -12,6 +12,7 @@
 //    launch with context-owned scratch).
 #pragma once
 #include <cuda_runtime.h>
+#include <cstring>
 #include <iostream>
 #include <stdexcept>
 #include <string>
@@ -252,6 +253,42 @@ inline void initialiseWeightKeyframe(const DepthMapf& src_depth, DeviceArray2D<f
   dst_weight.create(src_depth.rows(), src_depth.cols());
   check(rgbid_fill_image(t.tc.ctx, dst_weight.ptr(), dst_weight.step(), dst_weight.rows(), dst_weight.cols(), 1.f),
         "initialiseWeightKeyframe");
+  t.done();
+}
+
+/** showGPUMemoryUsage (src/internal.h:181, src/cuda/misc.cu:526-540): one diagnostic line on stdout */
+inline void showGPUMemoryUsage()
+{
+  size_t free_bytes = 0, total_bytes = 0;
+  cudaError_t e = cudaMemGetInfo(&free_bytes, &total_bytes);
+  if (e != cudaSuccess) throw std::runtime_error(std::string("showGPUMemoryUsage: ") + cudaGetErrorString(e));
+  const double mb = 1024.0 * 1024.0;
+  std::cout << "GPU memory usage: used =  " << (double)(total_bytes - free_bytes) / mb << " MB, free = "
+            << (double)free_bytes / mb << " MB, total = " << (double)total_bytes / mb << std::endl;
+}
+
+/** initialiseDeviceMemory2D<T> (src/internal.h:273-274, src/cuda/misc.cu:327-341, 491-512: instantiated for
+ *  unsigned char, unsigned int, char, int and float; the live call clears the overlap mask, src/visodo.cpp:2027).
+ *  A constant fill needs no kernel of its own: bytes go through cudaMemset2DAsync, 32-bit values through the float
+ *  fill with the value's bit pattern. */
+template <typename T>
+inline void initialiseDeviceMemory2D(DeviceArray2D<T>& src, T val, int numSMs = -1)
+{
+  (void)numSMs;
+  static_assert(sizeof(T) == 1 || sizeof(T) == 4, "initialiseDeviceMemory2D: the reference instantiates 8- and 32-bit types");
+  CallTimer t;
+  if (sizeof(T) == 1) {
+    unsigned char byte;
+    std::memcpy(&byte, &val, 1);
+    cudaError_t e = cudaMemset2DAsync(src.ptr(), src.step(), byte, (size_t)src.cols(), (size_t)src.rows(),
+                                      (cudaStream_t)rgbid_ctx_stream(t.tc.ctx));
+    if (e != cudaSuccess) throw std::runtime_error(std::string("initialiseDeviceMemory2D: ") + cudaGetErrorString(e));
+  } else {
+    float bits;
+    std::memcpy(&bits, &val, 4);
+    check(rgbid_fill_image(t.tc.ctx, reinterpret_cast<float*>(src.ptr()), src.step(), src.rows(), src.cols(), bits),
+          "initialiseDeviceMemory2D");
+  }
   t.done();
 }
 
