@@ -8,11 +8,14 @@
 // Eigen is not available in this image, so poses are returned as plain row-major structs (Affine3) instead of
 // Eigen::Affine3f / Affine3d; everything else keeps the reference's names.  Header-only.
 #pragma once
+#include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <mutex>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -165,6 +168,8 @@ class VisodoTracker {
   bool trackNewFrame()
   {
     ensure_created();
+    const auto t_begin = std::chrono::steady_clock::now();
+    computeInterframeTime();
     rgbid_frame_result r;
     int rc = rgbid_tracker_track_device(trk_, depth_.ptr(), depth_.step(), 0, (const uint8_t*)rgb24_.ptr(), rgb24_.step(), 0, &r);
     if (rc != RGBID_OK) throw std::runtime_error(std::string("rgbid_tracker_track: ") + rgbid_status_string(rc));
@@ -177,7 +182,11 @@ class VisodoTracker {
     std::memcpy(p.R, r.R, sizeof(p.R));
     std::memcpy(p.t, r.t, sizeof(p.t));
     poses_.push_back(p);
-    vis_odo_times_.push_back(0.f);
+    setSharedCameraPose(p);
+    // wall time of the frame in milliseconds (pcl::ScopeTime t1 of the reference, src/visodo.cpp:2231; 0 for frame 0, :542)
+    const float ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    vis_odo_times_.push_back(global_time_ == 0 ? 0.f : ms);
+    kf_time_accum_ += 1e-3f * ms;
     const bool first = (global_time_ == 0);
     ++global_time_;
     return !first && !lost_;
@@ -191,6 +200,40 @@ class VisodoTracker {
     return poses_[time];
   }
 
+  /** Milliseconds spent on frame `time` (-1: latest), src/visodo.cpp:1853-1860 */
+  float getVisOdoTime(int time = -1) const
+  {
+    if (vis_odo_times_.empty()) return 0.f;
+    if (time > (int)vis_odo_times_.size() || time < 0) time = (int)vis_odo_times_.size() - 1;
+    return vis_odo_times_[time];
+  }
+
+  /** RGB time stamp of frame `time` relative to the first one (0 unless compute_deltat_flag_), src/visodo.cpp:1863-1870 */
+  int64_t getTimestamp(int time = -1) const
+  {
+    if (timestamps_.empty()) return 0;
+    if (time > (int)timestamps_.size() || time < 0) time = (int)timestamps_.size() - 1;
+    return timestamps_[time];
+  }
+
+  /** Latest pose for a consumer thread (the reference's visualisation), src/visodo.cpp:505-512, 1873-1880 */
+  void setSharedCameraPose(const Affine3& pose)
+  {
+    std::lock_guard<std::mutex> lock(mutex_shared_camera_pose_);
+    shared_camera_pose_ = pose;
+    camera_pose_has_changed_ = true;
+  }
+  Affine3 getSharedCameraPose()
+  {
+    std::lock_guard<std::mutex> lock(mutex_shared_camera_pose_);
+    camera_pose_has_changed_ = false;
+    return shared_camera_pose_;
+  }
+  bool camera_pose_has_changed_ = false;
+
+  /** Tracking milliseconds accumulated between consecutive integration keyframes (src/visodo.cpp:1656) */
+  std::vector<float> kf_times_;
+
   const rgbid_frame_result& lastResult() const { return last_; }
 
   /** What the reference pushes to keyframe_manager_ptr_ (buffer_keyframes_, constraints_): every outgoing integration
@@ -202,6 +245,10 @@ class VisodoTracker {
   void reset()
   {
     poses_.clear();
+    vis_odo_times_.clear();
+    timestamps_.clear();
+    kf_times_.clear();
+    kf_time_accum_ = 0.f;
     global_time_ = 0;
     lost_ = false;
     if (trk_) rgbid_tracker_reset(trk_);
@@ -215,6 +262,16 @@ class VisodoTracker {
   int visodo_iterations_[RGBID_MAX_LEVELS];
 
  private:
+  /** computeInterframeTime, src/visodo.cpp:1929-1964: records the zeroed RGB time stamp of the frame.  The interval
+      itself stays the evaluation-mode constant (1 / 30 s) that the tracker was created with: compute_deltat_flag_ is
+      only set by the live-camera grabber (tools/RGBID_SLAMapp.cpp), which is out of scope. */
+  void computeInterframeTime()
+  {
+    if (!compute_deltat_flag_) { timestamp_rgb_curr_ = 0; timestamp_depth_curr_ = 0; return; }
+    if (global_time_ == 0) timestamp_ini_ = std::min(timestamp_rgb_curr_, timestamp_depth_curr_);
+    timestamps_.push_back((int64_t)(timestamp_rgb_curr_ - timestamp_ini_));
+  }
+
   void apply_custom_calibration()
   {
     int rc = rgbid_tracker_set_custom_calibration(trk_, custom_registration_ ? &custom_ : nullptr);
@@ -224,6 +281,8 @@ class VisodoTracker {
   static void keyframe_sink(void* user, const rgbid_keyframe_handoff* k)
   {
     VisodoTracker* self = (VisodoTracker*)user;
+    self->kf_times_.push_back(1000.f * self->kf_time_accum_);  // src/visodo.cpp:1656
+    self->kf_time_accum_ = 0.f;
     self->keyframe_buffers_.buffer_keyframes_.push_back(KeyframePtr(new Keyframe(*k)));
     self->keyframe_buffers_.constraints_.push_back(PoseConstraint(k->kf_index, k->frame_index, PoseConstraint::SEQ_KF, k->rel_R,
                                                                   k->rel_t, 1.f, k->rel_cov));
@@ -279,6 +338,10 @@ class VisodoTracker {
   rgbid_frame_result last_;
   std::vector<Affine3> poses_;
   std::vector<float> vis_odo_times_;
+  std::vector<int64_t> timestamps_;
+  float kf_time_accum_ = 0.f;
+  std::mutex mutex_shared_camera_pose_;
+  Affine3 shared_camera_pose_;
 };
 
 /** The three fields of the reference's Keyframe that KeyframeAlign reads (src/keyframe_align.cpp:119-129):
