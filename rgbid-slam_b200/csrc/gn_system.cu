@@ -396,6 +396,9 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
 #ifndef RGBID_ACC2
 #define RGBID_ACC2 0
 #endif
+#ifndef RGBID_SCALE_MLP
+#define RGBID_SCALE_MLP 0  // gn_scale_kernel: stage-wise sampling with explicit memory-level parallelism (see there)
+#endif
 constexpr int kChunkPx = 128;                   // one warp-chunk: 4 pixels per lane
 constexpr int kChunkBytes = kChunkPx * 4;       // per map
 // Two rings per warp: the keyframe inverse depth is needed by three pipeline stages (gather, second projection,
@@ -881,6 +884,46 @@ __global__ void __cluster_dims__(kScaleCluster, 1, 1) __launch_bounds__(kScaleTh
   cur.wpitch = M.Wc.pitch; cur.ipitch = M.Ic.pitch;
   cur.texW = TEX ? M.texW[b] : 0; cur.texI = TEX ? M.texI[b] : 0;
   const int s = P.sample_stride;
+#if RGBID_SCALE_MLP
+  // Prepared experiment (off by default, not measured yet): the loop below runs a thread's ~5 samples one after the
+  // other, each a chain of a global load and two dependent texture fetches (SASS: no unrolling, ~2 000 clk per
+  // sample).  Here the same samples are taken stage by stage -- all loads, all inverse-depth fetches, all intensity
+  // fetches -- with the stage functions of the generic system kernel (same expressions as warp_pixel).
+  if (TEX && !P.prewarped) {
+    constexpr int U = 5;
+    for (int base = threadIdx.x; base < n_local; base += U * kScaleThreads) {
+      float w0[U], i0[U], w1[U], fetched[U];
+      int px[U], py[U];
+      WarpCoord wc[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int il = base + k * kScaleThreads;
+        const int i = begin + min(il, n_local - 1);
+        const int ys = i / P.kept_cols, xs = i - ys * P.kept_cols;
+        px[k] = s * xs; py[k] = s * ys;
+        w0[k] = __ldg(M.W0.row(b, py[k]) + px[k]);
+        i0[k] = __ldg(M.I0.row(b, py[k]) + px[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) wc[k] = warp_stage1(proj, px[k], py[k], w0[k], P.cols, P.rows);
+#pragma unroll
+      for (int k = 0; k < U; ++k) fetched[k] = tex2D<float>(cur.texW, wc[k].xt, wc[k].yt);
+#pragma unroll
+      for (int k = 0; k < U; ++k)
+        w1[k] = warp_stage2(proj, px[k], py[k], w0[k], fetched[k], wc[k], P.cols, P.rows, geom_is_warped);
+#pragma unroll
+      for (int k = 0; k < U; ++k) fetched[k] = tex2D<float>(cur.texI, wc[k].xt, wc[k].yt);
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int il = base + k * kScaleThreads;
+        if (il < n_local) {
+          samp_int[il] = warp_stage3(fetched[k], wc[k]) - i0[k];
+          samp_dep[il] = w1[k] - w0[k];
+        }
+      }
+    }
+  } else
+#endif
   for (int il = threadIdx.x; il < n_local; il += kScaleThreads) {
     const int i = begin + il;
     const int ys = i / P.kept_cols, xs = i - ys * P.kept_cols;
