@@ -10,9 +10,13 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+# RGBID_BUILD_TAG=<tag> (with RGBID_EXTRA_NVCC_FLAGS) builds a kernel variant next to the product library:
+# build_<tag>/ and lib/librgbid_b200_<tag>.so, loaded with RGBID_LIB=<that path> (capi.py).  Variants are built here
+# and travel to the GPU box, so that no GPU time is spent compiling.
+_TAG = os.environ.get("RGBID_BUILD_TAG", "")
 LIBDIR = os.path.join(HERE, "lib")
-OBJDIR = os.path.join(HERE, "build")
-LIB = os.path.join(LIBDIR, "librgbid_b200.so")
+OBJDIR = os.path.join(HERE, "build" + ("_" + _TAG if _TAG else ""))
+LIB = os.path.join(LIBDIR, "librgbid_b200%s.so" % ("_" + _TAG if _TAG else ""))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 SOURCES = ["image_ops.cu", "warp_ops.cu", "calib_ops.cu", "scale_est.cu", "gn_system.cu", "api.cu", "aligner.cu", "tracker.cu"]

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "librgbid_b200.so")
+# RGBID_LIB selects another build of the same library (a kernel variant built with RGBID_BUILD_TAG, see build.py)
+LIB_PATH = os.environ.get("RGBID_LIB") or os.path.join(_HERE, "lib", "librgbid_b200.so")
 
 MAX_LEVELS = 8
 OK, ERR_NAN, ERR_ARG, ERR_NOMEM, ERR_STATE, ERR_TIMEOUT = 0, -1, -2, -3, -4, -5
