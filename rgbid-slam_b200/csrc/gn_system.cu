@@ -17,6 +17,9 @@
 //
 // Algorithmic HBM bytes: 32 B per keyframe pixel per iteration (6 keyframe maps + 2 current-frame maps,
 // fp32); this kernel is bandwidth bound (about 5 flop/B), tensor cores do not apply.
+#if defined(RGBID_TAIL_PROBE) && RGBID_TAIL_PROBE
+#include <cstdio>  // diagnostic build only
+#endif
 #include <cstdlib>
 #include "scale_core.cuh"
 #include "bulk_copy.cuh"
@@ -396,6 +399,9 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
 #ifndef RGBID_ACC2
 #define RGBID_ACC2 0
 #endif
+#ifndef RGBID_TAIL_PROBE
+#define RGBID_TAIL_PROBE 0  // gn_build_fast_kernel: clock64 break-down of the last CTA (diagnostic build only)
+#endif
 #ifndef RGBID_SCALE_MLP
 #define RGBID_SCALE_MLP 0  // gn_scale_kernel: stage-wise sampling with explicit memory-level parallelism (see there)
 #endif
@@ -482,6 +488,9 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
   const int b = blockIdx.y + P.first;
   GnState& st = states[b];
   if (st.status != RGBID_OK) return;  // lost pairs are skipped consistently by every CTA
+#if RGBID_TAIL_PROBE
+  const long long probe_t0 = clock64();
+#endif
   const int tid = threadIdx.x, lane = tid & 31;
   const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: bulk-copy operands stay in uniform registers
   if (tid < 12) ((float*)&sh.proj)[tid] = ((const float*)&st.proj[P.level])[tid];
@@ -808,10 +817,27 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
 #endif
   if (CHI) { acc[27] = chi[0]; acc[28] = chi[1]; acc[29] = chi[2]; acc[30] = chi[3]; }
 
+#if RGBID_TAIL_PROBE
+  // -DRGBID_TAIL_PROBE=1 (diagnostic build): clocks of the last CTA of pair 0 -- pixel loop,
+  // CTA reduction + election + fixed-order final sum, serial tail (6x6 solve, pose update, projection refresh, trace)
+  const long long probe_t1 = clock64();
+  if (!reduce_and_elect<NACC>(sh, acc, partials + (size_t)b * gridDim.x * partial_stride, partial_stride,
+                              &counters[b], gridDim.x, blockIdx.x))
+    return;
+  const long long probe_t2 = clock64();
+  if (threadIdx.x == 0) {
+    gn_tail(st, sh.total, P, sc, trace, b, CHI);
+    const long long probe_t3 = clock64();
+    if (b == 0)
+      printf("tail probe level %d iter %d cta %d | loop %lld reduce+elect %lld tail %lld\n", P.level, P.iter_index,
+             (int)blockIdx.x, probe_t1 - probe_t0, probe_t2 - probe_t1, probe_t3 - probe_t2);
+  }
+#else
   if (!reduce_and_elect<NACC>(sh, acc, partials + (size_t)b * gridDim.x * partial_stride, partial_stride,
                               &counters[b], gridDim.x, blockIdx.x))
     return;
   if (threadIdx.x == 0) gn_tail(st, sh.total, P, sc, trace, b, CHI);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------------
