@@ -1,5 +1,11 @@
-"""Prints the per-segment clock counts of gn_scale_kernel's rounds.  Needs a library built with
-RGBID_EXTRA_NVCC_FLAGS=-DRGBID_SCALE_PROBE=1 (the kernel then prints from CTA 0 / 131); one alignment of 32 streams."""
+"""Workload for the clock64 probes (diagnostic builds, never bench values): one alignment of 32 streams, un-graphed.
+
+  RGBID_BUILD_TAG=probe RGBID_EXTRA_NVCC_FLAGS="-DRGBID_SCALE_PROBE=1 -DRGBID_TAIL_PROBE=1" python rgbid-slam_b200/build.py
+  gpurun -- 'RGBID_LIB=$PWD/rgbid-slam_b200/lib/librgbid_b200_probe.so python tools/scale_round_probe.py'
+
+RGBID_SCALE_PROBE: gn_scale_kernel prints the per-segment clock counts of its rounds from CTA 0 / 131
+(profiles/r01m_scale_round_probe.txt); RGBID_TAIL_PROBE: gn_build_fast_kernel prints pixel loop / reduction / serial tail
+of the last CTA of stream 0."""
 import os
 import sys
 
