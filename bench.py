@@ -262,7 +262,7 @@ def run_b200(args, world, rank, local):
                          "note": "FP32-FMA-pipe bound (about 141 FMA-pipe instructions per pixel, 9 flop/B): see profiles/README.md"},
             "lost_streams": lost,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only: the scaling runs time the GPUs, not the host
             out["cpu_baseline"] = cpu_baseline(args, depth[:, 0].cpu(), rgb[:, 0].cpu(), intr, its)
     trk.close()
     ctx.close()
