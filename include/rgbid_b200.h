@@ -203,7 +203,20 @@ typedef struct {
   int warp_first;   /* tracker: 1 = WARP_ORDER warpFirst (src/visodo.cpp:1078-1105: above level 0 every iteration warps
                      * at level 0 and rebuilds the pyramid of the warped maps), 0 = pyrFirst (the shipped
                      * config_data/visodoRGBDconfig.ini).  NOT the reference's enum value: a zeroed config is pyrFirst. */
+  int termination;  /* RGBID_TERM_*: how a pyramid level ends before its iterations[] budget is spent (0: never) */
+  float conv_eps;   /* RGBID_TERM_CONVERGENCE: a level ends after the update whose |x| (6-vector, m and rad) < conv_eps */
 } rgbid_align_config;
+
+/* TERMINATION_CRITERIA of the tracker (src/internal.h:112; a zeroed config is ALL_ITERS, the shipped default).
+ * CHI_SQUARED restates src/visodo.cpp:1134-1164: from the second iteration of a level on, the robust chi^2 of ALL
+ * level-0 residuals at the current pose (computeErrorGridStride + computeChiSquare with the reference scales 5 /
+ * 0.0025) gives RMSE = sqrt(chi2) / sqrt(Ndof); if it grew since the previous iteration the last increment is undone
+ * and the level ends.  The reference evaluates the test on the level-0 WARPED maps, which pyrFirst only refreshes while
+ * level 0 iterates (above it the maps are stale, the RMSE repeats and the test never fires), so here the test runs at
+ * level 0 under pyrFirst and at every level under warpFirst.
+ * CONVERGENCE is not in the reference: BASELINE config 2's "full GN convergence" schedule (iterate a level until
+ * |x| < conv_eps or iterations[level] is reached). */
+enum { RGBID_TERM_ALL_ITERS = 0, RGBID_TERM_CHI_SQUARED = 1, RGBID_TERM_CONVERGENCE = 2 };
 
 typedef struct {
   int level, iter;
@@ -218,6 +231,9 @@ int rgbid_aligner_create(rgbid_ctx* ctx, const rgbid_align_config* cfg, rgbid_al
 int rgbid_aligner_destroy(rgbid_aligner* al);
 /* Total Gauss-Newton iterations per pair (sum of cfg.iterations over the active levels). */
 int rgbid_aligner_num_iterations(const rgbid_aligner* al);
+/* After rgbid_aligner_fetch / _run: iterations actually executed per pair and level, out[batch][RGBID_MAX_LEVELS]
+ * (equal to cfg.iterations unless cfg.termination ended a level early). */
+int rgbid_aligner_iterations_done(const rgbid_aligner* al, int* out);
 
 /* Load level-0 float maps (inverse depth, intensity) of the keyframe ("ini") of pair `index` and build
  * its pyramid, Sobel gradients and -- in tracker mode -- the bilateral-filtered covariance-only
@@ -283,11 +299,15 @@ typedef struct {
   float chi_square, chi_test, ndof;
   int status;                 /* RGBID_OK or RGBID_ERR_NAN (lost) */
   int new_odo_keyframe, new_integr_keyframe;
-  int frame_index;
+  int frame_index;            /* per stream: the reference's global_time_ when the frame was tracked */
   /* sequential odometry constraint (frame_index - 1 -> frame_index) the reference pushes to the keyframe manager as
    * PoseConstraint::SEQ_ODO (src/visodo.cpp:2126-2156): relative transform and its propagated 6x6 covariance; the
    * dummy constraint (identity, 100 I) when tracking was lost (:2068-2071) */
   double seq_R[9], seq_t[3], seq_cov[36];
+  /* 1: the alignment failed while the stream was already lost (src/visodo.cpp:2099-2116): both keyframes were re-saved
+   * from this frame and nothing else happened -- no constraint, no keyframe hand-off, frame_index (the reference's
+   * global_time_) does not advance.  The caller must not push the dummy constraint for such a frame. */
+  int lost_again;
 } rgbid_frame_result;
 
 /* ---- custom-calibration ingest and colour fusion / previews (f4) ------------------------------------

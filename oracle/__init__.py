@@ -38,7 +38,8 @@ class AlignConfig(C.Structure):
     _fields_ = [("rows", C.c_int), ("cols", C.c_int), ("levels", C.c_int), ("finest_level", C.c_int),
                 ("iterations", C.c_int * MAX_LEVELS), ("mode", C.c_int), ("mestimator", C.c_int),
                 ("weighting", C.c_int), ("sigma_estimator", C.c_int), ("nsamples", C.c_int),
-                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("warp_first", C.c_int)]
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("warp_first", C.c_int),
+                ("termination", C.c_int), ("conv_eps", C.c_float)]
 
 
 class Pyramids(C.Structure):
@@ -332,7 +333,8 @@ def prepare_current(W, I, levels):
 
 
 def make_config(rows, cols, levels, mode, iterations, fx, fy, cx, cy, finest_level=0, mestimator=STUDENT,
-                weighting=INDEPENDENT, sigma_estimator=SIGMA_PDF, nsamples=None, warp_first=0):
+                weighting=INDEPENDENT, sigma_estimator=SIGMA_PDF, nsamples=None, warp_first=0,
+                termination=0, conv_eps=0.0):
     c = AlignConfig()
     c.rows, c.cols, c.levels, c.finest_level = rows, cols, levels, finest_level
     for i in range(MAX_LEVELS):
@@ -341,6 +343,7 @@ def make_config(rows, cols, levels, mode, iterations, fx, fy, cx, cy, finest_lev
     c.nsamples = nsamples if nsamples is not None else (10000 if mode == MODE_TRACKER else 19200)
     c.fx, c.fy, c.cx, c.cy = fx, fy, cx, cy
     c.warp_first = int(warp_first)
+    c.termination, c.conv_eps = int(termination), float(conv_eps)  # ORC_TERM_*: 0 all iterations, 1 CHI_SQUARED, 2 convergence
     return c
 
 

@@ -1054,6 +1054,12 @@ int orc_align(const orc_align_config* C, const orc_pyramids* P, double* R, doubl
   float* W2 = warp_first ? (float*)malloc(sizeof(float) * maxpix) : NULL;
   float* I2 = warp_first ? (float*)malloc(sizeof(float) * maxpix) : NULL;
   int status = 0;
+  /* CHI_SQUARED termination, src/visodo.cpp:1134-1164: RMSE and RMSE_prev live across levels (:987-988), the pose
+   * before the last increment is what the reference's undo (:1147-1148) restores */
+  const int chi_term = (C->termination == ORC_TERM_CHI_SQUARED) && C->mode == ORC_MODE_TRACKER;
+  float rmse_prev = 9999.f;
+  double R_before[9], t_before[3];
+  memcpy(R_before, R, sizeof(R_before)); memcpy(t_before, t, sizeof(t_before));
 
   for (int level = C->levels - 1; level >= C->finest_level && !status; --level) {
     int rows = rows0 >> level, cols = cols0 >> level;
@@ -1062,6 +1068,7 @@ int orc_align(const orc_align_config* C, const orc_pyramids* P, double* R, doubl
     for (int iter = 0; iter < C->iterations[level]; ++iter) {
       float Rp[9], tp[3];
       float *W1 = W1buf, *I1 = I1buf;
+      int end_level = 0;
       if (warp_first && level > 0) {
         /* "expensive warping": warp at level 0 with the level-0 calibration, then build the pyramid of the
          * warped maps down to this level, every iteration (visodo.cpp:1078-1105) */
@@ -1070,6 +1077,14 @@ int orc_align(const orc_align_config* C, const orc_pyramids* P, double* R, doubl
         orc_projective_inverse_pose(R, t, fx0, fy0, cx0, cy0, Rp, tp);
         orc_warp_invdepth(P->W_cur[0], P->W_kf[0], W1, rows0, cols0, Rp, tp);
         orc_warp_intensity(P->I_cur[0], W1, I1, rows0, cols0, Rp, tp);
+        if (chi_term && iter != 0) { /* the test reads the level-0 warped maps, :1136-1139 */
+          float chi2, chit, ndof;
+          int n = orc_compute_error(I1, P->I_kf[0], rows0, cols0, 9999999, eI);
+          orc_compute_error(W1, P->W_kf[0], rows0, cols0, 9999999, eW);
+          orc_chi_square(eI, eW, n, 5.f, 0.0025f, C->mestimator, &chi2, &chit, &ndof);
+          float rmse = sqrtf(chi2) / sqrtf(ndof);
+          if (iter != 1 && rmse > rmse_prev) end_level = 1; else rmse_prev = rmse;
+        }
         float *Wn = W2, *In = I2;
         for (int i = 1; i <= level; ++i) {
           orc_pyr_down(I1, rows0 >> (i - 1), cols0 >> (i - 1), In);
@@ -1084,6 +1099,20 @@ int orc_align(const orc_align_config* C, const orc_pyramids* P, double* R, doubl
          * KeyframeAlign uses the keyframe iD (keyframe_align.cpp:239) */
         orc_warp_intensity(P->I_cur[level], C->mode == ORC_MODE_TRACKER ? W1 : P->W_kf[level], I1, rows,
                            cols, Rp, tp);
+        /* pyrFirst: warped_*_curr_[0] is only refreshed while level 0 iterates; above it the reference tests stale
+         * maps, the RMSE repeats and `RMSE > RMSE_prev` never holds -- the test is restated at level 0 only */
+        if (chi_term && iter != 0 && level == 0) {
+          float chi2, chit, ndof;
+          int n = orc_compute_error(I1, P->I_kf[0], rows0, cols0, 9999999, eI);
+          orc_compute_error(W1, P->W_kf[0], rows0, cols0, 9999999, eW);
+          orc_chi_square(eI, eW, n, 5.f, 0.0025f, C->mestimator, &chi2, &chit, &ndof);
+          float rmse = sqrtf(chi2) / sqrtf(ndof);
+          if (iter != 1 && rmse > rmse_prev) end_level = 1; else rmse_prev = rmse;
+        }
+      }
+      if (end_level) { /* undo the previous increment and end the iterations at this level, :1145-1151 */
+        memcpy(R, R_before, sizeof(R_before)); memcpy(t, t_before, sizeof(t_before));
+        break;
       }
       orc_system_params S;
       memset(&S, 0, sizeof(S));
@@ -1112,6 +1141,7 @@ int orc_align(const orc_align_config* C, const orc_pyramids* P, double* R, doubl
       orc_build_system(P->W_kf[level], P->I_kf[level], P->gWx_kf[level], P->gWy_kf[level],
                        P->gIx_kf[level], P->gIy_kf[level], W1, I1, rows, cols, &S, sums, A, b);
       double x[6];
+      memcpy(R_before, R, sizeof(R_before)); memcpy(t_before, t, sizeof(t_before));
       int bad = orc_gn_update(A, b, R, t, x);
       if (trace && nt < trace_cap) {
         orc_iter_trace* T = &trace[nt];
@@ -1126,6 +1156,11 @@ int orc_align(const orc_align_config* C, const orc_pyramids* P, double* R, doubl
       }
       ++nt;
       if (bad) { status = 1; break; }
+      if (C->termination == ORC_TERM_CONVERGENCE) {
+        double n2 = 0.0;
+        for (int k = 0; k < 6; ++k) n2 += x[k] * x[k];
+        if (n2 < (double)C->conv_eps * (double)C->conv_eps) break;
+      }
     }
   }
 

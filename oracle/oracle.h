@@ -37,7 +37,11 @@ typedef struct {
   int nsamples;        /* 10000 tracker, 19200 align */
   float fx, fy, cx, cy; /* level-0 intrinsics */
   int warp_first;      /* tracker only: WARP_ORDER = warpFirst (src/visodo.cpp:1078-1105); 0 = pyrFirst */
+  int termination;     /* ORC_TERM_*: tracker's TERMINATION_CRITERIA (src/internal.h:112, src/visodo.cpp:1134-1164) */
+  float conv_eps;      /* ORC_TERM_CONVERGENCE (BASELINE config 2, not in the reference): |x| < conv_eps ends a level */
 } orc_align_config;
+
+enum { ORC_TERM_ALL_ITERS = 0, ORC_TERM_CHI_SQUARED = 1, ORC_TERM_CONVERGENCE = 2 };
 
 typedef struct {
   const float* W_kf[ORC_MAX_LEVELS];

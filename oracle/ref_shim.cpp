@@ -283,6 +283,24 @@ int ref_align(const orc_align_config* C, const orc_pyramids* P, double* R, doubl
   }
   DeviceArray2D<float_type> gbuf; DeviceArray<float_type> mbuf;
   float3 z = make_float3(0, 0, 0);
+  /* CHI_SQUARED termination, src/visodo.cpp:1134-1164 (see oracle.c for the pyrFirst remark) */
+  const bool chi_term = (C->termination == ORC_TERM_CHI_SQUARED) && C->mode == ORC_MODE_TRACKER;
+  float rmse_prev = 9999.f;
+  double R_before[9], t_before[3];
+  memcpy(R_before, R, sizeof(R_before)); memcpy(t_before, t, sizeof(t_before));
+  DeviceArray<float> eI0, eW0;
+  auto chi_test = [&](int iter) -> bool {
+    Map Wkf0 = wrap(P->W_kf[0], (size_t)C->cols * sizeof(float), C->rows, C->cols);
+    Map Ikf0 = wrap(P->I_kf[0], (size_t)C->cols * sizeof(float), C->rows, C->cols);
+    computeErrorGridStride(I1[0], Ikf0, eI0);
+    computeErrorGridStride(W1[0], Wkf0, eW0);
+    float chi2 = 1.f, chit = 1.f, ndof = 1.f;
+    computeChiSquare(eI0, eW0, 5.f, 0.0025f, C->mestimator, chi2, chit, ndof);
+    float rmse = sqrt(chi2) / sqrt(ndof);
+    if (iter != 1 && rmse > rmse_prev) return true;
+    rmse_prev = rmse;
+    return false;
+  };
 
   for (int level = C->levels - 1; level >= C->finest_level && !status; --level) {
     int rows = C->rows >> level, cols = C->cols >> level;
@@ -295,6 +313,7 @@ int ref_align(const orc_align_config* C, const orc_pyramids* P, double* R, doubl
     Map Wc = wrap(P->W_cur[level], pitch, rows, cols), Ic = wrap(P->I_cur[level], pitch, rows, cols);
     for (int iter = 0; iter < C->iterations[level]; ++iter) {
       float Rp[9], tp[3];
+      bool end_level = false;
       if (C->warp_first && C->mode == ORC_MODE_TRACKER && level > 0) {
         /* WARP_ORDER = warpFirst, src/visodo.cpp:1078-1105: warp at level 0, pyramid of the warped maps */
         size_t pitch0 = (size_t)C->cols * sizeof(float);
@@ -305,6 +324,7 @@ int ref_align(const orc_align_config* C, const orc_pyramids* P, double* R, doubl
         Mat33 dR0 = mat33(Rp); float3 dt0 = make_float3(tp[0], tp[1], tp[2]);
         warpInvDepthWithTrafo3D(Wc0, W1[0], Wkf0, dR0, dt0, intr0);
         warpIntensityWithTrafo3DInvDepth(Ic0, I1[0], W1[0], dR0, dt0, intr0);
+        if (chi_term && iter != 0) end_level = chi_test(iter);
         for (int i = 1; i <= level; ++i) {
           pyrDownIntensity(I1[i - 1], I1[i]);
           pyrDownDepth(W1[i - 1], W1[i]);
@@ -314,7 +334,9 @@ int ref_align(const orc_align_config* C, const orc_pyramids* P, double* R, doubl
       Mat33 dR = mat33(Rp); float3 dt = make_float3(tp[0], tp[1], tp[2]);
       warpInvDepthWithTrafo3D(Wc, W1[level], Wkf, dR, dt, intr, numSMs);
       warpIntensityWithTrafo3DInvDepth(Ic, I1[level], C->mode == ORC_MODE_TRACKER ? W1[level] : Wkf, dR, dt, intr, numSMs);
+      if (chi_term && iter != 0 && level == 0) end_level = chi_test(iter);
       }
+      if (end_level) { memcpy(R, R_before, sizeof(R_before)); memcpy(t, t_before, sizeof(t_before)); break; }
       float sigma_int = 5.f, sigma_w = 0.0025f, bias_int = 0.f, bias_w = 0.f, nu_int = 5.f, nu_w = 5.f;
       if (C->mode == ORC_MODE_TRACKER) {
         if (C->sigma_estimator == ORC_SIGMA_PDF) {
@@ -336,6 +358,7 @@ int ref_align(const orc_align_config* C, const orc_pyramids* P, double* R, doubl
                                      C->mode == ORC_MODE_TRACKER ? C->weighting : (int)INDEPENDENT,
                                      sigma_w, sigma_int, bias_w, bias_int, nu_w, nu_int, intr, 6, gbuf, mbuf, A, b, numSMs);
       double x[6];
+      memcpy(R_before, R, sizeof(R_before)); memcpy(t_before, t, sizeof(t_before));
       int bad = orc_gn_update(A, b, R, t, x);
       if (trace && nt < trace_cap) {
         orc_iter_trace* T = &trace[nt];
@@ -348,6 +371,11 @@ int ref_align(const orc_align_config* C, const orc_pyramids* P, double* R, doubl
       }
       ++nt;
       if (bad) { status = 1; break; }
+      if (C->termination == ORC_TERM_CONVERGENCE) {
+        double n2 = 0.0;
+        for (int k = 0; k < 6; ++k) n2 += x[k] * x[k];
+        if (n2 < (double)C->conv_eps * (double)C->conv_eps) break;
+      }
     }
   }
   if (status) {

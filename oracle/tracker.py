@@ -94,12 +94,14 @@ def relative_constraint(R_last, t_last, cov_last, R_new, t_new, cov_new):
 class OracleTracker:
     def __init__(self, rows, cols, intr, levels=3, iterations=(10, 5, 3), kind="cpu", motion_model=True,
                  visratio_odo=0.9, visratio_integr=0.7, delta_t=0.03333, mestimator=orc.STUDENT,
-                 sigma_estimator=orc.SIGMA_PDF, nsamples=10000, factor_depth=1.0, warp_first=0):
+                 sigma_estimator=orc.SIGMA_PDF, nsamples=10000, factor_depth=1.0, warp_first=0, termination=0,
+                 conv_eps=0.0):
         self.B = backend(kind)
         self.rows, self.cols, self.intr, self.levels = rows, cols, intr, levels
         self.cfg = orc.make_config(rows, cols, levels, orc.MODE_TRACKER, list(iterations), intr["fx"], intr["fy"],
                                    intr["cx"], intr["cy"], mestimator=mestimator, sigma_estimator=sigma_estimator,
-                                   nsamples=nsamples, warp_first=warp_first)
+                                   nsamples=nsamples, warp_first=warp_first, termination=termination,
+                                   conv_eps=conv_eps)
         self.motion_model, self.vo, self.vi = motion_model, visratio_odo, visratio_integr
         self.dt = np.float32(delta_t)
         self.factor_depth = factor_depth
@@ -161,7 +163,7 @@ class OracleTracker:
         W, I = B.depth_to_invdepth(depth_u16, self.factor_depth), B.intensity(rgb_u8)
         cur = B.prepare_current(W, I, self.levels)
         res = dict(frame_index=self.global_time, status=0, new_odo_keyframe=0, new_integr_keyframe=0,
-                   visibility_odo=1.0, visibility_integr=1.0)
+                   visibility_odo=1.0, visibility_integr=1.0, lost_again=0)
         if self.global_time == 0:
             self.kf = B.prepare_keyframe(W, I, self.levels, tracker=True)
             self._save_integration_kf(cur)
@@ -170,6 +172,7 @@ class OracleTracker:
                        new_odo_keyframe=1, new_integr_keyframe=1)
             return res
         prevR, prevt, prevcov = self.dR.copy(), self.dt_.copy(), self.dcov.copy()
+        was_lost = self.lost
         if self.global_time > 1 and self.motion_model and not self.lost:
             dRp, dtp = orc.exp_map(self.omega * float(self.dt), self.vel * float(self.dt))
             Ri, ti = prevR @ dRp, prevR @ dtp + prevt
@@ -192,6 +195,14 @@ class OracleTracker:
         res.update(R=self.R_est.copy(), t=self.t_est.copy(), dR=self.dR.copy(), dt=self.dt_.copy(), cov=self.dcov.copy())
         dRi = np.linalg.inv(self.R_intKF) @ self.R_est
         dti = np.linalg.inv(self.R_intKF) @ (self.t_est - self.t_intKF)
+        if not ok and was_lost:
+            # failed again while lost (:2111-2116): re-save both keyframes from this frame, nothing else -- no reset of
+            # the keyframe poses, no keyframe or constraint for the back end, global_time_ stands still
+            self.kf = B.prepare_keyframe(W, I, self.levels, tracker=True)
+            self._save_integration_kf(cur)
+            res.update(new_odo_keyframe=1, new_integr_keyframe=1, lost_again=1, kf_handoff=None,
+                       seq=(np.eye(3), np.zeros(3), 100.0 * np.eye(6)))
+            return res
         if not ok:
             self.lost = True
             new_odo, new_int = True, True

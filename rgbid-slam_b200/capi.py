@@ -19,6 +19,7 @@ SIGMA_MAD, SIGMA_PDF, SIGMA_CONS = 0, 1, 2
 INDEPENDENT, MIN_WEIGHT, GEOM_ONLY, PHOT_ONLY = 0, 1, 2, 3
 NO_FILTERS, FILTER_GRADS = 0, 1
 MODE_TRACKER, MODE_ALIGN = 0, 1
+TERM_ALL_ITERS, TERM_CHI_SQUARED, TERM_CONVERGENCE = 0, 1, 2
 
 c_float_p = C.POINTER(C.c_float)
 c_double_p = C.POINTER(C.c_double)
@@ -50,7 +51,8 @@ class AlignConfig(C.Structure):
                 ("iterations", C.c_int * MAX_LEVELS), ("batch", C.c_int), ("mode", C.c_int),
                 ("mestimator", C.c_int), ("weighting", C.c_int), ("sigma_estimator", C.c_int),
                 ("nsamples", C.c_int), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float),
-                ("cy", C.c_float), ("factor_depth", C.c_float), ("with_fusion", C.c_int), ("warp_first", C.c_int)]
+                ("cy", C.c_float), ("factor_depth", C.c_float), ("with_fusion", C.c_int), ("warp_first", C.c_int),
+                ("termination", C.c_int), ("conv_eps", C.c_float)]
 
 
 class IterTrace(C.Structure):
@@ -72,7 +74,8 @@ class FrameResult(C.Structure):
                 ("cov", C.c_double * 36), ("visibility_odo", C.c_float), ("visibility_integr", C.c_float),
                 ("chi_square", C.c_float), ("chi_test", C.c_float), ("ndof", C.c_float), ("status", C.c_int),
                 ("new_odo_keyframe", C.c_int), ("new_integr_keyframe", C.c_int), ("frame_index", C.c_int),
-                ("seq_R", C.c_double * 9), ("seq_t", C.c_double * 3), ("seq_cov", C.c_double * 36)]
+                ("seq_R", C.c_double * 9), ("seq_t", C.c_double * 3), ("seq_cov", C.c_double * 36),
+                ("lost_again", C.c_int)]
 
 
 class KeyframeHandoff(C.Structure):
@@ -129,6 +132,7 @@ PROTOTYPES = {
     "rgbid_aligner_create": (I, [P, C.POINTER(AlignConfig), C.POINTER(P)]),
     "rgbid_aligner_destroy": (I, [P]),
     "rgbid_aligner_num_iterations": (I, [P]),
+    "rgbid_aligner_iterations_done": (I, [P, c_int_p]),
     "rgbid_aligner_set_keyframe": (I, [P, I, P, SZ, P, SZ, I]),
     "rgbid_aligner_set_current": (I, [P, I, P, SZ, P, SZ, I]),
     "rgbid_aligner_set_current_rgbd": (I, [P, I, P, SZ, P, SZ, I]),

@@ -87,6 +87,9 @@ static GnParams base_params(const rgbid_aligner* al, int level)
   P.sample_stride = al->geom[level].sample_stride;
   P.sigma_op = (c.mode == RGBID_MODE_TRACKER) ? SCALE_SIGMA_NU : SCALE_NU_ONLY;
   P.next_level = -1;
+  P.sched_level = level; P.sched_iter = 0;
+  P.termination = c.termination;
+  P.conv_eps = (c.termination == RGBID_TERM_CONVERGENCE) ? c.conv_eps : 0.f;
   return P;
 }
 
@@ -126,6 +129,19 @@ static void record_chain(rgbid_aligner* al, LaunchCtx L, int first, int count, c
       GnParams P = base_params(al, level);
       P.first = first; P.batch = count; P.batch_total = c.batch;
       P.iter_index = done;
+      P.sched_iter = it;
+      if (tracker && c.termination == RGBID_TERM_CHI_SQUARED && it > 0 && (warp_first || level == 0)) {
+        // cost-function test that ends the iterations of this level (src/visodo.cpp:1134-1164): robust chi^2 of ALL
+        // level-0 residuals at the current pose -- the fused kernel at level 0 with the chi^2 sums switched on and
+        // nothing else to do; its tail compares the RMSE with the previous test's and undoes the last increment
+        GnParams T = base_params(al, 0);
+        T.first = first; T.batch = count; T.batch_total = c.batch;
+        T.iter_index = -1; T.sched_level = level; T.sched_iter = it;
+        T.use_scale = 0; T.student_nu = 0; T.mestimator = RGBID_STUDENT;
+        T.update_pose = 0; T.compute_cov = 0; T.chi_mestimator = c.mestimator;
+        T.chi_test = (it == 1) ? 1 : 2;
+        launch_gn_build(L, level_maps(al, 0, false), T, al->d_states, nullptr, al->d_partials, 32, al->d_counters, nullptr);
+      }
       // the updated pose is consumed at this level again, at the next coarser-to-finer level that has iterations,
       // or by the covariance pass at the finest level
       P.next_level = level;
@@ -154,7 +170,9 @@ static void record_chain(rgbid_aligner* al, LaunchCtx L, int first, int count, c
         M.texW = nullptr; M.texI = nullptr; M.tex_border = 0;
         P.prewarped = 1;
       }
-      if (warp_first) P.next_level = -1;  // the level-0 projection is needed whatever level iterates next
+      // the level-0 projection is needed whatever level iterates next (warpFirst: level-0 warp every iteration;
+      // CHI_SQUARED: the test runs on level 0)
+      if (warp_first || (tracker && c.termination == RGBID_TERM_CHI_SQUARED)) P.next_level = -1;
       if (estimate_scale) launch_gn_scale(L, M, P, al->d_states, al->d_scales);
       if (!signalled) { cudaEventRecord(after_first_launch, L.stream); signalled = true; }
       launch_gn_build(L, M, P, al->d_states, al->d_scales, al->d_partials, 32, al->d_counters, al->d_trace);
@@ -214,6 +232,8 @@ int rgbid_aligner_create(rgbid_ctx* ctx, const rgbid_align_config* cfg, rgbid_al
   if (cfg->finest_level < 0 || cfg->finest_level >= cfg->levels) return RGBID_ERR_ARG;
   if ((cfg->rows % (1 << (cfg->levels - 1))) || (cfg->cols % (1 << (cfg->levels - 1)))) return RGBID_ERR_ARG;
   if (!(cfg->fx > 0.f) || !(cfg->fy > 0.f)) return RGBID_ERR_ARG;
+  if (cfg->termination < RGBID_TERM_ALL_ITERS || cfg->termination > RGBID_TERM_CONVERGENCE) return RGBID_ERR_ARG;
+  if (cfg->termination == RGBID_TERM_CONVERGENCE && !(cfg->conv_eps > 0.f)) return RGBID_ERR_ARG;
   RGBID_CUDA_TRY(cudaSetDevice(ctx->device));
   rgbid_aligner* al = new (std::nothrow) rgbid_aligner();
   if (!al) return RGBID_ERR_NOMEM;
@@ -350,6 +370,14 @@ int rgbid_aligner_destroy(rgbid_aligner* al)
 }
 
 int rgbid_aligner_num_iterations(const rgbid_aligner* al) { return al ? al->niters : 0; }
+
+int rgbid_aligner_iterations_done(const rgbid_aligner* al, int* out)
+{
+  if (!al || !out) return RGBID_ERR_ARG;
+  for (int b = 0; b < al->cfg.batch; ++b)
+    for (int l = 0; l < RGBID_MAX_LEVELS; ++l) out[b * RGBID_MAX_LEVELS + l] = al->h_states[b].iters_done[l];
+  return RGBID_OK;
+}
 
 int rgbid_aligner_set_keyframe(rgbid_aligner* al, int index, const float* depthinv, size_t dpitch,
                                const float* intensity, size_t ipitch, int from_host)

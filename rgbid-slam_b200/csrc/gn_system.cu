@@ -155,16 +155,31 @@ struct BuildShared {
 
 // Block reduce + publish the per-CTA partial + elect the last CTA of this pair + fixed-order final sum.
 // Returns true in every thread of the last CTA, with sh.total[0..NACC) holding the pair's sums.
+//
+// wscratch: NACC x 32 floats of shared memory owned by the calling WARP.  The lane sums go through it instead of
+// through shuffles: a double butterfly costs 10 SHFL + 5 DADD per value (27 values: 400 instructions per warp, at one
+// SHFL per clock per SM -- RGBID_TAIL_PROBE showed ~14 000 clocks between the end of the pixel loop and the election);
+// here lane k adds the 32 lane values of sum k in double (4 chains of 8, rotated start: conflict-free banks), fixed order.
 template <int NACC>
-__device__ __forceinline__ bool reduce_and_elect(BuildShared& sh, const float* acc, double* __restrict__ partials,
-                                                 int partial_stride, unsigned int* __restrict__ counter, int nblk,
-                                                 int blk)
+__device__ __forceinline__ bool reduce_and_elect(BuildShared& sh, const float* acc, float* wscratch,
+                                                 double* __restrict__ partials, int partial_stride,
+                                                 unsigned int* __restrict__ counter, int nblk, int blk)
 {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 #pragma unroll
-  for (int k = 0; k < NACC; ++k) {
-    double v = warp_sum((double)acc[k]);
-    if (lane == 0) sh.warp_part[wid][k] = v;
+  for (int k = 0; k < NACC; ++k) wscratch[k * 32 + lane] = acc[k];
+  __syncwarp();
+  if (lane < NACC) {
+    const float* row = wscratch + lane * 32;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      s0 += (double)row[(j + 0 + lane) & 31];
+      s1 += (double)row[(j + 1 + lane) & 31];
+      s2 += (double)row[(j + 2 + lane) & 31];
+      s3 += (double)row[(j + 3 + lane) & 31];
+    }
+    sh.warp_part[wid][lane] = (s0 + s1) + (s2 + s3);
   }
   __syncthreads();
   if (tid < NACC) {
@@ -172,8 +187,8 @@ __device__ __forceinline__ bool reduce_and_elect(BuildShared& sh, const float* a
 #pragma unroll
     for (int w = 0; w < kBuildWarps; ++w) v += sh.warp_part[w][tid];
     partials[(size_t)blk * partial_stride + tid] = v;
+    __threadfence();
   }
-  __threadfence();
   __syncthreads();
   if (tid == 0) {
     unsigned ticket = atomicAdd(counter, 1u);
@@ -202,12 +217,14 @@ __device__ __forceinline__ bool reduce_and_elect(BuildShared& sh, const float* a
 }
 
 // only: the one level the next launch reads (-1: all levels)
-__device__ __forceinline__ void refresh_proj(GnState& st, int levels, float fx0, float fy0, float cx0, float cy0,
-                                             int only = -1)
+__device__ __forceinline__ void refresh_proj(GnState& st, const double* R, const double* t, int levels, float fx0,
+                                             float fy0, float cx0, float cy0, int only = -1)
 {
+  // R is a product of rotations re-orthogonalised at every step: its inverse is its transpose to rounding (the
+  // reference calls Eigen's general inverse(), src/visodo.cpp:1066-1067 -- a division chain this tail cannot afford)
   double Ri[9], ti[3];
-  mat3_inverse(st.R, Ri);
-  mat3_vec(Ri, st.t, ti);
+  mat3_transpose(R, Ri);
+  mat3_vec(Ri, t, ti);
   ti[0] = -ti[0]; ti[1] = -ti[1]; ti[2] = -ti[2];
   for (int l = 0; l < levels; ++l) {
     if (only >= 0 && l != only) continue;
@@ -217,13 +234,53 @@ __device__ __forceinline__ void refresh_proj(GnState& st, int levels, float fx0,
 }
 
 // Tail executed by one thread of the last CTA: the host part of one reference iteration
-// (src/visodo.cpp:1242-1274 / src/keyframe_align.cpp:312-350) or of the covariance pass (:1382-1415).
-__device__ __noinline__ void gn_tail(GnState& st, const double* tot, const GnParams& P, const ScaleState* sc,
-                        rgbid_iter_trace* __restrict__ trace, int b, bool chi)
+// (src/visodo.cpp:1242-1274 / src/keyframe_align.cpp:312-350), of the covariance pass (:1382-1415) or of the
+// CHI_SQUARED termination test (:1134-1164).  Three separate functions, so that the per-iteration path is small (it is
+// cold code executed once per launch by a single thread: RGBID_TAIL_PROBE measured ~11 000 clocks for ~800 instructions)
+// and gets its own register allocation instead of inheriting the spills of the 6x6 Gauss-Jordan inverse.
+__device__ __noinline__ void gn_tail_update(GnState& st, const double* tot, const GnParams& P, double* x)
 {
-  double A[36], bv[6], x[6] = {0, 0, 0, 0, 0, 0};
-  unpack_system(tot, A, bv);
+  // pose in registers: every access through `st` is a global load / store the compiler may not reorder
+  double R[9], t[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = st.R[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) t[i] = st.t[i];
+  if (P.termination == RGBID_TERM_CHI_SQUARED) {  // the increment may have to be undone by the next test
+#pragma unroll
+    for (int i = 0; i < 9; ++i) st.Rprev[i] = R[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) st.tprev[i] = t[i];
+  }
+  llt_solve_packed(tot, x);
+  bool bad = gn_update_lean(x, R, t);
+  if (bad) {
+    // lost: keep the previous pose, covariance 100 I (src/visodo.cpp:1265-1274)
+    st.status = RGBID_ERR_NAN;
+    for (int i = 0; i < 9; ++i) R[i] = st.R0[i];
+    for (int i = 0; i < 3; ++i) t[i] = st.t0[i];
+    for (int i = 0; i < 36; ++i) st.cov[i] = (i % 7 == 0) ? 100.0 : 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) st.R[i] = R[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) st.t[i] = t[i];
+  st.iters_done[P.sched_level] = P.sched_iter + 1;
+  int next = P.next_level;
+  if (P.conv_eps > 0.f) {
+    // CONVERGENCE termination (BASELINE config 2): this update was small enough -> the level's remaining launches
+    // are no-ops for this pair, and whichever level iterates next needs its projection
+    const double n2 = (x[0] * x[0] + x[1] * x[1] + x[2] * x[2]) + (x[3] * x[3] + x[4] * x[4] + x[5] * x[5]);
+    if (n2 < (double)P.conv_eps * (double)P.conv_eps) { st.skip_level = P.sched_level; next = -1; }
+  }
+  refresh_proj(st, R, t, P.levels, P.fx0, P.fy0, P.cx0, P.cy0, next);
+}
+
+__device__ __noinline__ void gn_tail_cov(GnState& st, const double* tot, const GnParams& P, bool chi)
+{
   if (P.compute_cov) {
+    double A[36], bv[6];
+    unpack_system(tot, A, bv);
     for (int i = 0; i < 36; ++i) st.lastA[i] = A[i];
     inverse6(A, st.cov);
   }
@@ -233,35 +290,58 @@ __device__ __noinline__ void gn_tail(GnState& st, const double* tot, const GnPar
     float chi2 = (float)(tot[27] + tot[29]) / n;
     float z = (chi2 - n) / sqrtf(2.f * n);
     st.chi_square = chi2; st.ndof = n; st.chi_test = 0.5f * (1.f + erff(z / sqrtf(2.f)));
-  }
-  if (P.update_pose) {
-    llt_solve6(A, bv, x);
-    bool bad = gn_update(x, st.R, st.t);
-    if (bad) {
-      // lost: keep the previous pose, covariance 100 I (src/visodo.cpp:1265-1274)
-      st.status = RGBID_ERR_NAN;
-      for (int i = 0; i < 9; ++i) st.R[i] = st.R0[i];
-      for (int i = 0; i < 3; ++i) st.t[i] = st.t0[i];
-      for (int i = 0; i < 36; ++i) st.cov[i] = (i % 7 == 0) ? 100.0 : 0.0;
+    if (P.chi_test) {
+      // CHI_SQUARED termination (src/visodo.cpp:1139-1163): RMSE of all level-0 residuals at the current pose
+      const float rmse = sqrtf(chi2) / sqrtf(n);
+      if (P.chi_test == 2 && rmse > st.rmse_prev) {
+        // undo the previous increment and end the iterations of this level
+        double R[9], t[3];
+        for (int i = 0; i < 9; ++i) { R[i] = st.Rprev[i]; st.R[i] = R[i]; }
+        for (int i = 0; i < 3; ++i) { t[i] = st.tprev[i]; st.t[i] = t[i]; }
+        st.skip_level = P.sched_level;
+        st.iters_done[P.sched_level] = P.sched_iter - 1;  // the undone iteration does not count
+        refresh_proj(st, R, t, P.levels, P.fx0, P.fy0, P.cx0, P.cy0, -1);
+      } else {
+        st.rmse_prev = rmse;
+      }
     }
-    refresh_proj(st, P.levels, P.fx0, P.fy0, P.cx0, P.cy0, P.next_level);
   }
-  if (trace != nullptr && P.trace_stride > 0 && P.iter_index >= 0 && P.iter_index < P.trace_stride) {
-    rgbid_iter_trace& T = trace[(size_t)b * P.trace_stride + P.iter_index];
-    T.level = P.level; T.iter = P.iter_index;
-    for (int i = 0; i < 27; ++i) T.sums27[i] = tot[i];
-    if (sc != nullptr && P.use_scale) {
-      T.sigma_int = sc->sigma_int; T.sigma_depthinv = sc->sigma_depthinv; T.bias_int = sc->bias_int;
-      T.bias_depthinv = sc->bias_depthinv; T.nu_int = sc->nu_int; T.nu_depthinv = sc->nu_depthinv;
-      T.irls_iters_int = sc->irls_iters_int; T.irls_iters_depthinv = sc->irls_iters_depthinv;
-    } else {
-      T.sigma_int = 5.f; T.sigma_depthinv = 0.0025f; T.bias_int = 0.f; T.bias_depthinv = 0.f;
-      T.nu_int = 5.f; T.nu_depthinv = 5.f; T.irls_iters_int = 0; T.irls_iters_depthinv = 0;
-    }
-    for (int i = 0; i < 6; ++i) T.x[i] = x[i];
-    for (int i = 0; i < 9; ++i) T.R[i] = st.R[i];
-    for (int i = 0; i < 3; ++i) T.t[i] = st.t[i];
+}
+
+__device__ __noinline__ void gn_tail_trace(const GnState& st, const double* tot, const GnParams& P, const ScaleState* sc,
+                                           rgbid_iter_trace* __restrict__ trace, int b, const double* x)
+{
+  rgbid_iter_trace& T = trace[(size_t)b * P.trace_stride + P.iter_index];
+  T.level = P.level; T.iter = P.iter_index;
+  for (int i = 0; i < 27; ++i) T.sums27[i] = tot[i];
+  if (sc != nullptr && P.use_scale) {
+    T.sigma_int = sc->sigma_int; T.sigma_depthinv = sc->sigma_depthinv; T.bias_int = sc->bias_int;
+    T.bias_depthinv = sc->bias_depthinv; T.nu_int = sc->nu_int; T.nu_depthinv = sc->nu_depthinv;
+    T.irls_iters_int = sc->irls_iters_int; T.irls_iters_depthinv = sc->irls_iters_depthinv;
+  } else {
+    T.sigma_int = 5.f; T.sigma_depthinv = 0.0025f; T.bias_int = 0.f; T.bias_depthinv = 0.f;
+    T.nu_int = 5.f; T.nu_depthinv = 5.f; T.irls_iters_int = 0; T.irls_iters_depthinv = 0;
   }
+  for (int i = 0; i < 6; ++i) T.x[i] = x[i];
+  for (int i = 0; i < 9; ++i) T.R[i] = st.R[i];
+  for (int i = 0; i < 3; ++i) T.t[i] = st.t[i];
+}
+
+__device__ __forceinline__ void gn_tail(GnState& st, const double* tot, const GnParams& P, const ScaleState* sc,
+                                        rgbid_iter_trace* __restrict__ trace, int b, bool chi)
+{
+  double x[6] = {0, 0, 0, 0, 0, 0};
+  if (P.compute_cov || chi) gn_tail_cov(st, tot, P, chi);
+  if (P.update_pose) gn_tail_update(st, tot, P, x);
+  if (trace != nullptr && P.trace_stride > 0 && P.iter_index >= 0 && P.iter_index < P.trace_stride)
+    gn_tail_trace(st, tot, P, sc, trace, b, x);
+}
+
+// a launch is a no-op for a pair that is lost or whose level has been ended by cfg.termination; uniform over all CTAs
+// of the pair because both fields are only written by the tail of an earlier launch
+__device__ __forceinline__ bool pair_skipped(const GnState& st, const GnParams& P)
+{
+  return st.status != RGBID_OK || st.skip_level == P.sched_level;
 }
 
 __device__ __forceinline__ PixelParams make_pixel_params(const GnParams& P, const ScaleState* sc)
@@ -295,7 +375,7 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
   constexpr int NACC = CHI ? kAccChi : kAcc;
   const int b = blockIdx.y + P.first;
   GnState& st = states[b];
-  if (st.status != RGBID_OK) return;  // lost pairs are skipped consistently by every CTA
+  if (pair_skipped(st, P)) return;
   __shared__ BuildShared sh;
   if (threadIdx.x < 12) {
     const float* src = (const float*)&st.proj[P.level];
@@ -365,8 +445,9 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
       accumulate_pixel<CHI>(acc, x0 + k, y, w0[k], i0[k], gwx[k], gwy[k], gix[k], giy[k], w1[k], i1[k], pp);
   }
 
-  if (!reduce_and_elect<NACC>(sh, acc, partials + (size_t)b * gridDim.x * partial_stride, partial_stride,
-                              &counters[b], gridDim.x, blockIdx.x))
+  __shared__ float scratch[kBuildWarps][kAccChi * 32];
+  if (!reduce_and_elect<NACC>(sh, acc, scratch[threadIdx.x >> 5], partials + (size_t)b * gridDim.x * partial_stride,
+                              partial_stride, &counters[b], gridDim.x, blockIdx.x))
     return;
   if (threadIdx.x == 0) gn_tail(st, sh.total, P, sc, trace, b, CHI);
 }
@@ -487,7 +568,7 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
   __shared__ __align__(8) unsigned long long bars[kBuildWarps * (kStagesW + kStagesL)];
   const int b = blockIdx.y + P.first;
   GnState& st = states[b];
-  if (st.status != RGBID_OK) return;  // lost pairs are skipped consistently by every CTA
+  if (pair_skipped(st, P)) return;
 #if RGBID_TAIL_PROBE
   const long long probe_t0 = clock64();
 #endif
@@ -816,24 +897,31 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
   for (int k = 0; k < kAcc; ++k) acc[k] = accs[k];
 #endif
   if (CHI) { acc[27] = chi[0]; acc[28] = chi[1]; acc[29] = chi[2]; acc[30] = chi[3]; }
+  // every bulk copy this warp issued has been waited for and consumed: its ring (10 KiB) is free for the lane sums
+  float* wscratch = (float*)(ring + (size_t)wid * kWarpRingBytes);
+  static_assert(kWarpRingBytes >= kAccChi * 32 * (int)sizeof(float), "ring too small for the lane-sum scratch");
 
 #if RGBID_TAIL_PROBE
   // -DRGBID_TAIL_PROBE=1 (diagnostic build): clocks of the last CTA of pair 0 -- pixel loop,
   // CTA reduction + election + fixed-order final sum, serial tail (6x6 solve, pose update, projection refresh, trace)
   const long long probe_t1 = clock64();
-  if (!reduce_and_elect<NACC>(sh, acc, partials + (size_t)b * gridDim.x * partial_stride, partial_stride,
+  if (!reduce_and_elect<NACC>(sh, acc, wscratch, partials + (size_t)b * gridDim.x * partial_stride, partial_stride,
                               &counters[b], gridDim.x, blockIdx.x))
     return;
   const long long probe_t2 = clock64();
   if (threadIdx.x == 0) {
     gn_tail(st, sh.total, P, sc, trace, b, CHI);
     const long long probe_t3 = clock64();
+    // second call on the same data: the same instructions, now in the instruction cache (the pose of this diagnostic
+    // build is garbage afterwards)
+    gn_tail(st, sh.total, P, sc, trace, b, CHI);
+    const long long probe_t4 = clock64();
     if (b == 0)
-      printf("tail probe level %d iter %d cta %d | loop %lld reduce+elect %lld tail %lld\n", P.level, P.iter_index,
-             (int)blockIdx.x, probe_t1 - probe_t0, probe_t2 - probe_t1, probe_t3 - probe_t2);
+      printf("tail probe level %d iter %d cta %d | loop %lld reduce+elect %lld tail %lld, repeated %lld\n", P.level, P.iter_index,
+             (int)blockIdx.x, probe_t1 - probe_t0, probe_t2 - probe_t1, probe_t3 - probe_t2, probe_t4 - probe_t3);
   }
 #else
-  if (!reduce_and_elect<NACC>(sh, acc, partials + (size_t)b * gridDim.x * partial_stride, partial_stride,
+  if (!reduce_and_elect<NACC>(sh, acc, wscratch, partials + (size_t)b * gridDim.x * partial_stride, partial_stride,
                               &counters[b], gridDim.x, blockIdx.x))
     return;
   if (threadIdx.x == 0) gn_tail(st, sh.total, P, sc, trace, b, CHI);
@@ -873,7 +961,8 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
     for (int k = 0; k < VEC; ++k)
       accumulate_pixel<false>(acc, x0 + k, y, w0[k], i0[k], gwx[k], gwy[k], gix[k], giy[k], w1[k], i1[k], pp);
   }
-  if (!reduce_and_elect<kAcc>(sh, acc, partials, kAccChi, counter, gridDim.x, blockIdx.x)) return;
+  __shared__ float scratch[kBuildWarps][kAcc * 32];
+  if (!reduce_and_elect<kAcc>(sh, acc, scratch[threadIdx.x >> 5], partials, kAccChi, counter, gridDim.x, blockIdx.x)) return;
   if (threadIdx.x < kAcc) out27[threadIdx.x] = sh.total[threadIdx.x];
 }
 
@@ -893,7 +982,7 @@ __global__ void __cluster_dims__(kScaleCluster, 1, 1) __launch_bounds__(kScaleTh
   const int b = blockIdx.x / kScaleCluster + P.first;
   const int rank = (int)cluster.block_rank();
   const GnState& st = states[b];
-  if (st.status != RGBID_OK) return;  // uniform over the whole cluster
+  if (pair_skipped(st, P)) return;  // uniform over the whole cluster
   if (threadIdx.x < 12) ((float*)&s_proj)[threadIdx.x] = ((const float*)&st.proj[P.level])[threadIdx.x];
   __syncthreads();
   const Proj proj = s_proj;
@@ -992,8 +1081,10 @@ __global__ void gn_init_kernel(GnState* __restrict__ states, const double* __res
   for (int i = 0; i < 3; ++i) { st.t[i] = t_init[3 * b + i]; st.t0[i] = st.t[i]; }
   for (int i = 0; i < 36; ++i) { st.cov[i] = 0.0; st.lastA[i] = 0.0; }
   st.status = RGBID_OK; st.iter_count = 0;
+  st.skip_level = -1; st.rmse_prev = 9999.f;
+  for (int l = 0; l < RGBID_MAX_LEVELS; ++l) st.iters_done[l] = 0;
   st.chi_square = 0.f; st.chi_test = 0.f; st.ndof = 0.f;
-  refresh_proj(st, levels, fx0, fy0, cx0, cy0);
+  refresh_proj(st, st.R, st.t, levels, fx0, fy0, cx0, cy0);
 }
 
 // every stream of the map owns whole 128-pixel chunks (the aligner NaN-fills the padding and nothing writes it),
@@ -1034,8 +1125,16 @@ void launch_gn_scale(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P
   const int n = P.kept_rows * P.kept_cols;
   const int chunk = (n + kScaleCluster - 1) / kScaleCluster;
   size_t smem = (size_t)2 * chunk * sizeof(float);
-  static PerDevice table, smem_limit;
+  static PerDevice table, smem_limit, carve;
   table.once([] { upload_nu_table(); });
+  // RGBID_CHAINS=2: the scale kernel of one group of streams has to share SMs with the system kernel of the other; two
+  // kernels are only co-resident on an SM under the same shared-memory carve-out
+  static const bool same_carveout = [] { const char* e = getenv("RGBID_CHAINS"); return e && e[0] == '2'; }();
+  if (same_carveout)
+    carve.once([] {
+      cudaFuncSetAttribute(gn_scale_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(gn_scale_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    });
   if (smem > 48 * 1024)
     smem_limit.at_least(smem, [](size_t bytes) {
       cudaFuncSetAttribute(gn_scale_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -1097,6 +1196,15 @@ void launch_gn_build(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P
       cudaFuncSetAttribute(gn_build_fast_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
       cudaFuncSetAttribute(gn_build_fast_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
       cudaFuncSetAttribute(gn_build_fast_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
+      const char* e = getenv("RGBID_CHAINS");
+      if (e && e[0] == '2') {
+        cudaFuncSetAttribute(gn_build_fast_kernel<true, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(gn_build_fast_kernel<true, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(gn_build_fast_kernel<true, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(gn_build_fast_kernel<false, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(gn_build_fast_kernel<false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(gn_build_fast_kernel<false, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      }
     });
     const bool tracker = (P.mode == RGBID_MODE_TRACKER);
     const int chim = !chi ? 0 : (P.chi_mestimator == RGBID_STUDENT ? 2 : 1);

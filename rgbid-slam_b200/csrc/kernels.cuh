@@ -138,6 +138,12 @@ struct GnState {
   int status;                // RGBID_OK | RGBID_ERR_NAN
   int iter_count;            // trace cursor
   float chi_square, chi_test, ndof;
+  // cfg.termination: level whose remaining launches are no-ops for this pair (-1: none), iterations executed per
+  // level, pose before the last update (CHI_SQUARED undo) and the RMSE of the previous test
+  int skip_level;
+  int iters_done[RGBID_MAX_LEVELS];
+  double Rprev[9], tprev[3];
+  float rmse_prev;
   int pad;
 };
 
@@ -160,6 +166,12 @@ struct GnParams {
   int next_level;               // level of the launch that consumes the updated pose (-1: refresh proj[] of all levels)
   int first;                    // first frame pair of this launch (the batch may be launched in groups, see aligner.cu)
   int batch_total;              // pairs of the whole batch (grid sizing); 0: same as batch
+  int sched_level;              // level of the schedule step this launch belongs to (the termination test of a coarse
+                                // level runs on level-0 maps); a pair with skip_level == sched_level is skipped
+  int sched_iter;               // iteration of sched_level this launch belongs to
+  int termination;              // cfg.termination
+  int chi_test;                 // CHI_SQUARED termination test launch: 1 = record the RMSE, 2 = compare, undo, end level
+  float conv_eps;               // > 0: CONVERGENCE termination (|x| < conv_eps ends the level)
   int prewarped;                // 1: M.Wc / M.Ic already are the current frame warped into the keyframe view at this
                                 //    level (WARP_ORDER = warpFirst, see aligner.cu): read them pixel for pixel
 };

@@ -20,6 +20,61 @@
 
 namespace rgbid {
 
+// Reciprocal and reciprocal square root for the serial Gauss-Newton tail.  On the device a double division / rsqrt is
+// a ~40-instruction dependent chain with range fix-ups; the tail runs in one thread per frame pair while the GPU
+// waits (RGBID_TAIL_PROBE: ~11 000 clocks per launch before this), so both start from the float SFU seed and take two
+// Newton steps in double (relative error <= 2 ulp; operands outside the float range take the IEEE path).
+RGBID_HD double rcp_d(double x)
+{
+#if defined(__CUDA_ARCH__)
+  const double ax = fabs(x);
+  if (ax > 1e-30 && ax < 1e30) {
+    double y = (double)__frcp_rn((float)x);
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+  }
+#endif
+  return 1.0 / x;
+}
+
+RGBID_HD double rsqrt_d(double x)
+{
+#if defined(__CUDA_ARCH__)
+  if (x > 1e-30 && x < 1e30) {
+    double y = (double)rsqrtf((float)x);
+    double h = 0.5 * x * y;
+    double e = fma(-h, y, 0.5);
+    y = fma(y, e, y);
+    h = 0.5 * x * y;
+    e = fma(-h, y, 0.5);
+    return fma(y, e, y);
+  }
+  return rsqrt(x);  // zero / negative / NaN pivots keep their IEEE results (inf / NaN -> NaN pose -> "lost")
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+
+// sin(theta) / theta and (1 - cos(theta)) / theta^2 from t = theta^2.  Device: even Taylor series to t^7 for
+// theta < 0.5 rad (truncation < 5e-17; a Gauss-Newton increment is ~1e-3 rad), libm otherwise and on the host.
+RGBID_HD void sinc_cosc(double t, double* a, double* b)
+{
+#if defined(__CUDA_ARCH__)
+  if (t < 0.25) {
+    *a = 1.0 + t * (-1.0 / 6.0 + t * (1.0 / 120.0 + t * (-1.0 / 5040.0 + t * (1.0 / 362880.0 + t * (-1.0 / 39916800.0 +
+         t * (1.0 / 6227020800.0 - t * (1.0 / 1307674368000.0)))))));
+    *b = 0.5 + t * (-1.0 / 24.0 + t * (1.0 / 720.0 + t * (-1.0 / 40320.0 + t * (1.0 / 3628800.0 + t * (-1.0 / 479001600.0 +
+         t * (1.0 / 87178291200.0 - t * (1.0 / 20922789888000.0)))))));
+    return;
+  }
+#endif
+  const double theta = sqrt(t);
+  *a = sin(theta) / theta;
+  *b = (1.0 - cos(theta)) / (theta * theta);
+}
+
 RGBID_HD void mat3_mul(const double* A, const double* B, double* C)
 {
   double T[9];
@@ -52,7 +107,7 @@ RGBID_HD void mat3_transpose(const double* A, double* At)
 RGBID_HD void mat3_inverse(const double* M, double* Mi)
 {
   double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
-  double id = 1.0 / (M[0] * c00 + M[1] * c01 + M[2] * c02);
+  double id = rcp_d(M[0] * c00 + M[1] * c01 + M[2] * c02);
   double T[9];
   T[0] = c00 * id; T[1] = (M[2] * M[7] - M[1] * M[8]) * id; T[2] = (M[1] * M[5] - M[2] * M[4]) * id;
   T[3] = c01 * id; T[4] = (M[0] * M[8] - M[2] * M[6]) * id; T[5] = (M[2] * M[3] - M[0] * M[5]) * id;
@@ -99,12 +154,12 @@ RGBID_HD void skew3(const double* w, double* S)
 // expMapRot, src/util_funcs.cpp:125-148 (small-angle switch at 1e-5)
 RGBID_HD void exp_map_rot(const double* omega, double* R)
 {
-  double theta = sqrt(omega[0] * omega[0] + omega[1] * omega[1] + omega[2] * omega[2]);
+  const double theta2 = omega[0] * omega[0] + omega[1] * omega[1] + omega[2] * omega[2];
   double O[9], O2[9], M[9], a, b;
   skew3(omega, O);
   mat3_mul(O, O, O2);
-  if (theta < 0.00001) { a = 1.0; b = 0.5; }
-  else { a = sin(theta) / theta; b = (1.0 - cos(theta)) / (theta * theta); }
+  if (theta2 < 0.00001 * 0.00001) { a = 1.0; b = 0.5; }
+  else sinc_cosc(theta2, &a, &b);
   RGBID_UNROLL
   for (int i = 0; i < 9; ++i) M[i] = ((i % 4 == 0) ? 1.0 : 0.0) + a * O[i] + b * O2[i];
   force_orthogonal(M, R);
@@ -188,11 +243,7 @@ RGBID_HD void llt_solve6(const double* A, const double* b, double* x)
     double d = A[j * 6 + j];
     RGBID_UNROLL
     for (int k = 0; k < j; ++k) d -= L[j * 6 + k] * L[j * 6 + k];
-#if defined(__CUDA_ARCH__)
-    const double r = rsqrt(d);
-#else
-    const double r = 1.0 / sqrt(d);
-#endif
+    const double r = rsqrt_d(d);
     inv[j] = r;
     L[j * 6 + j] = d * r;
     RGBID_UNROLL
@@ -220,6 +271,40 @@ RGBID_HD void llt_solve6(const double* A, const double* b, double* x)
   }
 }
 
+// The same solve straight from the 27 packed sums [A00..A05,b0, A11..A15,b1, ...]: right-looking Cholesky on the
+// augmented upper triangle [A | b] in place (27 + 6 doubles live instead of 36 + 36 + 12: the Gauss-Newton tail is one
+// thread at the kernel's register limit, and the unpacked form spilled to local memory), trailing updates independent
+// of each other (instruction-level parallelism for the single thread).  x = A^-1 b as A.llt().solve(b).
+RGBID_HD void llt_solve_packed(const double* s27, double* x)
+{
+  double u[6][7], inv[6];
+  {
+    int shift = 0;
+    RGBID_UNROLL
+    for (int i = 0; i < 6; ++i)
+      RGBID_UNROLL
+      for (int j = i; j < 7; ++j) u[i][j] = s27[shift++];
+  }
+  RGBID_UNROLL
+  for (int k = 0; k < 6; ++k) {
+    const double r = rsqrt_d(u[k][k]);
+    inv[k] = r;
+    RGBID_UNROLL
+    for (int j = k; j < 7; ++j) u[k][j] *= r;  // row k of U = L^T, and y[k] in column 6
+    RGBID_UNROLL
+    for (int i = k + 1; i < 6; ++i)
+      RGBID_UNROLL
+      for (int j = i; j < 7; ++j) u[i][j] -= u[k][i] * u[k][j];
+  }
+  RGBID_UNROLL
+  for (int i = 5; i >= 0; --i) {
+    double s = u[i][6];
+    RGBID_UNROLL
+    for (int k = i + 1; k < 6; ++k) s -= u[i][k] * x[k];
+    x[i] = s * inv[i];
+  }
+}
+
 // 6x6 inverse by Gauss-Jordan with partial pivoting (covariance = A^-1, src/visodo.cpp:1409).
 RGBID_HD bool inverse6(const double* A, double* Ai)
 {
@@ -235,7 +320,7 @@ RGBID_HD bool inverse6(const double* A, double* Ai)
     for (int r = c + 1; r < 6; ++r) if (fabs(M[r][c]) > fabs(M[p][c])) p = r;
     if (M[p][c] == 0.0) return false;
     if (p != c) for (int j = 0; j < 12; ++j) { double t = M[c][j]; M[c][j] = M[p][j]; M[p][j] = t; }
-    double ip = 1.0 / M[c][c];
+    double ip = rcp_d(M[c][c]);
     RGBID_UNROLL
     for (int j = 0; j < 12; ++j) M[c][j] *= ip;
     RGBID_UNROLL
@@ -267,6 +352,39 @@ RGBID_HD bool gn_update(const double* x, double* R, double* t)
   RGBID_UNROLL
   for (int k = 0; k < 3; ++k) nt += t[k] * t[k];
   return (nr != nr) || (nt != nt);
+}
+
+// The same update for the device tail, as few dependent instructions as the algebra allows (the tail is one thread per
+// frame pair at the end of every launch): R_inc = exp(-[w]x) = I - a [w]x + b [w]x^2 directly instead of
+// inverse(orthogonalise(exp([w]x))), one Newton-Schulz step X (3 I - X^T X) / 2 for the polar factor (Rodrigues'
+// formula is orthogonal to rounding, so one quadratically convergent step is exact to double precision; the
+// reference runs an SVD), no division.  Differs from gn_update by rounding only (~1e-16).
+RGBID_HD bool gn_update_lean(const double* x, double* R, double* t)
+{
+  const double wx = x[3], wy = x[4], wz = x[5];
+  const double xx = wx * wx, yy = wy * wy, zz = wz * wz;
+  const double theta2 = xx + yy + zz;
+  double a, b;
+  if (theta2 < 0.00001 * 0.00001) { a = 1.0; b = 0.5; }
+  else sinc_cosc(theta2, &a, &b);
+  // O = [w]x, O^2 = w w^T - theta^2 I ; X = I - a O + b O^2
+  const double bxy = b * wx * wy, bxz = b * wx * wz, byz = b * wy * wz;
+  double X[9] = {1.0 - b * (yy + zz), bxy + a * wz, bxz - a * wy,
+                 bxy - a * wz, 1.0 - b * (xx + zz), byz + a * wx,
+                 bxz + a * wy, byz - a * wx, 1.0 - b * (xx + yy)};
+  // E = X^T X (symmetric), Rinc = X (3 I - E) / 2
+  const double e00 = X[0] * X[0] + X[3] * X[3] + X[6] * X[6], e01 = X[0] * X[1] + X[3] * X[4] + X[6] * X[7];
+  const double e02 = X[0] * X[2] + X[3] * X[5] + X[6] * X[8], e11 = X[1] * X[1] + X[4] * X[4] + X[7] * X[7];
+  const double e12 = X[1] * X[2] + X[4] * X[5] + X[7] * X[8], e22 = X[2] * X[2] + X[5] * X[5] + X[8] * X[8];
+  const double F[9] = {1.5 - 0.5 * e00, -0.5 * e01, -0.5 * e02, -0.5 * e01, 1.5 - 0.5 * e11, -0.5 * e12,
+                       -0.5 * e02, -0.5 * e12, 1.5 - 0.5 * e22};
+  double Rinc[9];
+  mat3_mul(X, F, Rinc);
+  const double d[3] = {t[0] - x[0], t[1] - x[1], t[2] - x[2]};  // t <- Rinc t - Rinc x_trans
+  mat3_vec(Rinc, d, t);
+  mat3_mul(Rinc, R, R);
+  const double chk = ((R[0] + R[1]) + (R[2] + R[3])) + ((R[4] + R[5]) + (R[6] + R[7])) + ((R[8] + t[0]) + (t[1] + t[2]));
+  return (chk != chk) || (fabs(chk) > 1e300);
 }
 
 // K R K^-1 and K t in float (Eigen float products of src/visodo.cpp:1110-1114, :1496-1500).

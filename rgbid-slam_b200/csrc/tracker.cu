@@ -117,7 +117,7 @@ struct rgbid_tracker {
   uint8_t* d_colors; size_t colors_sstride;
   Proj* d_proj; Proj* h_proj;              // [4][batch]: odo cur->KF, odo KF->cur, integr cur->KF, integr KF->cur
   unsigned int* d_counts; unsigned int* h_counts;  // [batch][8]
-  int* d_flags; int* h_flags;              // [3][batch]: new odo KF, new integration KF, fuse
+  int* d_flags; int* h_flags;              // [4][batch]: new odo KF, new integration KF, fuse, overlap mask refresh
   // custom calibration (rgbid_tracker_set_custom_calibration): parameters, projective matrices, one stream of scratch
   bool custom_on;
   rgbid_custom_calibration custom;
@@ -132,6 +132,7 @@ struct rgbid_tracker {
   char* d_prefetch[2];                     // [batch] depth, then [batch] rgb (same layout as the aligner's raw staging)
   const void* pf_depth[2]; const void* pf_rgb[2]; bool pf_valid[2]; int pf_next;
   long long pf_issued_at[2], track_calls;  // a prefetched frame is good for the current or the next track call only
+  cudaEvent_t ev_track_done; bool ev_track_done_valid;  // end of the device work queued by the last track call
 };
 
 namespace {
@@ -229,6 +230,7 @@ int rgbid_tracker_create(rgbid_ctx* ctx, const rgbid_tracker_config* cfg, rgbid_
   t->h_counts = nullptr; t->d_flags = nullptr; t->h_flags = nullptr;
   t->custom_on = false; t->d_custom = nullptr; t->d_canvas = nullptr;
   t->sink = nullptr; t->sink_user = nullptr; t->h_handoff = nullptr; t->handoff_bytes = 0;
+  t->ev_track_done = nullptr; t->ev_track_done_valid = false;
   t->copy_stream = nullptr; t->pf_next = 0; t->track_calls = 0; t->pf_issued_at[0] = t->pf_issued_at[1] = 0;
   for (int i = 0; i < 2; ++i) { t->ev_copy[i] = nullptr; t->d_prefetch[i] = nullptr; t->pf_depth[i] = t->pf_rgb[i] = nullptr; t->pf_valid[i] = false; }
   int rc = rgbid_aligner_create(ctx, &t->cfg.align, &t->al);
@@ -255,8 +257,8 @@ int rgbid_tracker_create(rgbid_ctx* ctx, const rgbid_tracker_config* cfg, rgbid_
   if (e == cudaSuccess) e = cudaMallocHost(&t->h_proj, sizeof(Proj) * 4 * B);
   if (e == cudaSuccess) e = cudaMalloc(&t->d_counts, sizeof(unsigned int) * 8 * B);
   if (e == cudaSuccess) e = cudaMallocHost(&t->h_counts, sizeof(unsigned int) * 8 * B);
-  if (e == cudaSuccess) e = cudaMalloc(&t->d_flags, sizeof(int) * 3 * B);
-  if (e == cudaSuccess) e = cudaMallocHost(&t->h_flags, sizeof(int) * 3 * B);
+  if (e == cudaSuccess) e = cudaMalloc(&t->d_flags, sizeof(int) * 4 * B);
+  if (e == cudaSuccess) e = cudaMallocHost(&t->h_flags, sizeof(int) * 4 * B);
   if (e != cudaSuccess) { rgbid_tracker_destroy(t); return RGBID_ERR_CUDA_BASE + (int)e; }
   t->st.resize(B);
   rc = rgbid_tracker_reset(t);
@@ -272,6 +274,7 @@ int rgbid_tracker_destroy(rgbid_tracker* t)
   if (t->al) rgbid_aligner_destroy(t->al);
   if (t->copy_stream) { cudaStreamSynchronize(t->copy_stream); cudaStreamDestroy(t->copy_stream); }
   for (int i = 0; i < 2; ++i) { if (t->ev_copy[i]) cudaEventDestroy(t->ev_copy[i]); cudaFree(t->d_prefetch[i]); }
+  if (t->ev_track_done_valid) cudaEventDestroy(t->ev_track_done);
   cudaFree(t->d_arena); cudaFree(t->d_proj); cudaFree(t->d_counts); cudaFree(t->d_flags);
   cudaFree(t->d_custom);
   if (t->h_handoff) cudaFreeHost(t->h_handoff);
@@ -294,6 +297,10 @@ int rgbid_tracker_reset(rgbid_tracker* t)
     s.last_integrKF_index = 0;
     s.lost = false; s.global_time = 0;
   }
+  // a frame prefetched before the reset must not be matched (by pointer) by the first track call after it
+  if (t->copy_stream) RGBID_CUDA_TRY(cudaStreamSynchronize(t->copy_stream));
+  for (int i = 0; i < 2; ++i) { t->pf_valid[i] = false; t->pf_depth[i] = nullptr; t->pf_rgb[i] = nullptr; t->pf_issued_at[i] = 0; }
+  t->track_calls = 0;
   const rgbid_align_config& c = t->al->cfg;
   cudaStream_t s = t->ctx->stream;
   size_t fl = (size_t)(t->d_mask - (uint8_t*)t->d_arena);
@@ -434,8 +441,10 @@ int rgbid_tracker_prefetch(rgbid_tracker* t, const uint16_t* depth, const uint8_
       RGBID_CUDA_TRY(cudaMalloc(&t->d_prefetch[i], (raw_depth + raw_rgb) * B));
     }
   }
-  // this staging buffer was last read by the ingest kernel of the frame before the current one, and every track call
-  // ends with a stream synchronisation, so it is free here
+  // This staging buffer was last read by the frame before the current one: by its ingest kernel and, if that frame
+  // became an integration keyframe, by the colour copy queued at the very end of track_core -- after the last stream
+  // synchronisation of that call.  The upload therefore waits for the event track_core records when it returns.
+  if (t->ev_track_done_valid) RGBID_CUDA_TRY(cudaStreamWaitEvent(t->copy_stream, t->ev_track_done, 0));
   const int slot = t->pf_next;
   t->pf_next ^= 1;
   char* dd = t->d_prefetch[slot];
@@ -569,8 +578,10 @@ static int track_core(rgbid_tracker* t, const uint16_t* depth, const uint8_t* rg
 
   // ---- estimateVisualOdometry (src/visodo.cpp:944-1479) -------------------------------------------------------
   std::vector<double> prevR(9 * B), prevt(3 * B), prevcov(36 * B);
+  std::vector<char> was_lost(B);
   for (int b = 0; b < B; ++b) {
     StreamState& S = t->st[b];
+    was_lost[b] = S.lost ? 1 : 0;
     memcpy(&prevR[9 * b], S.dR, sizeof(double) * 9);
     memcpy(&prevt[3 * b], S.dt, sizeof(double) * 3);
     memcpy(&prevcov[36 * b], S.dcov, sizeof(double) * 36);
@@ -603,7 +614,9 @@ static int track_core(rgbid_tracker* t, const uint16_t* depth, const uint8_t* rg
     const GnState& g = al->h_states[b];
     rgbid_frame_result& r = results[b];
     memset(&r, 0, sizeof(r));
-    r.frame_index = t->frame_index;
+    // the reference's global_time_: frames of this stream that entered the trajectory (a frame that fails while the
+    // stream is already lost does not, src/visodo.cpp:2111-2116)
+    r.frame_index = S.global_time;
     r.status = g.status;
     r.chi_square = g.chi_square; r.chi_test = g.chi_test; r.ndof = g.ndof;
     const bool ok = (g.status == RGBID_OK);
@@ -653,7 +666,7 @@ static int track_core(rgbid_tracker* t, const uint16_t* depth, const uint8_t* rg
   RGBID_CUDA_TRY(cudaStreamSynchronize(s));
 
   // ---- keyframe decisions (:2175-2215) ----------------------------------------------------------------------------
-  bool any_odo = false, any_int = false, any_fuse = false;
+  bool any_odo = false, any_int = false, any_fuse = false, any_mask = false;
   for (int b = 0; b < B; ++b) {
     StreamState& S = t->st[b];
     rgbid_frame_result& r = results[b];
@@ -662,7 +675,11 @@ static int track_core(rgbid_tracker* t, const uint16_t* depth, const uint8_t* rg
     float vis_odo = fminf(ratio(cnt[2], cnt[3]), ratio(cnt[0], cnt[1]));
     float vis_int = fminf(ratio(cnt[6], cnt[7]), ratio(cnt[4], cnt[5]));
     r.visibility_odo = vis_odo; r.visibility_integr = vis_int;
-    int new_odo = 0, new_int = 0, fuse = 0;
+    int new_odo = 0, new_int = 0, fuse = 0, mask = 0;
+    // `again`: the alignment failed while the stream was already lost (src/visodo.cpp:2099-2116) -- both keyframes are
+    // re-saved from the current frame and nothing else happens: no keyframe reset, no keyframe or constraint for the
+    // back end, global_time_ stands still
+    const bool again = (r.status != RGBID_OK) && was_lost[b];
     if (r.status != RGBID_OK) {
       // lost: both keyframes are re-initialised from the current frame (:2066-2097, :2111-2116)
       S.lost = true;
@@ -672,20 +689,22 @@ static int track_core(rgbid_tracker* t, const uint16_t* depth, const uint8_t* rg
       new_odo = (S.odoKF_count >= t->cfg.max_odo_kf_count) || (vis_odo < t->cfg.visratio_odo);
       new_int = (S.integrKF_count >= t->cfg.max_integr_kf_count) || (vis_int < t->cfg.visratio_integr);
       fuse = !new_int;
+      mask = new_int;  // computeOverlapping runs on the covisibility path only (:2199), never for a lost frame
     }
     memcpy(r.R, S.R_est, sizeof(double) * 9); memcpy(r.t, S.t_est, sizeof(double) * 3);
     memcpy(r.dR, S.dR, sizeof(double) * 9); memcpy(r.dt, S.dt, sizeof(double) * 3);
     memcpy(r.cov, S.dcov, sizeof(double) * 36);
     r.new_odo_keyframe = new_odo; r.new_integr_keyframe = new_int;
+    r.lost_again = again ? 1 : 0;
     if (r.status == RGBID_OK) {
       // odometry-keyframe constraint (KF, i) -> sequential constraint (i - 1, i) (:2126-2156)
       relative_constraint(&prevR[9 * b], &prevt[3 * b], &prevcov[36 * b], S.dR, S.dt, S.dcov, r.seq_R, r.seq_t, r.seq_cov);
     } else {
-      // dummy constraint: zero motion, very high covariance (:2068-2071)
+      // dummy constraint: zero motion, very high covariance (:2068-2071); not pushed when lost_again
       set_identity(r.seq_R, r.seq_t);
       for (int i = 0; i < 36; ++i) r.seq_cov[i] = (i % 7 == 0) ? 100.0 : 0.0;
     }
-    if (new_odo) {
+    if (new_odo && !again) {
       // resetOdometryKeyframe (:1541-1575)
       chain_compose(S);
       S.odoKF_count = 0;
@@ -693,7 +712,7 @@ static int track_core(rgbid_tracker* t, const uint16_t* depth, const uint8_t* rg
       set_identity(S.dR, S.dt);
       memset(S.dcov, 0, sizeof(S.dcov));
     }
-    if (new_int) {
+    if (new_int && !again) {
       // resetIntegrationKeyframe (:1577-1672): close the chain, hand the outgoing keyframe over with its SEQ_KF
       // constraint, switch to the new keyframe
       chain_compose(S);
@@ -711,20 +730,23 @@ static int track_core(rgbid_tracker* t, const uint16_t* depth, const uint8_t* rg
       set_identity(S.o2i_next_R, S.o2i_next_t);
       memset(S.o2i_next_cov, 0, sizeof(S.o2i_next_cov));
     }
+    t->h_flags[3 * B + b] = mask;
+    any_mask |= (mask != 0);
+    if (!again) S.global_time++;
     t->h_flags[0 * B + b] = new_odo; t->h_flags[1 * B + b] = new_int; t->h_flags[2 * B + b] = fuse;
     any_odo |= (new_odo != 0); any_int |= (new_int != 0); any_fuse |= (fuse != 0);
-    S.global_time++;
   }
-  upload_control(L, t->d_flags, t->h_flags, sizeof(int) * 3 * B);
+  upload_control(L, t->d_flags, t->h_flags, sizeof(int) * 4 * B);
   if (any_odo) {
     // saveCurrentImagesAsOdoKeyframes (:826-878), predicated per stream
     aligner_copy_current_to_keyframe(al, 0, B, t->d_flags + 0 * B);
     aligner_keyframe_derivatives(al, 0, B, t->d_flags + 0 * B, false);
   }
-  if (any_int) {
+  if (any_mask)
     // computeOverlapping (:1517-1539): mask of the new keyframe (current frame) against the old raw keyframe
     launch_visibility(L, Wcur, t->intWraw, t->d_proj + 2 * B, dummy, t->d_counts, 4, 8, t->d_mask, t->mask_pitch,
-                      t->mask_sstride, B, t->d_flags + 1 * B);
+                      t->mask_sstride, B, t->d_flags + 3 * B);
+  if (any_int) {
     save_integration_keyframes(t, t->d_flags + 1 * B);
     for (int b = 0; b < B; ++b)
       if (t->h_flags[1 * B + b])
@@ -737,6 +759,12 @@ static int track_core(rgbid_tracker* t, const uint16_t* depth, const uint8_t* rg
   }
   refresh_integration_maps(t);
   t->frame_index++;
+  // rgbid_tracker_prefetch orders its next upload into the staging buffers after everything queued above
+  if (!t->ev_track_done_valid) {
+    RGBID_CUDA_TRY(cudaEventCreateWithFlags(&t->ev_track_done, cudaEventDisableTiming));
+    t->ev_track_done_valid = true;
+  }
+  RGBID_CUDA_TRY(cudaEventRecord(t->ev_track_done, s));
   return check_last(ctx);
 }
 

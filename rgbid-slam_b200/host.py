@@ -126,6 +126,23 @@ class Context:
         self._leave()
         return gx, gy
 
+    def copy_image(self, src, dst=None):
+        """copyImage (src/internal.h:260): pitched device-to-device copy; dst may be a row-pitched view."""
+        rows, cols = src.shape
+        out = self.empty(rows, cols) if dst is None else dst
+        self._enter()
+        capi.check(self.lib.rgbid_copy_image(self.h, src.data_ptr(), _pitch(src), out.data_ptr(), _pitch(out), rows, cols), "copy_image")
+        self._leave()
+        return out
+
+    def fill_image(self, dst, value):
+        """initialiseDeviceMemory2D<float> / initialiseWeightKeyframe (src/internal.h:271-274)."""
+        rows, cols = dst.shape
+        self._enter()
+        capi.check(self.lib.rgbid_fill_image(self.h, dst.data_ptr(), _pitch(dst), rows, cols, float(value)), "fill_image")
+        self._leave()
+        return dst
+
     def bilateral_filter(self, src, sigma):
         rows, cols = src.shape
         out = self.empty(rows, cols)
@@ -322,7 +339,8 @@ class Context:
 
 def make_align_config(rows, cols, levels, mode, batch=1, fx=525.0, fy=525.0, cx=319.5, cy=239.5, iterations=None,
                       finest_level=0, mestimator=capi.STUDENT, weighting=capi.INDEPENDENT,
-                      sigma_estimator=capi.SIGMA_PDF, nsamples=None, factor_depth=1.0, warp_first=0):
+                      sigma_estimator=capi.SIGMA_PDF, nsamples=None, factor_depth=1.0, warp_first=0,
+                      termination=capi.TERM_ALL_ITERS, conv_eps=0.0):
     cfg = capi.AlignConfig()
     cfg.rows, cfg.cols, cfg.levels, cfg.finest_level = rows, cols, levels, finest_level
     its = iterations if iterations is not None else default_iterations(levels, mode)
@@ -335,6 +353,7 @@ def make_align_config(rows, cols, levels, mode, batch=1, fx=525.0, fy=525.0, cx=
     cfg.factor_depth = factor_depth
     cfg.with_fusion = 0
     cfg.warp_first = int(warp_first)  # tracker: WARP_ORDER = warpFirst (src/visodo.cpp:1078-1105); 0 = pyrFirst
+    cfg.termination, cfg.conv_eps = int(termination), float(conv_eps)  # include/rgbid_b200.h RGBID_TERM_*
     return cfg
 
 
@@ -422,6 +441,19 @@ class Aligner:
         stats = np.zeros((B, 3), dtype=np.float32)
         self.lib.rgbid_aligner_frame_stats(self.h, _fp(stats))
         out["stats"] = stats
+        done = np.zeros((B, capi.MAX_LEVELS), dtype=np.int32)
+        capi.check(self.lib.rgbid_aligner_iterations_done(self.h, done.ctypes.data_as(capi.c_int_p)), "iterations_done")
+        out["iterations_done"] = done
+        if want_trace and self.cfg.termination != capi.TERM_ALL_ITERS:
+            # a level that ended early leaves the slots of its remaining iterations untouched: keep the executed ones
+            its = [self.cfg.iterations[l] for l in range(self.cfg.levels)]
+            for b in range(B):
+                keep, k = [], 0
+                for l in range(self.cfg.levels - 1, self.cfg.finest_level - 1, -1):
+                    keep += list(range(k, k + int(done[b, l])))
+                    k += its[l]
+                keep.append(self.niters)  # covariance pass
+                out["trace"][b] = [out["trace"][b][i] for i in keep]
         return out
 
     def enqueue(self, R, t):

@@ -57,8 +57,6 @@ class VisodoTracker {
         Nsamples_(Nsamples), trk_(nullptr), lost_(false), global_time_(0)
   {
     if (optim_dim != 6) throw std::invalid_argument("only the 6-DoF optimisation of the reference is implemented");
-    if (termination != device::ALL_ITERS)
-      std::cerr << "VisodoTracker: CHI_SQUARED early termination is not implemented; using ALL_ITERS (the default)" << std::endl;
     setRGBIntrinsics(device::FOCAL_LENGTH, device::FOCAL_LENGTH, device::CENTER_X, device::CENTER_Y);
     factor_depth_ = 1.f;
     compute_deltat_flag_ = false;
@@ -175,6 +173,14 @@ class VisodoTracker {
     if (rc != RGBID_OK) throw std::runtime_error(std::string("rgbid_tracker_track: ") + rgbid_status_string(rc));
     last_ = r;
     lost_ = (r.status != RGBID_OK);
+    const float ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    kf_time_accum_ += 1e-3f * ms;
+    if (r.lost_again) {
+      // failed again while lost (src/visodo.cpp:2111-2116): the keyframes were re-saved from this frame; no pose, no
+      // constraint, global_time_ stands still
+      vis_odo_times_.push_back(ms);
+      return false;
+    }
     if (global_time_ > 0)  // SEQ_ODO constraint (or the dummy one when lost), src/visodo.cpp:2068-2071, 2147-2154
       keyframe_buffers_.constraints_.push_back(PoseConstraint(global_time_ - 1, global_time_, PoseConstraint::SEQ_ODO, r.seq_R,
                                                               r.seq_t, 1.f, r.seq_cov));
@@ -184,9 +190,7 @@ class VisodoTracker {
     poses_.push_back(p);
     setSharedCameraPose(p);
     // wall time of the frame in milliseconds (pcl::ScopeTime t1 of the reference, src/visodo.cpp:2231; 0 for frame 0, :542)
-    const float ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     vis_odo_times_.push_back(global_time_ == 0 ? 0.f : ms);
-    kf_time_accum_ += 1e-3f * ms;
     const bool first = (global_time_ == 0);
     ++global_time_;
     return !first && !lost_;
@@ -304,6 +308,8 @@ class VisodoTracker {
     c.align.fx = fx_; c.align.fy = fy_; c.align.cx = cx_; c.align.cy = cy_;
     c.align.factor_depth = factor_depth_;
     c.align.warp_first = (warping_ == device::WARP_FIRST) ? 1 : 0;  // src/visodo.cpp:1078
+    // TERMINATION_CRITERIA, src/internal.h:112 / src/visodo.cpp:1134-1164
+    c.align.termination = (termination_ == device::CHI_SQUARED) ? RGBID_TERM_CHI_SQUARED : RGBID_TERM_ALL_ITERS;
     c.motion_model = motion_model_;
     c.visratio_odo = visibility_ratio_odo_threshold_; c.visratio_integr = visibility_ratio_integr_threshold_;
     c.max_odo_kf_count = max_odoKF_count_; c.max_integr_kf_count = max_integrKF_count_;
