@@ -120,6 +120,7 @@ static void record_chain(rgbid_aligner* al, LaunchCtx L, int first, int count, c
 {
   bool signalled = (after_first_launch == nullptr);
   const rgbid_align_config& c = al->cfg;
+  L.pdl = al->use_pdl;  // scale and system kernels overlap their prologues with the predecessor's tail (kernels.cuh)
   const bool tracker = (c.mode == RGBID_MODE_TRACKER);
   const bool estimate_scale = tracker ? (c.sigma_estimator == RGBID_SIGMA_PDF) : true;
   const bool warp_first = tracker && c.warp_first;  // KeyframeAlign has no such option (src/keyframe_align.cpp:178-350)
@@ -338,6 +339,8 @@ int rgbid_aligner_create(rgbid_ctx* ctx, const rgbid_align_config* cfg, rgbid_al
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&al->ev_join, cudaEventDisableTiming);
     if (e != cudaSuccess) { rgbid_aligner_destroy(al); return RGBID_ERR_CUDA_BASE + (int)e; }
   }
+  const char* no_pdl = getenv("RGBID_NO_PDL");
+  al->use_pdl = !(no_pdl && no_pdl[0] == '1');
   const char* no_graph = getenv("RGBID_NO_GRAPH");
   al->use_graph = !(no_graph && no_graph[0] == '1') && (ctx->stream != (cudaStream_t)0);
   al->image_filtering = RGBID_NO_FILTERS;
@@ -507,11 +510,13 @@ static int time_kernel(rgbid_aligner* al, int level, int reps, float* ms_per_lau
   RGBID_CUDA_TRY(cudaEventCreate(&e0));
   RGBID_CUDA_TRY(cudaEventCreate(&e1));
   GnParams P = base_params(al, level);
-  P.iter_index = -1; P.update_pose = 0; P.compute_cov = 0;
+  // the shipped launch, tail included (final sum, 6x6 solve, pose update, projection refresh), repeatable: see dry_tail
+  P.iter_index = -1; P.update_pose = 1; P.dry_tail = 1; P.compute_cov = 0; P.next_level = level;
   const bool tracker = (al->cfg.mode == RGBID_MODE_TRACKER);
   P.use_scale = (tracker && al->cfg.sigma_estimator != RGBID_SIGMA_PDF) ? 0 : 1;
   GnLevelMaps M = level_maps(al, level, false);
   LaunchCtx L = al->ctx->L();
+  L.pdl = al->use_pdl;
   auto go = [&]() {
     if (scale) launch_gn_scale(L, M, P, al->d_states, al->d_scales);
     else launch_gn_build(L, M, P, al->d_states, al->d_scales, al->d_partials, 32, al->d_counters, nullptr);

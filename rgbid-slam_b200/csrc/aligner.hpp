@@ -47,6 +47,7 @@ struct rgbid_aligner {
   int* h_active;
   // CUDA graph of the whole schedule
   bool use_graph;
+  bool use_pdl;  // programmatic dependent launch between the Gauss-Newton kernels (RGBID_NO_PDL=1 disables)
   cudaGraphExec_t gn_exec;
   long long gn_graph_launches;
   int image_filtering;

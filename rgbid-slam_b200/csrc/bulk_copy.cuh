@@ -49,6 +49,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
       : "memory");
 }
 
+// programmatic dependent launch (no-ops when the kernel was launched without the attribute): wait = every prerequisite
+// grid has completed and its writes are visible; launch_dependents = this CTA no longer holds back the launch of the
+// next kernel's CTAs (they start once every CTA of this grid has said so or exited)
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // true in exactly one lane of a converged warp (the compiler then knows a single thread issues the bulk copies)
 __device__ __forceinline__ bool elect_one()
 {

@@ -254,6 +254,12 @@ __device__ __noinline__ void gn_tail_update(GnState& st, const double* tot, cons
   }
   llt_solve_packed(tot, x);
   bool bad = gn_update_lean(x, R, t);
+  if (P.dry_tail) {
+    // everything above and the projection refresh below are executed, but the pose is not committed and the
+    // projection goes to the slot of ANOTHER level than the one being timed (rewritten by gn_init before any real run)
+    refresh_proj(st, R, t, P.levels, P.fx0, P.fy0, P.cx0, P.cy0, (P.level + 1) % P.levels);
+    return;
+  }
   if (bad) {
     // lost: keep the previous pose, covariance 100 I (src/visodo.cpp:1265-1274)
     st.status = RGBID_ERR_NAN;
@@ -375,6 +381,7 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
   constexpr int NACC = CHI ? kAccChi : kAcc;
   const int b = blockIdx.y + P.first;
   GnState& st = states[b];
+  grid_dep_wait();
   if (pair_skipped(st, P)) return;
   __shared__ BuildShared sh;
   if (threadIdx.x < 12) {
@@ -444,6 +451,7 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
     for (int k = 0; k < VEC; ++k)
       accumulate_pixel<CHI>(acc, x0 + k, y, w0[k], i0[k], gwx[k], gwy[k], gix[k], giy[k], w1[k], i1[k], pp);
   }
+  grid_dep_launch();
 
   __shared__ float scratch[kBuildWarps][kAccChi * 32];
   if (!reduce_and_elect<NACC>(sh, acc, scratch[threadIdx.x >> 5], partials + (size_t)b * gridDim.x * partial_stride,
@@ -482,9 +490,6 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
 #endif
 #ifndef RGBID_TAIL_PROBE
 #define RGBID_TAIL_PROBE 0  // gn_build_fast_kernel: clock64 break-down of the last CTA (diagnostic build only)
-#endif
-#ifndef RGBID_SCALE_MLP
-#define RGBID_SCALE_MLP 0  // gn_scale_kernel: stage-wise sampling with explicit memory-level parallelism (see there)
 #endif
 constexpr int kChunkPx = 128;                   // one warp-chunk: 4 pixels per lane
 constexpr int kChunkBytes = kChunkPx * 4;       // per map
@@ -568,13 +573,11 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
   __shared__ __align__(8) unsigned long long bars[kBuildWarps * (kStagesW + kStagesL)];
   const int b = blockIdx.y + P.first;
   GnState& st = states[b];
-  if (pair_skipped(st, P)) return;
 #if RGBID_TAIL_PROBE
   const long long probe_t0 = clock64();
 #endif
   const int tid = threadIdx.x, lane = tid & 31;
   const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: bulk-copy operands stay in uniform registers
-  if (tid < 12) ((float*)&sh.proj)[tid] = ((const float*)&st.proj[P.level])[tid];
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < kBuildWarps * (kStagesW + kStagesL); ++i) mbar_init(smem_u32(&bars[i]), 1);
@@ -617,6 +620,8 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
     bulk_g2s(dst + 3 * kChunkBytes, gIx + off, kChunkBytes, bar);
     bulk_g2s(dst + 4 * kChunkBytes, gIy + off, kChunkBytes, bar);
   };
+  // the keyframe maps were written before this Gauss-Newton schedule started: the first bulk copies may be in flight
+  // while the previous kernel (scale estimation, or the previous iteration's solve) is still finishing
   if (elect_one()) {
 #pragma unroll
     for (int i = 0; i < kStagesW; ++i)
@@ -624,6 +629,18 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
 #pragma unroll
     for (int i = 0; i < kStagesL; ++i)
       if (i < my_n) issue_l(i);
+  }
+  grid_dep_wait();
+  // a skipped pair leaves with its bulk copies in flight: they land in this CTA's own shared memory, which stays
+  // allocated until the copies have completed
+  const bool skipped = pair_skipped(st, P);
+  if (tid < 12 && !skipped) ((float*)&sh.proj)[tid] = ((const float*)&st.proj[P.level])[tid];
+  __syncthreads();
+  if (skipped) {
+    // drain: wait for every copy this warp issued before the CTA exits
+    for (int i = 0; i < kStagesW && i < my_n; ++i) mbar_wait(barW + (uint32_t)i * 8u, 0u);
+    for (int i = 0; i < kStagesL && i < my_n; ++i) mbar_wait(barL + (uint32_t)i * 8u, 0u);
+    return;
   }
 
   // per-stream constants
@@ -888,6 +905,7 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
     iteration(i, w1a, i1a, pina, w1b, i1b, pinb);
     if (i + 1 < my_n) iteration(i + 1, w1b, i1b, pinb, w1a, i1a, pina);
   }
+  grid_dep_launch();  // the next kernel's CTAs may take the slots this grid frees while its last CTAs reduce and solve
 
   float acc[NACC];
 #if RGBID_ACC2
@@ -982,10 +1000,7 @@ __global__ void __cluster_dims__(kScaleCluster, 1, 1) __launch_bounds__(kScaleTh
   const int b = blockIdx.x / kScaleCluster + P.first;
   const int rank = (int)cluster.block_rank();
   const GnState& st = states[b];
-  if (pair_skipped(st, P)) return;  // uniform over the whole cluster
-  if (threadIdx.x < 12) ((float*)&s_proj)[threadIdx.x] = ((const float*)&st.proj[P.level])[threadIdx.x];
-  __syncthreads();
-  const Proj proj = s_proj;
+  grid_dep_launch();  // the system kernel that follows may start staging its keyframe tiles
 
   const int n = P.kept_rows * P.kept_cols;
   const int chunk = (n + kScaleCluster - 1) / kScaleCluster;
@@ -993,57 +1008,31 @@ __global__ void __cluster_dims__(kScaleCluster, 1, 1) __launch_bounds__(kScaleTh
   const int n_local = min(chunk, n - begin);
   float* samp_int = smem_samples;
   float* samp_dep = smem_samples + chunk;
+  const int s = P.sample_stride;
+  // Pose-independent part first: the keyframe values of this CTA's samples go to shared memory while the previous
+  // kernel (the last CTAs of the system kernel: final sum, 6x6 solve, pose update) is still running.
+  for (int il = threadIdx.x; il < n_local; il += kScaleThreads) {
+    const int i = begin + il;
+    const int ys = i / P.kept_cols, xs = i - ys * P.kept_cols;
+    samp_dep[il] = __ldg(M.W0.row(b, s * ys) + s * xs);
+    samp_int[il] = __ldg(M.I0.row(b, s * ys) + s * xs);
+  }
+  grid_dep_wait();
+  if (pair_skipped(st, P)) return;  // uniform over the whole cluster
+  if (threadIdx.x < 12) ((float*)&s_proj)[threadIdx.x] = ((const float*)&st.proj[P.level])[threadIdx.x];
+  __syncthreads();
+  const Proj proj = s_proj;
+
   const bool geom_is_warped = (P.mode == RGBID_MODE_TRACKER);
   CurFrame cur;
   cur.Wc = M.Wc.row(b, 0); cur.Ic = M.Ic.row(b, 0);
   cur.wpitch = M.Wc.pitch; cur.ipitch = M.Ic.pitch;
   cur.texW = TEX ? M.texW[b] : 0; cur.texI = TEX ? M.texI[b] : 0;
-  const int s = P.sample_stride;
-#if RGBID_SCALE_MLP
-  // Prepared experiment (off by default, not measured yet): the loop below runs a thread's ~5 samples one after the
-  // other, each a chain of a global load and two dependent texture fetches (SASS: no unrolling, ~2 000 clk per
-  // sample).  Here the same samples are taken stage by stage -- all loads, all inverse-depth fetches, all intensity
-  // fetches -- with the stage functions of the generic system kernel (same expressions as warp_pixel).
-  if (TEX && !P.prewarped) {
-    constexpr int U = 5;
-    for (int base = threadIdx.x; base < n_local; base += U * kScaleThreads) {
-      float w0[U], i0[U], w1[U], fetched[U];
-      int px[U], py[U];
-      WarpCoord wc[U];
-#pragma unroll
-      for (int k = 0; k < U; ++k) {
-        const int il = base + k * kScaleThreads;
-        const int i = begin + min(il, n_local - 1);
-        const int ys = i / P.kept_cols, xs = i - ys * P.kept_cols;
-        px[k] = s * xs; py[k] = s * ys;
-        w0[k] = __ldg(M.W0.row(b, py[k]) + px[k]);
-        i0[k] = __ldg(M.I0.row(b, py[k]) + px[k]);
-      }
-#pragma unroll
-      for (int k = 0; k < U; ++k) wc[k] = warp_stage1(proj, px[k], py[k], w0[k], P.cols, P.rows);
-#pragma unroll
-      for (int k = 0; k < U; ++k) fetched[k] = tex2D<float>(cur.texW, wc[k].xt, wc[k].yt);
-#pragma unroll
-      for (int k = 0; k < U; ++k)
-        w1[k] = warp_stage2(proj, px[k], py[k], w0[k], fetched[k], wc[k], P.cols, P.rows, geom_is_warped);
-#pragma unroll
-      for (int k = 0; k < U; ++k) fetched[k] = tex2D<float>(cur.texI, wc[k].xt, wc[k].yt);
-#pragma unroll
-      for (int k = 0; k < U; ++k) {
-        const int il = base + k * kScaleThreads;
-        if (il < n_local) {
-          samp_int[il] = warp_stage3(fetched[k], wc[k]) - i0[k];
-          samp_dep[il] = w1[k] - w0[k];
-        }
-      }
-    }
-  } else
-#endif
   for (int il = threadIdx.x; il < n_local; il += kScaleThreads) {
     const int i = begin + il;
     const int ys = i / P.kept_cols, xs = i - ys * P.kept_cols;
     const int x = s * xs, y = s * ys;
-    float w0 = __ldg(M.W0.row(b, y) + x), i0 = __ldg(M.I0.row(b, y) + x);
+    const float w0 = samp_dep[il], i0 = samp_int[il];  // staged above by this very thread
     float w1, i1;
     if (P.prewarped) { w1 = __ldg(M.Wc.row(b, y) + x); i1 = __ldg(M.Ic.row(b, y) + x); }  // uniform; see gn_build_kernel
     else warp_pixel<TEX>(proj, x, y, w0, cur, P.cols, P.rows, geom_is_warped, w1, i1);
@@ -1125,25 +1114,17 @@ void launch_gn_scale(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P
   const int n = P.kept_rows * P.kept_cols;
   const int chunk = (n + kScaleCluster - 1) / kScaleCluster;
   size_t smem = (size_t)2 * chunk * sizeof(float);
-  static PerDevice table, smem_limit, carve;
+  static PerDevice table, smem_limit;
   table.once([] { upload_nu_table(); });
-  // RGBID_CHAINS=2: the scale kernel of one group of streams has to share SMs with the system kernel of the other; two
-  // kernels are only co-resident on an SM under the same shared-memory carve-out
-  static const bool same_carveout = [] { const char* e = getenv("RGBID_CHAINS"); return e && e[0] == '2'; }();
-  if (same_carveout)
-    carve.once([] {
-      cudaFuncSetAttribute(gn_scale_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      cudaFuncSetAttribute(gn_scale_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    });
   if (smem > 48 * 1024)
     smem_limit.at_least(smem, [](size_t bytes) {
       cudaFuncSetAttribute(gn_scale_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
       cudaFuncSetAttribute(gn_scale_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     });
   if (M.texW != nullptr && M.texI != nullptr)
-    gn_scale_kernel<true><<<kScaleCluster * P.batch, kScaleThreads, smem, L.stream>>>(M, P, states, scales);
+    launch_kernel_pdl(gn_scale_kernel<true>, dim3(kScaleCluster * P.batch), dim3(kScaleThreads), smem, L.stream, L.pdl, M, P, states, scales);
   else
-    gn_scale_kernel<false><<<kScaleCluster * P.batch, kScaleThreads, smem, L.stream>>>(M, P, states, scales);
+    launch_kernel_pdl(gn_scale_kernel<false>, dim3(kScaleCluster * P.batch), dim3(kScaleThreads), smem, L.stream, L.pdl, M, P, states, scales);
   ++*L.launches;
 }
 
@@ -1153,9 +1134,9 @@ static void launch_gn_build_t(const LaunchCtx& L, dim3 grid, bool tex, const GnL
                               unsigned int* counters, rgbid_iter_trace* trace)
 {
   if (tex)
-    gn_build_kernel<VEC, CHI, true><<<grid, kBuildThreads, 0, L.stream>>>(M, P, states, scales, partials, partial_stride, counters, trace);
+    launch_kernel_pdl(gn_build_kernel<VEC, CHI, true>, grid, dim3(kBuildThreads), 0, L.stream, L.pdl, M, P, states, scales, partials, partial_stride, counters, trace);
   else
-    gn_build_kernel<VEC, CHI, false><<<grid, kBuildThreads, 0, L.stream>>>(M, P, states, scales, partials, partial_stride, counters, trace);
+    launch_kernel_pdl(gn_build_kernel<VEC, CHI, false>, grid, dim3(kBuildThreads), 0, L.stream, L.pdl, M, P, states, scales, partials, partial_stride, counters, trace);
 }
 
 void launch_gn_build(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P, GnState* states,
@@ -1196,20 +1177,11 @@ void launch_gn_build(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P
       cudaFuncSetAttribute(gn_build_fast_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
       cudaFuncSetAttribute(gn_build_fast_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
       cudaFuncSetAttribute(gn_build_fast_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
-      const char* e = getenv("RGBID_CHAINS");
-      if (e && e[0] == '2') {
-        cudaFuncSetAttribute(gn_build_fast_kernel<true, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(gn_build_fast_kernel<true, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(gn_build_fast_kernel<true, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(gn_build_fast_kernel<false, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(gn_build_fast_kernel<false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(gn_build_fast_kernel<false, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      }
     });
     const bool tracker = (P.mode == RGBID_MODE_TRACKER);
     const int chim = !chi ? 0 : (P.chi_mestimator == RGBID_STUDENT ? 2 : 1);
 #define RGBID_FAST_LAUNCH(T, C) \
-    gn_build_fast_kernel<T, C><<<grid, kBuildThreads, kFastSmemBytes, L.stream>>>(M, P, G, states, scales, partials, partial_stride, counters, trace)
+    launch_kernel_pdl(gn_build_fast_kernel<T, C>, grid, dim3(kBuildThreads), kFastSmemBytes, L.stream, L.pdl, M, P, G, states, scales, partials, partial_stride, counters, trace)
     if (tracker) { if (chim == 0) RGBID_FAST_LAUNCH(true, 0); else if (chim == 1) RGBID_FAST_LAUNCH(true, 1); else RGBID_FAST_LAUNCH(true, 2); }
     else { if (chim == 0) RGBID_FAST_LAUNCH(false, 0); else if (chim == 1) RGBID_FAST_LAUNCH(false, 1); else RGBID_FAST_LAUNCH(false, 2); }
 #undef RGBID_FAST_LAUNCH

@@ -10,7 +10,26 @@ struct LaunchCtx {
   cudaStream_t stream;
   long long* launches;
   int num_sms;
+  // programmatic dependent launch: the Gauss-Newton kernels are launched with the stream-serialisation attribute, so
+  // the next kernel's CTAs become resident (and run their pose-independent prologue) while the previous one is in
+  // its serial tail; every such kernel executes griddepcontrol.wait before it reads what a predecessor wrote
+  bool pdl = false;
 };
+
+// Launch with (or without) cudaLaunchAttributeProgrammaticStreamSerialization; works under stream capture (the graph
+// gets programmatic dependency edges).
+template <class... KArgs, class... Args>
+inline cudaError_t launch_kernel_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     bool pdl, Args&&... args)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // One-time set-up that lives in a device's context (constant tables, kernel attributes) has to happen once per DEVICE
 // the process uses, not once per process, and two host threads may get here together (the tracker and the keyframe
@@ -172,6 +191,8 @@ struct GnParams {
   int termination;              // cfg.termination
   int chi_test;                 // CHI_SQUARED termination test launch: 1 = record the RMSE, 2 = compare, undo, end level
   float conv_eps;               // > 0: CONVERGENCE termination (|x| < conv_eps ends the level)
+  int dry_tail;                 // measurement hook (rgbid_aligner_time_build): run the whole tail -- final sum, solve, pose
+                                // update, projection refresh -- but do not commit it, so that the launch can be repeated
   int prewarped;                // 1: M.Wc / M.Ic already are the current frame warped into the keyframe view at this
                                 //    level (WARP_ORDER = warpFirst, see aligner.cu): read them pixel for pixel
 };
