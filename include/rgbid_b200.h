@@ -264,6 +264,13 @@ int rgbid_aligner_fetch(rgbid_aligner* al, double* R_out, double* t_out, double*
 /* Frame statistics of the last tracker-mode run: chi_square / chi_test / ndof of the end-of-frame test
  * (src/visodo.cpp:1411-1415), 3 floats per pair. */
 int rgbid_aligner_frame_stats(rgbid_aligner* al, float* stats_out);
+/* Device-side export of the alignment results for a multi-GPU exchange: writes, on the context's
+ * stream, [batch][48] doubles into DEVICE memory `d_out` -- per pair the 6x6 covariance (row-major, the inverse of the
+ * last normal-equation matrix), R (9, row-major) and t (3) of _{KF}T^{cur} -- straight from the solver state, so that an
+ * NCCL all-gather can follow on a side stream without any host copy.  Pairs whose alignment failed export NaN. */
+int rgbid_aligner_export_systems(rgbid_aligner* al, double* d_out);
+/* Bytes of device->host traffic rgbid_aligner_fetch / rgbid_tracker_track read back per pair (the solver state). */
+size_t rgbid_aligner_state_bytes(void);
 /* Measurement hook for bench.py's roofline: launches the fused warp+residual+J^T J kernel of `level` `reps`
  * times back to back on the aligner's current maps / poses / scales (no pose update), bracketed by CUDA
  * events on the context's stream; returns the average launch duration in milliseconds.  Synchronous. */

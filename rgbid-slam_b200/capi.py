@@ -141,6 +141,8 @@ PROTOTYPES = {
     "rgbid_aligner_enqueue": (I, [P, c_double_p, c_double_p]),
     "rgbid_aligner_fetch": (I, [P, c_double_p, c_double_p, c_double_p, c_int_p, C.POINTER(IterTrace)]),
     "rgbid_aligner_frame_stats": (I, [P, c_float_p]),
+    "rgbid_aligner_export_systems": (I, [P, P]),
+    "rgbid_aligner_state_bytes": (SZ, []),
     "rgbid_aligner_time_build": (I, [P, I, I, c_float_p]),
     "rgbid_aligner_time_scale": (I, [P, I, I, c_float_p]),
     "rgbid_aligner_map": (I, [P, I, I, I, C.POINTER(P), C.POINTER(SZ)]),

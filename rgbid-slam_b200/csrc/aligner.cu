@@ -490,6 +490,15 @@ int rgbid_aligner_frame_stats(rgbid_aligner* al, float* stats_out)
   return RGBID_OK;
 }
 
+size_t rgbid_aligner_state_bytes(void) { return sizeof(GnState); }
+
+int rgbid_aligner_export_systems(rgbid_aligner* al, double* d_out)
+{
+  if (!al || !d_out) return RGBID_ERR_ARG;
+  launch_export_systems(al->ctx->L(), al->d_states, d_out, al->cfg.batch);
+  return check_last(al->ctx);
+}
+
 static int time_kernel(rgbid_aligner* al, int level, int reps, float* ms_per_launch, bool scale);
 
 int rgbid_aligner_time_build(rgbid_aligner* al, int level, int reps, float* ms_per_launch)

@@ -491,12 +491,23 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
 #ifndef RGBID_TAIL_PROBE
 #define RGBID_TAIL_PROBE 0  // gn_build_fast_kernel: clock64 break-down of the last CTA (diagnostic build only)
 #endif
-constexpr int kChunkPx = 128;                   // one warp-chunk: 4 pixels per lane
+#ifndef RGBID_PX
+#define RGBID_PX 4
+#endif
+constexpr int kPx = RGBID_PX;                   // pixels per lane and chunk (4: 128-bit shared-memory loads; 2: half the live gather state)
+constexpr int kChunkPx = 32 * kPx;              // one warp-chunk
+struct __align__(4 * kPx) LaneVec { float v[kPx]; };
 constexpr int kChunkBytes = kChunkPx * 4;       // per map
 // Two rings per warp: the keyframe inverse depth is needed by three pipeline stages (gather, second projection,
 // constraints) and therefore lives two iterations longer than the other five maps.
-constexpr int kStagesW = 5;                     // W0 ring: 5 x 512 B
-constexpr int kStagesL = 3;                     // I0, gWx, gWy, gIx, gIy ring: 3 x 2560 B
+#ifndef RGBID_STAGES_W
+#define RGBID_STAGES_W 5
+#endif
+#ifndef RGBID_STAGES_L
+#define RGBID_STAGES_L 3
+#endif
+constexpr int kStagesW = RGBID_STAGES_W;        // W0 ring: 5 x 512 B
+constexpr int kStagesL = RGBID_STAGES_L;        // I0, gWx, gWy, gIx, gIy ring: 3 x 2560 B
 constexpr int kLateBytes = 5 * kChunkBytes;
 constexpr int kWarpRingBytes = kStagesW * kChunkBytes + kStagesL * kLateBytes;  // 10 KiB
 constexpr int kFastSmemBytes = kBuildWarps * kWarpRingBytes;                    // 80 KiB per CTA
@@ -514,9 +525,9 @@ __device__ __forceinline__ void unpack_acc(const f32x2* a2, float* acc)
 #pragma unroll
   for (int k = 0; k < 15; ++k) unpack2(a2[k], lo[k], hi[k]);
   // row 0: 00 01 02 03 04 05 0e
-  acc[0] = lo[0]; acc[1] = lo[1]; acc[2] = lo[2]; acc[3] = lo[3]; acc[4] = lo[4]; acc[5] = lo[5]; acc[6] = lo[12];
+  acc[0] = lo[0]; acc[1] = lo[1]; acc[2] = lo[2]; acc[3] = lo[3]; acc[kPx] = lo[kPx]; acc[5] = lo[5]; acc[6] = lo[12];
   // row 1: 11 12 13 14 15 1e
-  acc[7] = hi[0]; acc[8] = hi[3]; acc[9] = hi[2]; acc[10] = hi[5]; acc[11] = hi[4]; acc[12] = hi[12];
+  acc[7] = hi[0]; acc[8] = hi[3]; acc[9] = hi[2]; acc[10] = hi[5]; acc[11] = hi[kPx]; acc[12] = hi[12];
   // row 2: 22 23 24 25 2e
   acc[13] = lo[6]; acc[14] = lo[7]; acc[15] = lo[8]; acc[16] = lo[9]; acc[17] = lo[13];
   // row 3: 33 34 35 3e
@@ -539,7 +550,7 @@ __device__ __forceinline__ void accumulate_packed(f32x2* a2, float s, float r0, 
   const f32x2 sA = mul2(S, A), sB = mul2(S, B), sC = mul2(S, C);
   fma2(a2[0], sA, A);   fma2(a2[1], sA, As);
   fma2(a2[2], sA, B);   fma2(a2[3], sA, Bs);
-  fma2(a2[4], sA, C);   fma2(a2[5], sA, Cs);
+  fma2(a2[kPx], sA, C);   fma2(a2[5], sA, Cs);
   fma2(a2[6], sB, B);   fma2(a2[7], sB, Bs);
   fma2(a2[8], sB, C);   fma2(a2[9], sB, Cs);
   fma2(a2[10], sC, C);  fma2(a2[11], sC, Cs);
@@ -679,8 +690,8 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
   // and 12 + 4 registers travel between iterations.  KeyframeAlign mode samples the intensity where it sampled the
   // inverse depth, so both gathers are issued in S2 and S1 disappears.
   struct ChunkGeom { float xf0, yf, rcx, rcy, rcz; };
-  const float r1 = sh.proj.r[1], r2 = sh.proj.r[2], r4 = sh.proj.r[4], r5 = sh.proj.r[5], r7 = sh.proj.r[7], r8 = sh.proj.r[8];
-  const float idxf0 = __int2float_rn(my_first * kChunkPx + lane * 4) + 0.5f;  // pixel index + 0.5, exact below 2^23
+  const float r1 = sh.proj.r[1], r2 = sh.proj.r[2], r4 = sh.proj.r[kPx], r5 = sh.proj.r[5], r7 = sh.proj.r[7], r8 = sh.proj.r[8];
+  const float idxf0 = __int2float_rn(my_first * kChunkPx + lane * kPx) + 0.5f;  // pixel index + 0.5, exact below 2^23
   auto chunk_geom = [&](int i) {
     ChunkGeom g;
     const float idxh = fmaf(__int2float_rn(i), (float)(kBuildWarps * kChunkPx), idxf0);
@@ -694,9 +705,9 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
   // plain shared-memory loads (not volatile asm): the mbarrier waits carry a memory clobber, so the loads cannot move
   // above them, and the compiler is free to schedule them and to pick destination registers that are not the target of
   // a texture fetch still in flight (a volatile LDS stalled 9 % of all samples on exactly that hazard)
-  const unsigned char* ringW_p = ring + (size_t)wid * kWarpRingBytes + (size_t)lane * 16;
+  const unsigned char* ringW_p = ring + (size_t)wid * kWarpRingBytes + (size_t)lane * (4 * kPx);
   const unsigned char* ringL_p = ringW_p + kStagesW * kChunkBytes;
-  auto lds_w0 = [&](int i, float* w0) { *(float4*)w0 = *(const float4*)(ringW_p + (size_t)(i % kStagesW) * kChunkBytes); };
+  auto lds_w0 = [&](int i, float* w0) { *(LaneVec*)w0 = *(const LaneVec*)(ringW_p + (size_t)(i % kStagesW) * kChunkBytes); };
   // floor(xt) in [0, cols) && floor(yt) in [0, rows) (warping_registration.cu:490-491) as four float compares -- exact,
   // false for the NaN coordinates of an invalid geometry, and on the ALU pipe (this kernel is bound by the FMA pipe);
   // returned as 0 / NaN so that it can be added to the sample later
@@ -706,11 +717,11 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
   // S2: first projection (geometry = keyframe inverse depth) of chunk i and its gather(s)
   auto gather = [&](int i, float* w2, float* wcs, float* i1, float* pinf) {
     mbar_wait(barW + (uint32_t)(i % kStagesW) * 8u, (uint32_t)(i / kStagesW) & 1u);
-    float w0[4], xt[4], yt[4];
+    float w0[kPx], xt[kPx], yt[kPx];
     lds_w0(i, w0);
     const ChunkGeom g = chunk_geom(i);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < kPx; ++k) {
       const float xf = g.xf0 + (float)k;
       const float z = 1.f / w0[k];
       const float Xc = fmaf(fmaf(r0, xf, g.rcx), z, t0), Yc = fmaf(fmaf(r3, xf, g.rcy), z, t1);
@@ -720,12 +731,12 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
       xt[k] = fmaf(Xc, wc, 0.5f); yt[k] = fmaf(Yc, wc, 0.5f);
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) w2[k] = tex2D<float>(texW, xt[k], yt[k]);  // border addressing: 0 outside
+    for (int k = 0; k < kPx; ++k) w2[k] = tex2D<float>(texW, xt[k], yt[k]);  // border addressing: 0 outside
     if (!TRACKER) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) i1[k] = tex2D<float>(texI, xt[k], yt[k]);
+      for (int k = 0; k < kPx; ++k) i1[k] = tex2D<float>(texI, xt[k], yt[k]);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) pinf[k] = in_image_nan(xt[k], yt[k]);
+      for (int k = 0; k < kPx; ++k) pinf[k] = in_image_nan(xt[k], yt[k]);
     }
   };
   // trafo3DKernelInvDepthGridStride, warping_registration.cu:533-538, operation for operation (v1z is
@@ -740,10 +751,10 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
   // (src/visodo.cpp:1121-1126)
   auto second_projection = [&](int i, const float* w2, const float* wcs, float* w1, float* i1, float* pinf) {
     const ChunkGeom g = chunk_geom(i);
-    float w0[4], xt[4], yt[4];
+    float w0[kPx], xt[kPx], yt[kPx];
     lds_w0(i, w0);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < kPx; ++k) {
       const float xf = g.xf0 + (float)k;
       w1[k] = warped_invdepth(w0[k], wcs[k], w2[k]);
       const float zz = 1.f / w1[k];
@@ -752,15 +763,15 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
       xt[k] = fmaf(Xc, wc1, 0.5f); yt[k] = fmaf(Yc, wc1, 0.5f);
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) i1[k] = tex2D<float>(texI, xt[k], yt[k]);
+    for (int k = 0; k < kPx; ++k) i1[k] = tex2D<float>(texI, xt[k], yt[k]);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) pinf[k] = in_image_nan(xt[k], yt[k]);
+    for (int k = 0; k < kPx; ++k) pinf[k] = in_image_nan(xt[k], yt[k]);
   };
 
-  float w2n[4], wcn[4];                  // S2 -> S1 (tracker) / S3 (align): gathered inverse depth, 1 / Zc
+  float w2n[kPx], wcn[kPx];                  // S2 -> S1 (tracker) / S3 (align): gathered inverse depth, 1 / Zc
   // S1 -> S3: warped inverse depth, raw intensity sample, 0 / NaN in-image flag.  Two sets, used alternately by a
   // loop unrolled by two, so that nothing has to be copied between iterations.
-  float w1a[4], i1a[4], pina[4], w1b[4], i1b[4], pinb[4];
+  float w1a[kPx], i1a[kPx], pina[kPx], w1b[kPx], i1b[kPx], pinb[kPx];
   if (my_n > 0) {
     if (TRACKER) {
       gather(0, w2n, wcn, nullptr, nullptr);
@@ -777,10 +788,10 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
       if (i + 1 < my_n) second_projection(i + 1, w2n, wcn, w1n, i1n, pinn);  // warp-uniform
       if (i + 2 < my_n) gather(i + 2, w2n, wcn, nullptr, nullptr);
     } else {
-      float w0a[4];
+      float w0a[kPx];
       lds_w0(i, w0a);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) w1c[k] = warped_invdepth(w0a[k], wcn[k], w2n[k]);
+      for (int k = 0; k < kPx; ++k) w1c[k] = warped_invdepth(w0a[k], wcn[k], w2n[k]);
       if (i + 1 < my_n) gather(i + 1, w2n, wcn, i1n, pinn);
     }
 
@@ -790,12 +801,12 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
     const float py2p1 = fmaf(py, py, 1.f);
     const unsigned char* buf = ringL_p + (size_t)(i % kStagesL) * kLateBytes;
     mbar_wait(barL + (uint32_t)(i % kStagesL) * 8u, (uint32_t)(i / kStagesL) & 1u);
-    float w0[4], gwx[4], gwy[4];
+    float w0[kPx], gwx[kPx], gwy[kPx];
     lds_w0(i, w0);
-    *(float4*)gwx = *(const float4*)(buf + 1 * kChunkBytes);
-    *(float4*)gwy = *(const float4*)(buf + 2 * kChunkBytes);
+    *(LaneVec*)gwx = *(const LaneVec*)(buf + 1 * kChunkBytes);
+    *(LaneVec*)gwy = *(const LaneVec*)(buf + 2 * kChunkBytes);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < kPx; ++k) {
       const float xf = g.xf0 + (float)k;
       const float px = (xf - P.cx) * ifx;
       // invDepthConstraint (estimate_VO.cu:214-262).  The reference's n = (g0, g1, g2) / w0 + (0, 0, 1) satisfies
@@ -814,7 +825,7 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
       const float h2 = gs2 + w1s;
       float rd[6];
       rd[0] = gs0 * w0s; rd[1] = gs1 * w0s; rd[2] = h2 * w0s;
-      rd[3] = fmaf(h2, py, -gs1); rd[4] = fmaf(-h2, px, gs0); rd[5] = fmaf(gs1, px, -(gs0 * py));
+      rd[3] = fmaf(h2, py, -gs1); rd[kPx] = fmaf(-h2, px, gs0); rd[5] = fmaf(gs1, px, -(gs0 * py));
       const float ed = w0s - w1s;
       const float eud = fmaf(w0[k] - w1[k], is_d, -bos_d);
       const float sd = fmaxf(nf * (c_d * (1.f / fmaf(eud, eud, nu_d))), 0.f);
@@ -826,7 +837,7 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
       const float h2 = gd2 + w1[k];
       float rd[6];
       rd[0] = gd0 * w0[k]; rd[1] = gd1 * w0[k]; rd[2] = h2 * w0[k];
-      rd[3] = fmaf(h2, py, -gd1); rd[4] = fmaf(-h2, px, gd0); rd[5] = fmaf(gd1, px, -(gd0 * py));
+      rd[3] = fmaf(h2, py, -gd1); rd[kPx] = fmaf(-h2, px, gd0); rd[5] = fmaf(gd1, px, -(gd0 * py));
       const float ed = w0[k] - w1[k];
       const float eud = fmaf(ed, is_d, -bos_d);
       const float sd = nf * (c_d * (1.f / fmaf(eud, eud, nu_d)));  // NaN if any of w0, w1, gwx, gwy is NaN
@@ -841,19 +852,19 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
         }
       }
 #if RGBID_ACC2
-      accumulate_packed(acc2, sd, rd[0], rd[1], rd[2], rd[3], rd[4], rd[5], ed);
+      accumulate_packed(acc2, sd, rd[0], rd[1], rd[2], rd[3], rd[kPx], rd[5], ed);
 #else
       accumulate_scalar(accs, sd, rd, ed, fd);
 #endif
     }
 
     // --- S3: intensity constraint + accumulation ---------------------------------------------------------------
-    float i0[4], gix[4], giy[4];
-    *(float4*)i0 = *(const float4*)(buf + 0 * kChunkBytes);
-    *(float4*)gix = *(const float4*)(buf + 3 * kChunkBytes);
-    *(float4*)giy = *(const float4*)(buf + 4 * kChunkBytes);
+    float i0[kPx], gix[kPx], giy[kPx];
+    *(LaneVec*)i0 = *(const LaneVec*)(buf + 0 * kChunkBytes);
+    *(LaneVec*)gix = *(const LaneVec*)(buf + 3 * kChunkBytes);
+    *(LaneVec*)giy = *(const LaneVec*)(buf + 4 * kChunkBytes);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < kPx; ++k) {
       const float xf = g.xf0 + (float)k;
       const float px = (xf - P.cx) * ifx;
       // max(0, min(r, 255)): a NaN sample becomes 255 like in the reference (warping_registration.cu:493-494);
@@ -866,7 +877,7 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
       const float gs2 = -fmaf(gs0, px, gs1 * py);
       float ri[6];
       ri[0] = gs0 * w0s; ri[1] = gs1 * w0s; ri[2] = gs2 * w0s;
-      ri[3] = fmaf(gs2, py, -gs1); ri[4] = fmaf(-gs2, px, gs0); ri[5] = fmaf(gs1, px, -(gs0 * py));
+      ri[3] = fmaf(gs2, py, -gs1); ri[kPx] = fmaf(-gs2, px, gs0); ri[5] = fmaf(gs1, px, -(gs0 * py));
       const float ei_raw = i0[k] - i1v;
       const float ei = fmaxf(ei_raw, -1e30f);
       const float eui = fmaf(ei_raw, is_i, -bos_i);
@@ -876,7 +887,7 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
       const float gi2 = -fmaf(gi0, px, gi1 * py);
       float ri[6];
       ri[0] = gi0 * w0[k]; ri[1] = gi1 * w0[k]; ri[2] = gi2 * w0[k];
-      ri[3] = fmaf(gi2, py, -gi1); ri[4] = fmaf(-gi2, px, gi0); ri[5] = fmaf(gi1, px, -(gi0 * py));
+      ri[3] = fmaf(gi2, py, -gi1); ri[kPx] = fmaf(-gi2, px, gi0); ri[5] = fmaf(gi1, px, -(gi0 * py));
       const float ei = i0[k] - i1v;
       const float eui = fmaf(ei, is_i, -bos_i);
       float si = c_i * (1.f / fmaf(eui, eui, nu_i));
@@ -890,7 +901,7 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
         }
       }
 #if RGBID_ACC2
-      accumulate_packed(acc2, si, ri[0], ri[1], ri[2], ri[3], ri[4], ri[5], ei);
+      accumulate_packed(acc2, si, ri[0], ri[1], ri[2], ri[3], ri[kPx], ri[5], ei);
 #else
       accumulate_scalar(accs, si, ri, ei, fi);
 #endif
@@ -1076,6 +1087,16 @@ __global__ void gn_init_kernel(GnState* __restrict__ states, const double* __res
   refresh_proj(st, st.R, st.t, levels, fx0, fy0, cx0, cy0);
 }
 
+__global__ void export_systems_kernel(const GnState* __restrict__ states, double* __restrict__ out, int batch)
+{
+  const int b = blockIdx.x, k = threadIdx.x;  // 48 threads per pair
+  if (b >= batch || k >= 48) return;
+  const GnState& st = states[b];
+  double v = (k < 36) ? st.cov[k] : (k < 45) ? st.R[k - 36] : st.t[k - 45];
+  if (st.status != RGBID_OK) v = __longlong_as_double(0x7ff8000000000000ll);
+  out[(size_t)b * 48 + k] = v;
+}
+
 // every stream of the map owns whole 128-pixel chunks (the aligner NaN-fills the padding and nothing writes it),
 // so the fast kernel may read the last chunk in full
 inline bool padded(const ImgB& m, const GnParams& P)
@@ -1100,6 +1121,12 @@ int gn_build_grid_x(int rows, int cols, int batch, int num_sms)
   const int k = (units + cap * kBuildThreads - 1) / (cap * kBuildThreads);  // units per thread
   int g = (units + k * kBuildThreads - 1) / (k * kBuildThreads);
   return g < 1 ? 1 : g;
+}
+
+void launch_export_systems(const LaunchCtx& L, const GnState* states, double* out, int batch)
+{
+  export_systems_kernel<<<batch, 64, 0, L.stream>>>(states, out, batch);
+  ++*L.launches;
 }
 
 void launch_gn_init(const LaunchCtx& L, GnState* states, const double* R_init, const double* t_init, int batch,

@@ -208,6 +208,8 @@ void launch_gn_build(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P
 void launch_gn_init(const LaunchCtx& L, GnState* states, const double* R_init, const double* t_init, int batch,
                     int levels, float fx0, float fy0, float cx0, float cy0);
 int gn_build_grid_x(int rows, int cols, int batch, int num_sms);
+// [batch][48] doubles (cov 36, R 9, t 3) from the solver state; NaN for lost pairs
+void launch_export_systems(const LaunchCtx& L, const GnState* states, double* out, int batch);
 
 // un-fused drop-in (pre-warped W1 / I1), one pair
 void launch_build_system(const LaunchCtx& L, ImgB W0, ImgB I0, ImgB gWx, ImgB gWy, ImgB gIx, ImgB gIy, ImgB W1,

@@ -456,6 +456,11 @@ class Aligner:
                 out["trace"][b] = [out["trace"][b][i] for i in keep]
         return out
 
+    def export_systems(self, out):
+        assert out.is_cuda and out.dtype == torch.float64 and out.is_contiguous() and out.numel() == self.batch * 48
+        capi.check(self.lib.rgbid_aligner_export_systems(self.h, out.data_ptr()), "export_systems")
+        return out
+
     def enqueue(self, R, t):
         R = np.ascontiguousarray(R, dtype=np.float64)
         t = np.ascontiguousarray(t, dtype=np.float64)
@@ -601,6 +606,13 @@ class Tracker:
         ms = _F(0)
         capi.check(self.lib.rgbid_aligner_time_build(self.aligner_handle, level, reps, C.byref(ms)), "aligner_time_build")
         return ms.value
+
+    def export_systems(self, out):
+        """[batch, 48] float64 CUDA tensor <- (cov 36, R 9, t 3) of every stream's last alignment, written on the
+        context's stream by a kernel (no host copy): the payload of the multi-GPU all-gather."""
+        assert out.is_cuda and out.dtype == torch.float64 and out.is_contiguous() and out.numel() == self.batch * 48
+        capi.check(self.lib.rgbid_aligner_export_systems(self.aligner_handle, out.data_ptr()), "export_systems")
+        return out
 
     def overlap_mask(self, index=0):
         """Overlap mask of the integration keyframe of stream `index` (uint8, 1 = seen by the previous keyframe)."""

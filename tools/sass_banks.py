@@ -48,7 +48,7 @@ def find_loop(ins):
             if m and int(m.group(1), 16) < a and int(m.group(1), 16) in idx:
                 lo = idx[int(m.group(1), 16)]
                 ops = [o.split(".")[0] for _, o, _ in ins[lo:i + 1]]
-                if ops.count("FFMA") + 2 * ops.count("FFMA2") > 50 and "SHFL" not in ops and (best is None or i - lo > best[1] - best[0]):
+                if ops.count("FFMA") + 2 * ops.count("FFMA2") > 50 and "SHFL" not in ops and "DADD" not in ops and (best is None or i - lo > best[1] - best[0]):
                     best = (lo, i)
     return best
 
