@@ -98,7 +98,8 @@ int main(int argc, char** argv)
   cudaSafeCall(cudaSetDevice(device::dev_id));
   cudaSafeCall(cudaGetDeviceProperties(&device::dev_prop, device::dev_id));
 
-  std::string poses_logfile("poses"), config_file, calib_file, eval_folder, match_file, out_override;
+  std::string poses_logfile("poses"), misc_logfile("misc"), kf_times_logfile("kf_times"), config_file, calib_file, eval_folder,
+      match_file, out_override;
   int max_frames = -1;
   parse_argument<std::string>(argc, argv, "-config", config_file, to_str);
   parse_argument<std::string>(argc, argv, "-calib", calib_file, to_str);
@@ -115,9 +116,19 @@ int main(int argc, char** argv)
     std::size_t found_prelast = eval_folder2.find_last_of("/\\");
     std::string dataset_name = eval_folder2.substr(found_prelast + 1);
     poses_logfile = dataset_name + "_" + poses_logfile;
+    misc_logfile = dataset_name + "_" + misc_logfile;
+    kf_times_logfile = dataset_name + "_" + kf_times_logfile;
   }
   poses_logfile.append(".txt");
-  if (!out_override.empty()) poses_logfile = out_override;
+  misc_logfile.append(".txt");
+  kf_times_logfile.append(".txt");
+  if (!out_override.empty()) {  // -o <file>: the two time logs go next to it
+    poses_logfile = out_override;
+    const std::string stem = out_override.substr(0, out_override.find_last_of('.'));
+    misc_logfile = stem + "_misc.txt";
+    kf_times_logfile = stem + "_kf_times.txt";
+  }
+  const bool inline_tracking = find_switch(argc, argv, "-inline");
 
   try {
     tum::Sequence seq(eval_folder, match_file);
@@ -146,12 +157,36 @@ int main(int argc, char** argv)
     std::vector<tum::PoseRt> poses;
     int num_failures = 0, lost = 0, odo_kf = 0;
     const auto t0 = std::chrono::steady_clock::now();
+    // The reference's structure (tools/RGBID_SLAMapp.cpp:163-214, 459-460): the tracker runs in its own thread and waits
+    // on new_frame_cond_; the grabber try-locks visodo.mutex_, uploads the frame and notifies.  The reference then sleeps
+    // 30 ms (playback pacing, :209); an evaluation run must neither drop nor repeat a frame, so this grabber waits for
+    // the tracker's frame counter instead.  -inline calls trackNewFrame() from this thread.
+    if (!inline_tracking) visodo.start();
     for (size_t i = 0; num_failures < 10 && (max_frames < 0 || (int)poses.size() < max_frames); ++i) {
       if (i > 0 && !seq.grab(i, depth, rgb, rows, cols)) { ++num_failures; continue; }
       num_failures = 0;
-      visodo.depth_.upload(depth.data(), (size_t)cols * 2, rows, cols);
-      visodo.rgb24_.upload(rgb.data(), (size_t)cols * 3, rows, cols);
-      visodo.trackNewFrame();
+      if (inline_tracking) {
+        visodo.depth_.upload(depth.data(), (size_t)cols * 2, rows, cols);
+        visodo.rgb24_.upload(rgb.data(), (size_t)cols * 3, rows, cols);
+        visodo.trackNewFrame();
+      } else {
+        int before;
+        for (;;) {
+          std::unique_lock<std::mutex> lock(visodo.mutex_, std::try_to_lock);
+          if (!lock) { std::this_thread::yield(); continue; }
+          before = visodo.frames_tracked_by_thread_;
+          visodo.depth_.upload(depth.data(), (size_t)cols * 2, rows, cols);
+          visodo.rgb24_.upload(rgb.data(), (size_t)cols * 3, rows, cols);
+          visodo.new_frame_cond_.notify_one();
+          break;
+        }
+        for (;;) {  // the tracker holds mutex_ while it works on the frame
+          std::unique_lock<std::mutex> lock(visodo.mutex_);
+          if (visodo.frames_tracked_by_thread_ != before) break;
+          lock.unlock();
+          std::this_thread::yield();
+        }
+      }
       const Affine3 p = visodo.getCameraPose();
       tum::PoseRt pr;
       for (int k = 0; k < 9; ++k) pr.R[k] = p.R[k];
@@ -160,9 +195,16 @@ int main(int argc, char** argv)
       lost += visodo.visOdoIsLost() ? 1 : 0;
       odo_kf += visodo.lastResult().new_odo_keyframe;
     }
+    visodo.stop();
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     std::cout << "Writing " << poses.size() << " poses to " << poses_logfile << std::endl;
     tum::save_all_poses(poses_logfile, seq, poses);
+    {  // Evaluation::saveAllPoses' time statistics and saveTimeLogFiles (tools/evaluation.cpp:353-420)
+      std::vector<float> times;
+      for (size_t i = 0; i < visodo.getNumberOfPoses(); ++i) times.push_back(visodo.getVisOdoTime((int)i));
+      tum::save_misc_log(misc_logfile, times);
+      tum::save_kf_times_log(kf_times_logfile, visodo.kf_times_);
+    }
     std::cout << "frames " << poses.size() << "  lost " << lost << "  odometry keyframes " << odo_kf << "  "
               << (poses.size() / secs) << " frames/s including PNG decoding" << std::endl;
   } catch (const std::exception& e) {

@@ -227,5 +227,33 @@ inline void save_all_poses(const std::string& path, const Sequence& seq, const s
   }
 }
 
+// "<dataset>_misc.txt": mean / std / max tracking time per frame in ms, the header lines of
+// Evaluation::saveAllPoses (tools/evaluation.cpp:397-420; the reference writes them to its chi-tests / misc log)
+inline void save_misc_log(const std::string& path, const std::vector<float>& vis_odo_times_ms)
+{
+  const int n = (int)vis_odo_times_ms.size();
+  float mean = 0.f, sd = 0.f, mx = 0.f;
+  for (int i = 0; i < n; ++i) { mean += vis_odo_times_ms[i] / n; if (vis_odo_times_ms[i] > mx) mx = vis_odo_times_ms[i]; }
+  for (int i = 0; i < n; ++i) sd += (vis_odo_times_ms[i] - mean) * (vis_odo_times_ms[i] - mean) / n;
+  sd = std::sqrt(sd);
+  std::ofstream out(path.c_str());
+  out.setf(std::ios::fixed, std::ios::floatfield);
+  out << "Mean time per frame: " << mean << std::endl << "Std time per frame: " << sd << std::endl
+      << "Max time per frame: " << mx << std::endl;
+}
+
+// "<dataset>_kf_times.txt", Evaluation::saveTimeLogFiles (tools/evaluation.cpp:353-377): one line per keyframe handed to
+// the back end.  The five KeyframeManager columns (total, segmentation, BoW, loop detection, pose graph) belong to the
+// back end, which is out of scope: they are written as 0 so that the file keeps the reference's columns.
+inline void save_kf_times_log(const std::string& path, const std::vector<float>& kf_times_ms)
+{
+  std::ofstream out(path.c_str());
+  out.setf(std::ios::fixed, std::ios::floatfield);
+  out << "ObtainKeyframe " << "ProcessKeyframeTotal " << "Segmentation " << "DescriptionBoW " << "LoopDetection "
+      << "PoseGraphOptim" << std::endl;
+  for (size_t i = 0; i < kf_times_ms.size(); ++i)
+    out << kf_times_ms[i] << " " << 0.f << " " << 0.f << " " << 0.f << " " << 0.f << " " << 0.f << std::endl;
+}
+
 }  // namespace tum
 }  // namespace RGBID_SLAM

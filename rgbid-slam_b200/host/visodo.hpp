@@ -10,6 +10,7 @@
 #pragma once
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -18,7 +19,9 @@
 #include <mutex>
 #include <sstream>
 #include <stdexcept>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rgbid_b200/internal.hpp"
@@ -67,7 +70,62 @@ class VisodoTracker {
     depth_.create(rows_, cols_);
   }
 
-  ~VisodoTracker() { if (trk_) rgbid_tracker_destroy(trk_); }
+  ~VisodoTracker()
+  {
+    stop();
+    if (trk_) rgbid_tracker_destroy(trk_);
+  }
+
+  /** Starts the tracking thread and returns once it is waiting for frames (src/visodo.cpp:437-445).  The grabber
+      then hands frames over exactly like tools/RGBID_SLAMapp.cpp:144-214: try-lock `mutex_`, upload into `depth_` /
+      `rgb24_`, `new_frame_cond_.notify_one()`.  std:: primitives stand in for the reference's boost:: ones. */
+  void start()
+  {
+    std::unique_lock<std::mutex> lock(created_aux_mutex_);
+    created_ = false;
+    visodo_thread_.reset(new std::thread([this] { (*this)(); }));
+    created_cond_.wait(lock, [this] { return created_; });
+  }
+
+  /** Body of the tracking thread (src/visodo.cpp:2249-2267): wait for a frame, track it, until exit_ is set. */
+  bool operator()()
+  {
+    std::unique_lock<std::mutex> lock(mutex_);
+    exit_ = false;
+    {
+      std::lock_guard<std::mutex> aux(created_aux_mutex_);
+      created_ = true;
+    }
+    created_cond_.notify_one();
+    while (!exit_) {
+      new_frame_cond_.wait(lock);
+      if (exit_) break;
+      trackNewFrame();
+      ++frames_tracked_by_thread_;
+    }
+    return true;
+  }
+
+  /** Ends the tracking thread (the reference sets exit_ from the application and never joins). */
+  void stop()
+  {
+    if (!visodo_thread_) return;
+    {
+      std::lock_guard<std::mutex> lock(mutex_);
+      exit_ = true;
+    }
+    new_frame_cond_.notify_all();
+    if (visodo_thread_->joinable()) visodo_thread_->join();
+    visodo_thread_.reset();
+  }
+
+  // hand-shake with the grabber thread (include/visodo.h:121-127)
+  std::mutex mutex_;
+  std::condition_variable new_frame_cond_;
+  std::mutex created_aux_mutex_;
+  std::condition_variable created_cond_;
+  bool exit_ = false;
+  int frames_tracked_by_thread_ = 0;
 
   /** [VISODO] keys of the reference (src/visodo.cpp:321-435) */
   void loadSettings(Settings& settings)
@@ -340,6 +398,8 @@ class VisodoTracker {
   float fx_, fy_, cx_, cy_, factor_depth_;
   rgbid_tracker* trk_;
   bool lost_;
+  bool created_ = false;
+  std::unique_ptr<std::thread> visodo_thread_;
   int global_time_;
   rgbid_frame_result last_;
   std::vector<Affine3> poses_;

@@ -57,6 +57,20 @@ def test_app_on_tum_sequence(built, tmp_path):
                        capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
     assert r.returncode == 0, r.stdout + r.stderr
     assert os.path.exists(tmp_path / "rgbd_dataset_synth_poses.txt")
+    # the two time logs of tools/evaluation.cpp:353-420 next to it
+    misc = (tmp_path / "rgbd_dataset_synth_misc.txt").read_text().splitlines()
+    assert [ln.split(":")[0] for ln in misc] == ["Mean time per frame", "Std time per frame", "Max time per frame"]
+    assert float(misc[2].split(":")[1]) >= float(misc[0].split(":")[1]) > 0.0
+    kft = (tmp_path / "rgbd_dataset_synth_kf_times.txt").read_text().splitlines()
+    assert kft[0].split() == ["ObtainKeyframe", "ProcessKeyframeTotal", "Segmentation", "DescriptionBoW", "LoopDetection", "PoseGraphOptim"]
+    assert all(len(ln.split()) == 6 for ln in kft[1:])
+
+    # the tracker thread (VisodoTracker::start / operator(), the default) and -inline must write the same poses
+    log2 = tmp_path / "poses_inline.txt"
+    r = subprocess.run([APP, "-eval", folder + "/", "-match_file", "matches.txt", "-calib", str(calib), "-config", str(config),
+                        "-o", str(log2), "-inline"], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert log2.read_text() == log.read_text()
 
 
 def test_app_with_custom_calibration_file(built, tmp_path):
