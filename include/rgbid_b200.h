@@ -179,6 +179,12 @@ int rgbid_build_system(rgbid_ctx* ctx, const float* W0, const float* I0, const f
                        const float* gradW0_y, const float* gradI0_x, const float* gradI0_y, const float* W1,
                        const float* I1, size_t pitch, int rows, int cols, const rgbid_system_params* params,
                        double* A36_host, double* b6_host);
+/* Same with one row pitch per map, pitch8[i] for the i-th pointer argument (PtrStep<float>::step of each map,
+ * src/internal.h:360-384: maps from cudaMallocPitch and wrapped dense maps may be mixed). */
+int rgbid_build_system_pitched(rgbid_ctx* ctx, const float* W0, const float* I0, const float* gradW0_x,
+                               const float* gradW0_y, const float* gradI0_x, const float* gradI0_y, const float* W1,
+                               const float* I1, const size_t* pitch8, int rows, int cols,
+                               const rgbid_system_params* params, double* A36_host, double* b6_host);
 
 /* ---------------------------------------------------------------------------------------------- */
 /* Fused, device-resident coarse-to-fine alignment of `batch` independent frame pairs               */
@@ -397,7 +403,10 @@ int rgbid_tracker_track(rgbid_tracker* trk, const uint16_t* depth, const uint8_t
  * the current or the next track call only; after that it is dropped and the frame is copied inside the call as usual. */
 int rgbid_tracker_prefetch(rgbid_tracker* trk, const uint16_t* depth, const uint8_t* rgb);
 /* Same with pitched DEVICE buffers (what VisodoTracker::depth_ / rgb24_ are: DeviceArray2D, include/visodo.h:118-119):
- * row pitch and per-stream stride in bytes (stride is ignored when batch == 1). */
+ * row pitch and per-stream stride in bytes (stride is ignored when batch == 1).  The pose read-backs are complete on
+ * return, but the keyframe colour copy and the depth fusion of this frame may still be reading the two buffers on the
+ * context's stream: call rgbid_ctx_sync (VisodoTracker::trackNewFrame does, like the reference's device::sync()) or
+ * order the next write after that stream before refilling them. */
 int rgbid_tracker_track_device(rgbid_tracker* trk, const uint16_t* depth, size_t depth_pitch, size_t depth_stride,
                                const uint8_t* rgb, size_t rgb_pitch, size_t rgb_stride, rgbid_frame_result* results_host);
 /* Integration-keyframe maps of stream `index` (device pointers; pitch in bytes):

@@ -526,12 +526,10 @@ inline float build_system_common(const DepthMapf& W0, const IntensityMapf& I0, c
                                  float_type* matrixA_host, float_type* vectorB_host)
 {
   CallTimer t;
-  const size_t pitch = W0.step();
-  if (I0.step() != pitch || gradW0_x.step() != pitch || gradW0_y.step() != pitch || gradI0_x.step() != pitch ||
-      gradI0_y.step() != pitch || W1.step() != pitch || I1.step() != pitch)
-    throw std::runtime_error("buildSystem: all maps of one level must share the row pitch");
-  check(rgbid_build_system(t.tc.ctx, W0.ptr(), I0.ptr(), gradW0_x.ptr(), gradW0_y.ptr(), gradI0_x.ptr(), gradI0_y.ptr(),
-                           W1.ptr(), I1.ptr(), pitch, W0.rows(), W0.cols(), &p, matrixA_host, vectorB_host), "buildSystem");
+  const size_t pitch8[8] = {W0.step(), I0.step(), gradW0_x.step(), gradW0_y.step(), gradI0_x.step(), gradI0_y.step(),
+                            W1.step(), I1.step()};  // every PtrStep carries its own step
+  check(rgbid_build_system_pitched(t.tc.ctx, W0.ptr(), I0.ptr(), gradW0_x.ptr(), gradW0_y.ptr(), gradI0_x.ptr(), gradI0_y.ptr(),
+                                   W1.ptr(), I1.ptr(), pitch8, W0.rows(), W0.cols(), &p, matrixA_host, vectorB_host), "buildSystem");
   return t.done();
 }
 

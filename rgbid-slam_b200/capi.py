@@ -129,6 +129,8 @@ PROTOTYPES = {
     "rgbid_sigma_pdf": (I, [P, P, I, c_float_p, c_float_p, I]),
     "rgbid_chi_square": (I, [P, P, P, I, F, F, I, c_float_p, c_float_p, c_float_p]),
     "rgbid_build_system": (I, [P, P, P, P, P, P, P, P, P, SZ, I, I, C.POINTER(SystemParams), c_double_p, c_double_p]),
+    "rgbid_build_system_pitched": (I, [P, P, P, P, P, P, P, P, P, C.POINTER(C.c_size_t), I, I, C.POINTER(SystemParams),
+                                       c_double_p, c_double_p]),
     "rgbid_aligner_create": (I, [P, C.POINTER(AlignConfig), C.POINTER(P)]),
     "rgbid_aligner_destroy": (I, [P]),
     "rgbid_aligner_num_iterations": (I, [P]),

@@ -419,4 +419,26 @@ int rgbid_build_system(rgbid_ctx* ctx, const float* W0, const float* I0, const f
   return check_last(ctx);
 }
 
+/* Same with one row pitch per map, in the order of the pointer arguments (a PtrStep carries its own step:
+ * cudaMallocPitch gives the maps a caller allocates a different pitch from the ones it wraps) */
+int rgbid_build_system_pitched(rgbid_ctx* ctx, const float* W0, const float* I0, const float* gWx, const float* gWy,
+                               const float* gIx, const float* gIy, const float* W1, const float* I1, const size_t* pitch8,
+                               int rows, int cols, const rgbid_system_params* sp, double* A36, double* b6)
+{
+  if (!ctx || !W0 || !I0 || !gWx || !gWy || !gIx || !gIy || !W1 || !I1 || !pitch8 || !sp || !A36 || !b6 || rows <= 0 || cols <= 0)
+    return RGBID_ERR_ARG;
+  for (int i = 0; i < 8; ++i)
+    if (pitch8[i] < (size_t)cols * sizeof(float)) return RGBID_ERR_ARG;
+  launch_build_system(ctx->L(), make_img(W0, pitch8[0], rows, cols), make_img(I0, pitch8[1], rows, cols),
+                      make_img(gWx, pitch8[2], rows, cols), make_img(gWy, pitch8[3], rows, cols),
+                      make_img(gIx, pitch8[4], rows, cols), make_img(gIy, pitch8[5], rows, cols),
+                      make_img(W1, pitch8[6], rows, cols), make_img(I1, pitch8[7], rows, cols), *sp, ctx->d_partials,
+                      ctx->d_counter, ctx->d_out);
+  double* h = (double*)ctx->h_small;
+  RGBID_CUDA_TRY(cudaMemcpyAsync(h, ctx->d_out, 27 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  RGBID_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  unpack_system(h, A36, b6);
+  return check_last(ctx);
+}
+
 }  // extern "C"

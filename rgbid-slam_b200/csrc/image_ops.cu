@@ -251,20 +251,29 @@ __global__ void __launch_bounds__(BX* BY) bilateral2_kernel(ImgB srcA, ImgB dstA
   const float sigma_floatmap = (z < batch) ? sigmaA : sigmaB;
   int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= src.cols || y >= src.rows) return;
-  const int R = 2;
   float value = __ldg(src.row(b, y) + x);
   if (isnan(value)) { dst.row(b, y)[x] = qnanf(); return; }
-  int tx = min(x + R + 1, src.cols), ty = min(y + R + 1, src.rows);
   const float s2ih = 0.5f / (5.f * 5.f);  // sigma_space = 5 (filters.cu:83)
+  // (value - tmp) / sigma under --prec-div=false is (value - tmp) * rcp.approx(sigma): the reciprocal is the same for
+  // all 25 taps, so it is taken once (25 MUFU per pixel instead of 50 -- the kernel is bound by the SFU pipe); the taps
+  // are unrolled over fixed offsets so that the spatial term s2ih * (dx^2 + dy^2) is a compile-time constant -- the same
+  // single-precision product the loop computed.  Same taps, same order, same arithmetic: bit-identical output.
+  const float rsigma = __fdividef(1.f, sigma_floatmap);  // rcp.approx.ftz, the reciprocal div.approx multiplies by
   float sum1 = 0.f, sum2 = 0.f;
-  for (int cy = max(y - R, 0); cy < ty; ++cy) {
+#pragma unroll
+  for (int dy = -2; dy <= 2; ++dy) {
+    const int cy = y + dy;
+    if (cy < 0 || cy >= src.rows) continue;
     const float* srow = src.row(b, cy);
-    for (int cx = max(x - R, 0); cx < tx; ++cx) {
-      float tmp = __ldg(srow + cx);
+#pragma unroll
+    for (int dx = -2; dx <= 2; ++dx) {
+      const int cx = x + dx;
+      if (cx < 0 || cx >= src.cols) continue;
+      const float tmp = __ldg(srow + cx);
       if (!isnan(tmp)) {
-        float space2 = __int2float_rn((x - cx) * (x - cx) + (y - cy) * (y - cy));
-        float fn = (value - tmp) / sigma_floatmap;
-        float weight = __expf(-(s2ih * space2 + 0.5f * fn * fn));
+        const float space2 = (float)(dx * dx + dy * dy);
+        const float fn = (value - tmp) * rsigma;
+        const float weight = __expf(-(s2ih * space2 + 0.5f * fn * fn));
         sum1 += tmp * weight;
         sum2 += weight;
       }

@@ -106,6 +106,9 @@ void launch_warp_integrate(const LaunchCtx& L, ImgB cur, ImgB kf, ImgB kf_weight
 void launch_visibility(const LaunchCtx& L, ImgB src, ImgB dst, const Proj* P_dev, Proj P_host,
                        unsigned int* counts, int count_offset, int count_stride, uint8_t* mask, size_t mpitch,
                        size_t mstride, int batch, const int* active = nullptr);
+// the four covisibility passes of a tracked frame in one launch (counts[b * 8 + 2 * pass + {visible, valid}], P[pass * batch + b])
+void launch_visibility4(const LaunchCtx& L, ImgB cur, ImgB kf, ImgB ikf, const Proj* P_dev, unsigned int* counts, int batch);
+bool visibility4_applicable(const ImgB& cur, const ImgB& kf, const ImgB& ikf);
 
 // ---- calib_ops.cu ---------------------------------------------------------------------------------
 void launch_undistort_intensity(const LaunchCtx& L, ImgB src, ImgB dst, const rgbid_intr& intr);

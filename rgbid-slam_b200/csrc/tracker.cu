@@ -658,10 +658,14 @@ static int track_core(rgbid_tracker* t, const uint16_t* depth, const uint8_t* rg
   memset(&dummy, 0, sizeof(dummy));
   const ImgB& Wcur = al->maps[MAP_W_CUR][0];
   const ImgB& Wkf = al->maps[MAP_W_KF][0];
-  launch_visibility(L, Wcur, Wkf, t->d_proj + 0 * B, dummy, t->d_counts, 0, 8, nullptr, 0, 0, B);
-  launch_visibility(L, Wkf, Wcur, t->d_proj + 1 * B, dummy, t->d_counts, 2, 8, nullptr, 0, 0, B);
-  launch_visibility(L, Wcur, t->intWraw, t->d_proj + 2 * B, dummy, t->d_counts, 4, 8, nullptr, 0, 0, B);
-  launch_visibility(L, t->intWraw, Wcur, t->d_proj + 3 * B, dummy, t->d_counts, 6, 8, nullptr, 0, 0, B);
+  if (visibility4_applicable(Wcur, Wkf, t->intWraw)) {
+    launch_visibility4(L, Wcur, Wkf, t->intWraw, t->d_proj, t->d_counts, B);  // both tests, both directions, one launch
+  } else {
+    launch_visibility(L, Wcur, Wkf, t->d_proj + 0 * B, dummy, t->d_counts, 0, 8, nullptr, 0, 0, B);
+    launch_visibility(L, Wkf, Wcur, t->d_proj + 1 * B, dummy, t->d_counts, 2, 8, nullptr, 0, 0, B);
+    launch_visibility(L, Wcur, t->intWraw, t->d_proj + 2 * B, dummy, t->d_counts, 4, 8, nullptr, 0, 0, B);
+    launch_visibility(L, t->intWraw, Wcur, t->d_proj + 3 * B, dummy, t->d_counts, 6, 8, nullptr, 0, 0, B);
+  }
   RGBID_CUDA_TRY(cudaMemcpyAsync(t->h_counts, t->d_counts, sizeof(unsigned int) * 8 * B, cudaMemcpyDeviceToHost, s));
   RGBID_CUDA_TRY(cudaStreamSynchronize(s));
 

@@ -323,7 +323,83 @@ __global__ void __launch_bounds__(256) visibility_vec_kernel(ImgB src, ImgB dst,
   }
 }
 
+// All four covisibility passes of one tracked frame in ONE launch (computeCovisibility is called twice per frame, each
+// a pair of getVisibilityRatio calls in both directions, src/visodo.cpp:1481-1514, 2172-2186):
+//   pass 0  current -> odometry keyframe      pass 1  odometry keyframe -> current
+//   pass 2  current -> integration keyframe   pass 3  integration keyframe -> current
+// Each of the three maps is read once (float4), the 16 projections of a thread's 4 pixels are computed first and their
+// 16 gathers issued together (clamped addresses: memory-level parallelism instead of load-compare-load chains).  The
+// per-pixel test is visibility_vec_kernel's, the counts are integers: bit-identical results.
+// counts[b * 8 + 2 * pass + {0: visible, 1: valid}], transforms P[pass * batch + b].
+__global__ void __launch_bounds__(256) visibility4_vec_kernel(ImgB cur, ImgB kf, ImgB ikf, const Proj* __restrict__ P_dev,
+                                                              unsigned int* __restrict__ counts, int batch)
+{
+  const int b = blockIdx.y;
+  __shared__ Proj sP[4];
+  __shared__ unsigned s_cnt[8];
+  const int tid = threadIdx.x;
+  if (tid < 48) ((float*)&sP[tid / 12])[tid % 12] = ((const float*)&P_dev[(tid / 12) * batch + b])[tid % 12];
+  if (tid < 8) s_cnt[tid] = 0;
+  __syncthreads();
+  const int qpr = cur.cols >> 2, total = qpr * cur.rows;
+  const float xmax = __int2float_rn(cur.cols - 1), ymax = __int2float_rn(cur.rows - 1);
+  unsigned cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int q = blockIdx.x * blockDim.x + tid; q < total; q += gridDim.x * blockDim.x) {
+    const int y = q / qpr, x0 = (q - y * qpr) * 4;
+    float wc[4], wk[4], wi[4];
+    *(float4*)wc = __ldg((const float4*)(cur.row(b, y) + x0));
+    *(float4*)wk = __ldg((const float4*)(kf.row(b, y) + x0));
+    *(float4*)wi = __ldg((const float4*)(ikf.row(b, y) + x0));
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+      const float* src = (pass == 0 || pass == 2) ? wc : (pass == 1 ? wk : wi);
+      const ImgB& dst = (pass == 0) ? kf : (pass == 2 ? ikf : cur);
+      float wd[4], got[4];
+      bool in[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float xd, yd;
+        wd[k] = project_pixel(sP[pass], x0 + k, y, src[k], xd, yd);
+        in[k] = !isnan(src[k]) && xd > 0.f && xd < xmax && yd > 0.f && yd < ymax;
+        const int xi = in[k] ? __float2int_rn(xd) : 0, yi = in[k] ? __float2int_rn(yd) : 0;
+        got[k] = __ldg(dst.row(b, yi) + xi);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        cnt[2 * pass + 1] += isnan(src[k]) ? 0u : 1u;
+        // geom_tol is ignored by the reference: 0.020 is hard-coded (warping_registration.cu:332, :405)
+        cnt[2 * pass + 0] += (in[k] && fabsf(wd[k] - got[k]) < 0.020f) ? 1u : 0u;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    unsigned v = cnt[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0 && v) atomicAdd(&s_cnt[c], v);
+  }
+  __syncthreads();
+  if (tid < 8 && s_cnt[tid]) atomicAdd(&counts[b * 8 + tid], s_cnt[tid]);
+}
+
 }  // namespace
+
+void launch_visibility4(const LaunchCtx& L, ImgB cur, ImgB kf, ImgB ikf, const Proj* P_dev, unsigned int* counts, int batch)
+{
+  const int total = (cur.cols / 4) * cur.rows;
+  int gx = (total + 255) / 256;
+  const int cap = (L.num_sms * 8 + batch - 1) / batch;  // ~8 CTAs of 256 threads per SM over the whole batch
+  if (gx > cap) gx = cap;
+  visibility4_vec_kernel<<<dim3(gx, batch), 256, 0, L.stream>>>(cur, kf, ikf, P_dev, counts, batch);
+  ++*L.launches;
+}
+
+bool visibility4_applicable(const ImgB& cur, const ImgB& kf, const ImgB& ikf)
+{
+  auto ok = [](const ImgB& m) { return (m.cols % 4 == 0) && ((uintptr_t)m.p % 16 == 0) && (m.pitch % 16 == 0) && (m.sstride % 16 == 0); };
+  return ok(cur) && ok(kf) && ok(ikf);
+}
 
 void launch_warp_invdepth(const LaunchCtx& L, ImgB src, ImgB prev, ImgB dst, const Proj& P)
 {

@@ -330,10 +330,14 @@ class Context:
         b = np.zeros(6, dtype=np.float64)
         maps = [W0, I0, gWx, gWy, gIx, gIy, W1, I1]
         pitch = _pitch(W0)
-        assert all(_pitch(m) == pitch for m in maps)
         self._enter()
-        capi.check(self.lib.rgbid_build_system(self.h, *[m.data_ptr() for m in maps], pitch, rows, cols, C.byref(params),
-                                               _dp(A), _dp(b)), "build_system")
+        if all(_pitch(m) == pitch for m in maps):
+            capi.check(self.lib.rgbid_build_system(self.h, *[m.data_ptr() for m in maps], pitch, rows, cols, C.byref(params),
+                                                   _dp(A), _dp(b)), "build_system")
+        else:  # every map with its own row pitch (PtrStep::step of the reference)
+            p8 = (C.c_size_t * 8)(*[_pitch(m) for m in maps])
+            capi.check(self.lib.rgbid_build_system_pitched(self.h, *[m.data_ptr() for m in maps], p8, rows, cols,
+                                                           C.byref(params), _dp(A), _dp(b)), "build_system_pitched")
         return A.reshape(6, 6), b
 
 

@@ -17,7 +17,6 @@ def build():
             os.path.join(LIBDIR, "librgbid_b200.so")]
     if os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         build_app()
-        build_refloop()
         return OUT
     gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     cmd = [gxx, "-O2", "-std=c++17", "-Wall", "-I/usr/local/cuda/include", SRC, "-o", OUT, "-L" + LIBDIR, "-lrgbid_b200",
@@ -26,36 +25,7 @@ def build():
     if r.returncode != 0:
         raise RuntimeError("building test_dropin failed:\n" + r.stderr)
     build_app()
-    build_refloop()
     return OUT
-
-
-def build_refloop():
-    """tests/cpp/librefloop_dropin.so: oracle/ref_shim.cpp (the reference-order host loop, unchanged) compiled against
-    include/rgbid_b200/internal.hpp instead of the reference's src/internal.h, linked with librgbid_b200.so."""
-    src = os.path.join(ROOT, "oracle", "ref_shim.cpp")
-    orc = os.path.join(ROOT, "oracle", "oracle.c")
-    out = os.path.join(ROOT, "tests", "cpp", "librefloop_dropin.so")
-    inc = os.path.join(ROOT, "tests", "cpp", "refloop_include")
-    deps = [src, orc, os.path.join(ROOT, "oracle", "oracle.h"), os.path.join(inc, "internal.h"),
-            os.path.join(ROOT, "include", "rgbid_b200", "internal.hpp"), os.path.join(ROOT, "include", "rgbid_b200", "device_array.hpp"),
-            os.path.join(ROOT, "include", "rgbid_b200.h"), os.path.join(LIBDIR, "librgbid_b200.so")]
-    if os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
-        return out
-    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
-    obj_c = out + ".oracle.o"
-    r = subprocess.run([gcc, "-O2", "-fPIC", "-std=c11", "-ffp-contract=off", "-c", orc, "-o", obj_c], capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("building the refloop library failed:\n" + r.stderr)
-    cmd = [gxx, "-O2", "-fPIC", "-shared", "-std=c++17", "-w", "-I/usr/local/cuda/include", "-I" + os.path.join(ROOT, "oracle"),
-           "-I" + inc, "-I" + os.path.join(ROOT, "include"), src, obj_c, "-o", out, "-L" + LIBDIR, "-lrgbid_b200",
-           "-L/usr/local/cuda/lib64", "-lcudart", "-lm", "-Wl,-rpath," + LIBDIR, "-Wl,-rpath,/usr/local/cuda/lib64"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    os.remove(obj_c)
-    if r.returncode != 0:
-        raise RuntimeError("the reference-order host loop does not compile against include/rgbid_b200/internal.hpp:\n" + r.stderr)
-    return out
 
 
 def build_app():

@@ -74,6 +74,7 @@ class VisodoTracker {
   {
     stop();
     if (trk_) rgbid_tracker_destroy(trk_);
+    if (ctx_) rgbid_ctx_destroy(ctx_);
   }
 
   /** Starts the tracking thread and returns once it is waiting for frames (src/visodo.cpp:437-445).  The grabber
@@ -229,6 +230,10 @@ class VisodoTracker {
     rgbid_frame_result r;
     int rc = rgbid_tracker_track_device(trk_, depth_.ptr(), depth_.step(), 0, (const uint8_t*)rgb24_.ptr(), rgb24_.step(), 0, &r);
     if (rc != RGBID_OK) throw std::runtime_error(std::string("rgbid_tracker_track: ") + rgbid_status_string(rc));
+    // device::sync() at the end of trackNewFrame (src/visodo.cpp:2230): the keyframe colour copy and the fusion queued
+    // behind the last read-back still read rgb24_ / depth_, which the grabber refills (legacy stream) as soon as we return
+    rc = rgbid_ctx_sync(ctx_);
+    if (rc != RGBID_OK) throw std::runtime_error(std::string("rgbid_ctx_sync: ") + rgbid_status_string(rc));
     last_ = r;
     lost_ = (r.status != RGBID_OK);
     const float ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
@@ -373,7 +378,11 @@ class VisodoTracker {
     c.max_odo_kf_count = max_odoKF_count_; c.max_integr_kf_count = max_integrKF_count_;
     c.image_filtering = image_filtering_;
     c.delta_t = 0.03333f;  // computeInterframeTime in evaluation mode, src/visodo.cpp:1932
-    int rc = rgbid_tracker_create(device::thread_context().ctx, &c, &trk_);
+    // The tracker owns its context: a thread-local one would be destroyed with the thread that first tracked a frame
+    // (the tracking thread of start()), while the tracker itself is destroyed by the thread that owns the object.
+    int rc = ctx_ ? RGBID_OK : rgbid_ctx_create(&ctx_, device::dev_id, nullptr);
+    if (rc != RGBID_OK) throw std::runtime_error(std::string("rgbid_ctx_create: ") + rgbid_status_string(rc));
+    rc = rgbid_tracker_create(ctx_, &c, &trk_);
     if (rc != RGBID_OK) throw std::runtime_error(std::string("rgbid_tracker_create: ") + rgbid_status_string(rc));
     rgbid_tracker_set_keyframe_sink(trk_, &VisodoTracker::keyframe_sink, this);
     apply_custom_calibration();
@@ -397,6 +406,7 @@ class VisodoTracker {
   int max_integrKF_count_, Nsamples_;
   float fx_, fy_, cx_, cy_, factor_depth_;
   rgbid_tracker* trk_;
+  rgbid_ctx* ctx_ = nullptr;
   bool lost_;
   bool created_ = false;
   std::unique_ptr<std::thread> visodo_thread_;
@@ -423,8 +433,12 @@ class KeyframeAlign {
  public:
   enum { LEVELS = 4 };  // include/keyframe_align.h:50
 
-  KeyframeAlign() : al_(nullptr), rows_(0), cols_(0) {}
-  ~KeyframeAlign() { if (al_) rgbid_aligner_destroy(al_); }
+  KeyframeAlign() : al_(nullptr), ctx_(nullptr), rows_(0), cols_(0) {}
+  ~KeyframeAlign()
+  {
+    if (al_) rgbid_aligner_destroy(al_);
+    if (ctx_) rgbid_ctx_destroy(ctx_);
+  }
 
   /** alignKeyframes(kf_ini, kf_end, rotation_ini2end, translation_ini2end, covariance_ini2end)
       (include/keyframe_align.h:52-54; src/keyframe_align.cpp:115-357).  R (row-major 3x3) and t hold the initial
@@ -436,7 +450,7 @@ class KeyframeAlign {
     const size_t pitch = (size_t)cols_ * sizeof(float);
     for (size_t i = 0; i < grey_f_.size(); ++i) grey_f_[i] = (float)kf_ini.grey[i];  // cv::Mat::convertTo(CV_32F)
     check(rgbid_aligner_set_keyframe(al_, 0, kf_ini.depthinv, pitch, grey_f_.data(), pitch, 1));
-    check(rgbid_ctx_sync(device::thread_context().ctx));
+    check(rgbid_ctx_sync(ctx_));
     for (size_t i = 0; i < grey_f_.size(); ++i) grey_f_[i] = (float)kf_end.grey[i];
     check(rgbid_aligner_set_current(al_, 0, kf_end.depthinv, pitch, grey_f_.data(), pitch, 1));
     int status = 0;
@@ -463,9 +477,11 @@ class KeyframeAlign {
     c.nsamples = 19200;  // src/keyframe_align.cpp:247-248
     c.fx = (float)kf.K[0]; c.fy = (float)kf.K[4]; c.cx = (float)kf.K[2]; c.cy = (float)kf.K[5];
     c.factor_depth = 1.f;
-    check(rgbid_aligner_create(device::thread_context().ctx, &c, &al_));
+    if (!ctx_) check(rgbid_ctx_create(&ctx_, device::dev_id, nullptr));  // owned: see VisodoTracker::ensure_created
+    check(rgbid_aligner_create(ctx_, &c, &al_));
   }
   rgbid_aligner* al_;
+  rgbid_ctx* ctx_;
   int rows_, cols_;
   double K_[9];
   std::vector<float> grey_f_;

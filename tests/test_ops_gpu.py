@@ -296,6 +296,32 @@ def test_build_system(ctx, P, pose, student_nu, mest, weighting):
         assert sums_rel_err(sg, sr) < 1e-5
 
 
+def test_build_system_mixed_pitches(ctx, P, pose):
+    """The warped maps come from cudaMallocPitch in the reference's drivers while the keyframe maps are dense: every
+    PtrStep carries its own step (rgbid_build_system_pitched)."""
+    from rgbid_slam_b200 import capi
+    W1, I1 = _warped(P, pose)
+    gWx, gWy = orc.gradient(P["WA"])
+    gIx, gIy = orc.gradient(P["IA"])
+    i = P["intr"]
+    pg = capi.SystemParams(i["fx"], i["fy"], i["cx"], i["cy"], 3, 0, 1, 0.0012, 3.5, 1e-5, 0.2, 4.25, 6.5)
+    dense = [cuda(m) for m in (P["WA"], P["IA"], gWx, gWy, gIx, gIy, W1, I1)]
+    A0, b0 = ctx.build_system(*dense, pg)
+
+    def padded(m, extra):
+        buf = torch.full((m.shape[0], m.shape[1] + extra), float("nan"), device="cuda")
+        buf[:, :m.shape[1]] = m
+        return buf[:, :m.shape[1]]
+    mixed = [padded(m, e) for m, e in zip(dense, (0, 0, 0, 0, 0, 0, 64, 64))]
+    mixed[2] = padded(dense[2], 4)
+    mixed[5] = padded(dense[5], 3)     # 12 bytes more per row: not 16-byte aligned rows -> the scalar kernel
+    A1, b1 = ctx.build_system(*mixed[:6], mixed[6], mixed[7], pg)
+    assert np.max(np.abs(A1 - A0)) <= 1e-5 * np.max(np.abs(A0)) and np.max(np.abs(b1 - b0)) <= 1e-5 * np.max(np.abs(b0))
+    mixed[5] = padded(dense[5], 8)     # all rows 16-byte aligned: the float4 kernel, bit-identical sums
+    A2, b2 = ctx.build_system(*mixed[:6], mixed[6], mixed[7], pg)
+    assert np.array_equal(A2, A0) and np.array_equal(b2, b0)
+
+
 def test_build_system_all_invalid(ctx):
     from rgbid_slam_b200 import capi
     z = torch.full((16, 32), float("nan")).cuda()

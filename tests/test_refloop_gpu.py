@@ -2,7 +2,7 @@
 reference's own order (src/visodo.cpp:1041-1415, src/keyframe_align.cpp:178-350, trackNewFrame's image preparation,
 covisibility and fusion calls) -- is compiled a second time, UNCHANGED, against include/rgbid_b200/internal.hpp
 (through tests/cpp/refloop_include/internal.h) and linked with librgbid_b200.so (tests/cpp/librefloop_dropin.so, built by
-rgbid-slam_b200/host/build_host.py).  The same translation unit built on the reference's own kernels is
+tests/cpp/build_refloop.py).  The same translation unit built on the reference's own kernels is
 oracle/_ref/libref_oracle.so; both must produce the same results."""
 import contextlib
 import ctypes as C
