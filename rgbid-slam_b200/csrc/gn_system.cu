@@ -148,18 +148,22 @@ __device__ __forceinline__ void accumulate_pixel(float* __restrict__ acc, int x,
 struct BuildShared {
   double warp_part[kBuildWarps][kAccChi];
   double total[kAccChi];
-  double fin[kBuildWarps][kAccChi];
   Proj proj;
-  int is_last;
 };
 
 // Block reduce + publish the per-CTA partial + elect the last CTA of this pair + fixed-order final sum.
-// Returns true in every thread of the last CTA, with sh.total[0..NACC) holding the pair's sums.
+// Returns true in the threads of WARP 0 of the last CTA (false everywhere else), with sh.total[0..NACC) holding the
+// pair's sums.
 //
 // wscratch: NACC x 32 floats of shared memory owned by the calling WARP.  The lane sums go through it instead of
 // through shuffles: a double butterfly costs 10 SHFL + 5 DADD per value (27 values: 400 instructions per warp, at one
 // SHFL per clock per SM -- RGBID_TAIL_PROBE showed ~14 000 clocks between the end of the pixel loop and the election);
 // here lane k adds the 32 lane values of sum k in double (4 chains of 8, rotated start: conflict-free banks), fixed order.
+//
+// After the one CTA-wide barrier everything is done by warp 0 alone -- cross-warp sum, partial store, ONE cumulative
+// fence + ticket by lane 0 behind a warp barrier (instead of a fence in each of the 27 storing threads, a second fence
+// in all 256 and three more CTA barriers: RGBID_TAIL_PROBE showed 12 000 clocks from the end of the loop to the start of
+// the solve), then, in the last CTA, the fixed-order final sum with every lane's loads in flight together.
 template <int NACC>
 __device__ __forceinline__ bool reduce_and_elect(BuildShared& sh, const float* acc, float* wscratch,
                                                  double* __restrict__ partials, int partial_stride,
@@ -182,37 +186,38 @@ __device__ __forceinline__ bool reduce_and_elect(BuildShared& sh, const float* a
     sh.warp_part[wid][lane] = (s0 + s1) + (s2 + s3);
   }
   __syncthreads();
-  if (tid < NACC) {
+  if (wid != 0) return false;
+  if (lane < NACC) {
     double v = 0.0;
 #pragma unroll
-    for (int w = 0; w < kBuildWarps; ++w) v += sh.warp_part[w][tid];
-    partials[(size_t)blk * partial_stride + tid] = v;
+    for (int w = 0; w < kBuildWarps; ++w) v += sh.warp_part[w][lane];
+    partials[(size_t)blk * partial_stride + lane] = v;
+  }
+  __syncwarp();  // orders the 27 stores before lane 0's fence (the fence is cumulative)
+  unsigned ticket = 0;
+  if (lane == 0) {
     __threadfence();
+    ticket = atomicAdd(counter, 1u);
+    __threadfence();  // the other CTAs' partials are visible to the loads below (ordered behind the warp barrier)
   }
-  __syncthreads();
-  if (tid == 0) {
-    unsigned ticket = atomicAdd(counter, 1u);
-    sh.is_last = (ticket == (unsigned)(nblk - 1));
+  ticket = __shfl_sync(0xffffffffu, ticket, 0);
+  if (ticket != (unsigned)(nblk - 1)) return false;
+  // fixed-order final sum: lane k owns value k; four independent chains over the CTAs, combined in order
+  if (lane < NACC) {
+    const double* col = partials + lane;
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+    int c = 0;
+#pragma unroll 2
+    for (; c + 4 <= nblk; c += 4) {
+      const double a0 = __ldcg(col + (size_t)(c + 0) * partial_stride), a1 = __ldcg(col + (size_t)(c + 1) * partial_stride);
+      const double a2 = __ldcg(col + (size_t)(c + 2) * partial_stride), a3 = __ldcg(col + (size_t)(c + 3) * partial_stride);
+      v0 += a0; v1 += a1; v2 += a2; v3 += a3;
+    }
+    for (; c < nblk; ++c) v0 += __ldcg(col + (size_t)c * partial_stride);
+    sh.total[lane] = (v0 + v1) + (v2 + v3);
   }
-  __syncthreads();
-  if (!sh.is_last) return false;
-  __threadfence();
-  // fixed-order final sum: value k is summed by 8 threads over interleaved CTAs, then combined in order
-  const int k = tid % 32, part = tid / 32;  // NACC <= 32, kBuildWarps parts
-  if (k < NACC) {
-    double v = 0.0;
-    for (int c = part; c < nblk; c += kBuildWarps) v += __ldcg(&partials[(size_t)c * partial_stride + k]);
-    sh.fin[part][k] = v;
-  }
-  __syncthreads();
-  if (tid < NACC) {
-    double v = 0.0;
-#pragma unroll
-    for (int p = 0; p < kBuildWarps; ++p) v += sh.fin[p][tid];
-    sh.total[tid] = v;
-  }
-  __syncthreads();
-  if (tid == 0) *counter = 0u;  // ready for the next launch
+  if (lane == 0) *counter = 0u;  // ready for the next launch
+  __syncwarp();
   return true;
 }
 
@@ -584,9 +589,6 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
   __shared__ __align__(8) unsigned long long bars[kBuildWarps * (kStagesW + kStagesL)];
   const int b = blockIdx.y + P.first;
   GnState& st = states[b];
-#if RGBID_TAIL_PROBE
-  const long long probe_t0 = clock64();
-#endif
   const int tid = threadIdx.x, lane = tid & 31;
   const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: bulk-copy operands stay in uniform registers
   if (tid == 0) {
@@ -642,6 +644,9 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
       if (i < my_n) issue_l(i);
   }
   grid_dep_wait();
+#if RGBID_TAIL_PROBE
+  const long long probe_t0 = clock64();  // the pixel loop is counted from the end of the dependency wait
+#endif
   // a skipped pair leaves with its bulk copies in flight: they land in this CTA's own shared memory, which stays
   // allocated until the copies have completed
   const bool skipped = pair_skipped(st, P);
