@@ -1,5 +1,5 @@
 """Workload for ncu captures: a few tracker steps of the bench configuration (see /opt/skills/guides/B200_PROFILING.md).
-Usage: python tools/profile_step.py [streams] [frames]"""
+Usage: python tools/profile_step.py [streams] [frames] [pyrFirst|warpFirst]"""
 import os
 import sys
 
@@ -21,7 +21,9 @@ def main():
     depth, rgb, intr = bench.make_frames(A, list(range(S)), n, "cuda")
     ctx = host.Context(0)
     its = host.default_iterations(A.levels, capi.MODE_TRACKER)
-    acfg = host.make_align_config(A.rows, A.cols, A.levels, capi.MODE_TRACKER, batch=S, iterations=its, **intr)
+    warp_first = 1 if (len(sys.argv) > 3 and sys.argv[3] == "warpFirst") else 0
+    acfg = host.make_align_config(A.rows, A.cols, A.levels, capi.MODE_TRACKER, batch=S, iterations=its, warp_first=warp_first,
+                                  **intr)
     trk = host.Tracker(ctx, host.make_tracker_config(acfg))
     for k in range(n):
         trk.track(depth[k], rgb[k])
