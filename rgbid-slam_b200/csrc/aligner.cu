@@ -236,6 +236,8 @@ int rgbid_aligner_create(rgbid_ctx* ctx, const rgbid_align_config* cfg, rgbid_al
   if (cfg->termination < RGBID_TERM_ALL_ITERS || cfg->termination > RGBID_TERM_CONVERGENCE) return RGBID_ERR_ARG;
   if (cfg->termination == RGBID_TERM_CONVERGENCE && !(cfg->conv_eps > 0.f)) return RGBID_ERR_ARG;
   RGBID_CUDA_TRY(cudaSetDevice(ctx->device));
+  // constant tables and kernel attributes now, outside any stream capture (the upload is a synchronous legacy-stream copy)
+  if (int e = gn_prepare_device()) return RGBID_ERR_CUDA_BASE + e;
   rgbid_aligner* al = new (std::nothrow) rgbid_aligner();
   if (!al) return RGBID_ERR_NOMEM;
   memset(al, 0, sizeof(*al));

@@ -1,5 +1,5 @@
 // bulk_copy.cuh -- sm_100a asynchronous bulk copies (TMA engine, SASS: UBLKCP) with mbarrier completion, and the
-// packed-FP32 (f32x2) arithmetic used by the fused Gauss-Newton kernel.
+// predicated FMA used by the fused Gauss-Newton kernel.
 //
 // The keyframe maps are flat fp32 arrays (pitch == cols * 4), so a warp's slice of a tile is one contiguous
 // 512-byte segment per map: a 1-D bulk copy needs no tensor map and is issued by a single lane.
@@ -70,40 +70,8 @@ __device__ __forceinline__ float4 lds128(uint32_t addr)
   return v;
 }
 
-// ---- packed FP32 pairs (FFMA2 / FMUL2: one issue slot for two lanes of the FMA pipe) -------------------------
-typedef unsigned long long f32x2;
-
-__device__ __forceinline__ f32x2 pack2(float lo, float hi)
-{
-  f32x2 r;
-  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-
-__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi)
-{
-  asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
-{
-  f32x2 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-
-__device__ __forceinline__ void fma2(f32x2& d, f32x2 a, f32x2 b)
-{
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
-}
-
 // d += a * b where flag != 0 (predicated, not branched: invalid pixels carry NaN operands that must not be
 // accumulated, and a branch per pixel and constraint would serialise the four pixels of a thread)
-__device__ __forceinline__ void pfma2(f32x2& d, f32x2 a, f32x2 b, int flag)
-{
-  asm("{\n.reg .pred p;\nsetp.ne.s32 p, %3, 0;\n@p fma.rn.f32x2 %0, %1, %2, %0;\n}" : "+l"(d) : "l"(a), "l"(b), "r"(flag));
-}
-
 __device__ __forceinline__ void pfma(float& d, float a, float b, int flag)
 {
   asm("{\n.reg .pred p;\nsetp.ne.s32 p, %3, 0;\n@p fma.rn.f32 %0, %1, %2, %0;\n}" : "+f"(d) : "f"(a), "f"(b), "r"(flag));

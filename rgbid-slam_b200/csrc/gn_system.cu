@@ -486,13 +486,6 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
 // Arithmetic differs from the generic kernel only in rounding (same formulas re-associated); the parity tests
 // hold both against the oracle and the reference's own kernels.
 // ------------------------------------------------------------------------------------------------------------
-// RGBID_ACC2=1 selects the packed (FFMA2) accumulation.  Measured on B200 (tools/ubench/pipes.cu): an FFMA2 on three
-// distinct register pairs issues every 3.1 clk per SMSP -- the same FP32 rate as scalar FFMAs on distinct registers
-// (0.68 / clk) -- so packing saves issue slots but no FMA-pipe time, and this kernel is FMA-pipe bound: the packed
-// variant (178 instead of 195 instructions per pixel) is not faster (90.2 vs 89.3 us).  Kept as an experiment.
-#ifndef RGBID_ACC2
-#define RGBID_ACC2 0
-#endif
 #ifndef RGBID_TAIL_PROBE
 #define RGBID_TAIL_PROBE 0  // gn_build_fast_kernel: clock64 break-down of the last CTA (diagnostic build only)
 #endif
@@ -522,45 +515,6 @@ struct FastGeom {
   int nchunks;    // ceil(npx / 128)
   float colsf, rowsf, inv_cols;
 };
-
-// the 27 sums in the reference's order from the 15 packed accumulators (see accumulate_packed)
-__device__ __forceinline__ void unpack_acc(const f32x2* a2, float* acc)
-{
-  float lo[15], hi[15];
-#pragma unroll
-  for (int k = 0; k < 15; ++k) unpack2(a2[k], lo[k], hi[k]);
-  // row 0: 00 01 02 03 04 05 0e
-  acc[0] = lo[0]; acc[1] = lo[1]; acc[2] = lo[2]; acc[3] = lo[3]; acc[kPx] = lo[kPx]; acc[5] = lo[5]; acc[6] = lo[12];
-  // row 1: 11 12 13 14 15 1e
-  acc[7] = hi[0]; acc[8] = hi[3]; acc[9] = hi[2]; acc[10] = hi[5]; acc[11] = hi[kPx]; acc[12] = hi[12];
-  // row 2: 22 23 24 25 2e
-  acc[13] = lo[6]; acc[14] = lo[7]; acc[15] = lo[8]; acc[16] = lo[9]; acc[17] = lo[13];
-  // row 3: 33 34 35 3e
-  acc[18] = hi[6]; acc[19] = hi[9]; acc[20] = hi[8]; acc[21] = hi[13];
-  // row 4: 44 45 4e ; row 5: 55 5e
-  acc[22] = lo[10]; acc[23] = lo[11]; acc[24] = lo[14];
-  acc[25] = hi[10]; acc[26] = hi[14];
-}
-
-// acc2 += s * (r, e) (r, e)^T restricted to the 27 needed terms; rows as pairs A = (r0, r1), B = (r2, r3),
-// C = (r4, r5).  Cross products of two different pairs fill both lanes (X * Y and X * swap(Y)); the three
-// within-pair products waste one lane each.  FFMA2 cannot be predicated (ptxas turns a predicated one into FFMA2 +
-// two selects), so the caller passes s = 0 and FINITE rows for an invalid pixel.
-__device__ __forceinline__ void accumulate_packed(f32x2* a2, float s, float r0, float r1, float r2, float r3, float r4,
-                                                  float r5, float e)
-{
-  const f32x2 A = pack2(r0, r1), B = pack2(r2, r3), C = pack2(r4, r5);
-  const f32x2 As = pack2(r1, r0), Bs = pack2(r3, r2), Cs = pack2(r5, r4);
-  const f32x2 S = pack2(s, s), E = pack2(e, e);
-  const f32x2 sA = mul2(S, A), sB = mul2(S, B), sC = mul2(S, C);
-  fma2(a2[0], sA, A);   fma2(a2[1], sA, As);
-  fma2(a2[2], sA, B);   fma2(a2[3], sA, Bs);
-  fma2(a2[kPx], sA, C);   fma2(a2[5], sA, Cs);
-  fma2(a2[6], sB, B);   fma2(a2[7], sB, Bs);
-  fma2(a2[8], sB, C);   fma2(a2[9], sB, Cs);
-  fma2(a2[10], sC, C);  fma2(a2[11], sC, Cs);
-  fma2(a2[12], sA, E);  fma2(a2[13], sB, E);  fma2(a2[14], sC, E);
-}
 
 __device__ __forceinline__ void accumulate_scalar(float* acc, float s, const float* r, float e, int flag)
 {
@@ -675,15 +629,9 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
   const float ifx = 1.f / P.fx, ify = 1.f / P.fy;
   const cudaTextureObject_t texW = M.texW[b], texI = M.texI[b];
 
-#if RGBID_ACC2
-  f32x2 acc2[15];
-#pragma unroll
-  for (int k = 0; k < 15; ++k) acc2[k] = 0ull;
-#else
   float accs[kAcc];
 #pragma unroll
   for (int k = 0; k < kAcc; ++k) accs[k] = 0.f;
-#endif
   float chi[4] = {0.f, 0.f, 0.f, 0.f};
 
   // Software pipeline over this warp's chunks.  With 128 registers only four warps share a scheduler, so the two
@@ -818,23 +766,6 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
       // n . p = 1 identically (g2 = -(g0 px + g1 py)), so n_factor = |n . p| / (|n| |p|) = |w0| / (|m| |p|) with
       // m = (g0, g1, g2 + w0).
       const float gd0 = gwx[k] * P.fx, gd1 = gwy[k] * P.fy;
-#if RGBID_ACC2
-      // rows from sanitised inputs (NaN -> a finite value that a zero weight annihilates), weight from the raw ones
-      // (NaN propagates into sd and fmaxf(sd, 0) turns it into 0)
-      const float gs0 = fmaxf(gd0, -1e30f), gs1 = fmaxf(gd1, -1e30f);
-      const float w0s = fmaxf(w0[k], 0.f), w1s = fmaxf(w1[k], 0.f);
-      const float gs2 = -fmaf(gs0, px, gs1 * py);
-      const float m2 = gs2 + w0[k];
-      const float mm = fmaf(gd0, gd0, fmaf(gd1, gd1, m2 * m2));
-      const float nf = fabsf(w0[k]) * rsqrtf(mm * fmaf(px, px, py2p1));
-      const float h2 = gs2 + w1s;
-      float rd[6];
-      rd[0] = gs0 * w0s; rd[1] = gs1 * w0s; rd[2] = h2 * w0s;
-      rd[3] = fmaf(h2, py, -gs1); rd[kPx] = fmaf(-h2, px, gs0); rd[5] = fmaf(gs1, px, -(gs0 * py));
-      const float ed = w0s - w1s;
-      const float eud = fmaf(w0[k] - w1[k], is_d, -bos_d);
-      const float sd = fmaxf(nf * (c_d * (1.f / fmaf(eud, eud, nu_d))), 0.f);
-#else
       const float gd2 = -fmaf(gd0, px, gd1 * py);
       const float m2 = gd2 + w0[k];
       const float mm = fmaf(gd0, gd0, fmaf(gd1, gd1, m2 * m2));
@@ -847,7 +778,6 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
       const float eud = fmaf(ed, is_d, -bos_d);
       const float sd = nf * (c_d * (1.f / fmaf(eud, eud, nu_d)));  // NaN if any of w0, w1, gwx, gwy is NaN
       const int fd = (sd > 0.f);
-#endif
       if (CHI) {
         // end-of-frame chi^2 on all finite full-resolution residuals (src/visodo.cpp:1411-1414,
         // sigmaFuncs.cu:137-150, 541-611) with the reference scales 5 / 0.0025
@@ -856,11 +786,7 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
           if (!(isnan(cd) || isinf(cd))) { chi[2] += chi_rho_dev(cd, chi_mest); chi[3] += 1.f; }
         }
       }
-#if RGBID_ACC2
-      accumulate_packed(acc2, sd, rd[0], rd[1], rd[2], rd[3], rd[kPx], rd[5], ed);
-#else
       accumulate_scalar(accs, sd, rd, ed, fd);
-#endif
     }
 
     // --- S3: intensity constraint + accumulation ---------------------------------------------------------------
@@ -877,18 +803,6 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
       const float i1v = fmaxf(0.f, fminf(i1[k], 255.f)) + pin[k];
       // intensityConstraint (estimate_VO.cu:176-212)
       const float gi0 = gix[k] * P.fx, gi1 = giy[k] * P.fy;
-#if RGBID_ACC2
-      const float gs0 = fmaxf(gi0, -1e30f), gs1 = fmaxf(gi1, -1e30f), w0s = fmaxf(w0[k], 0.f);
-      const float gs2 = -fmaf(gs0, px, gs1 * py);
-      float ri[6];
-      ri[0] = gs0 * w0s; ri[1] = gs1 * w0s; ri[2] = gs2 * w0s;
-      ri[3] = fmaf(gs2, py, -gs1); ri[kPx] = fmaf(-gs2, px, gs0); ri[5] = fmaf(gs1, px, -(gs0 * py));
-      const float ei_raw = i0[k] - i1v;
-      const float ei = fmaxf(ei_raw, -1e30f);
-      const float eui = fmaf(ei_raw, is_i, -bos_i);
-      // NaN gradients invalidate the row (a NaN w0 gives a NaN i1; i0 and i1 enter ei)
-      const float si = fmaxf(fmaf(0.f, gi0 + gi1, c_i * (1.f / fmaf(eui, eui, nu_i))), 0.f);
-#else
       const float gi2 = -fmaf(gi0, px, gi1 * py);
       float ri[6];
       ri[0] = gi0 * w0[k]; ri[1] = gi1 * w0[k]; ri[2] = gi2 * w0[k];
@@ -898,18 +812,13 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
       float si = c_i * (1.f / fmaf(eui, eui, nu_i));
       si = fmaf(0.f, gi2, si);  // NaN gradients invalidate the row (a NaN w0 gives a NaN i1, i0 and i1 enter ei)
       const int fi = (si > 0.f);
-#endif
       if (CHI) {
         if (P.chi_mestimator >= 0) {
           const float ci = (i1v - i0[k]) / 5.f;
           if (!(isnan(ci) || isinf(ci))) { chi[0] += chi_rho_dev(ci, chi_mest); chi[1] += 1.f; }
         }
       }
-#if RGBID_ACC2
-      accumulate_packed(acc2, si, ri[0], ri[1], ri[2], ri[3], ri[kPx], ri[5], ei);
-#else
       accumulate_scalar(accs, si, ri, ei, fi);
-#endif
     }
     __syncwarp();
     if (elect_one()) {
@@ -924,12 +833,8 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
   grid_dep_launch();  // the next kernel's CTAs may take the slots this grid frees while its last CTAs reduce and solve
 
   float acc[NACC];
-#if RGBID_ACC2
-  unpack_acc(acc2, acc);
-#else
 #pragma unroll
   for (int k = 0; k < kAcc; ++k) acc[k] = accs[k];
-#endif
   if (CHI) { acc[27] = chi[0]; acc[28] = chi[1]; acc[29] = chi[2]; acc[30] = chi[3]; }
   // every bulk copy this warp issued has been waited for and consumed: its ring (10 KiB) is free for the lane sums
   float* wscratch = (float*)(ring + (size_t)wid * kWarpRingBytes);
@@ -1128,6 +1033,24 @@ int gn_build_grid_x(int rows, int cols, int batch, int num_sms)
   return g < 1 ? 1 : g;
 }
 
+int gn_prepare_device()
+{
+  static PerDevice prepared;
+  cudaError_t err = cudaSuccess;
+  prepared.once([&err] {
+    if (!upload_nu_table()) { err = cudaGetLastError(); if (err == cudaSuccess) err = cudaErrorUnknown; return false; }
+    cudaError_t e = cudaSuccess;
+#define RGBID_FAST_ATTR(T, C) \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gn_build_fast_kernel<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes)
+    RGBID_FAST_ATTR(true, 0); RGBID_FAST_ATTR(true, 1); RGBID_FAST_ATTR(true, 2);
+    RGBID_FAST_ATTR(false, 0); RGBID_FAST_ATTR(false, 1); RGBID_FAST_ATTR(false, 2);
+#undef RGBID_FAST_ATTR
+    err = e;
+    return e == cudaSuccess;
+  });
+  return (int)err;
+}
+
 void launch_export_systems(const LaunchCtx& L, const GnState* states, double* out, int batch)
 {
   export_systems_kernel<<<batch, 64, 0, L.stream>>>(states, out, batch);
@@ -1146,8 +1069,8 @@ void launch_gn_scale(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P
   const int n = P.kept_rows * P.kept_cols;
   const int chunk = (n + kScaleCluster - 1) / kScaleCluster;
   size_t smem = (size_t)2 * chunk * sizeof(float);
-  static PerDevice table, smem_limit;
-  table.once([] { upload_nu_table(); });
+  static PerDevice smem_limit;
+  gn_prepare_device();  // no-op after rgbid_aligner_create
   if (smem > 48 * 1024)
     smem_limit.at_least(smem, [](size_t bytes) {
       cudaFuncSetAttribute(gn_scale_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -1201,15 +1124,7 @@ void launch_gn_build(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P
     int gx = (G.nchunks + kBuildWarps - 1) / kBuildWarps;
     if (gx > cap) gx = cap;
     dim3 grid(gx, P.batch);
-    static PerDevice configured;
-    configured.once([] {
-      cudaFuncSetAttribute(gn_build_fast_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
-      cudaFuncSetAttribute(gn_build_fast_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
-      cudaFuncSetAttribute(gn_build_fast_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
-      cudaFuncSetAttribute(gn_build_fast_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
-      cudaFuncSetAttribute(gn_build_fast_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
-      cudaFuncSetAttribute(gn_build_fast_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
-    });
+    gn_prepare_device();  // no-op after rgbid_aligner_create
     const bool tracker = (P.mode == RGBID_MODE_TRACKER);
     const int chim = !chi ? 0 : (P.chi_mestimator == RGBID_STUDENT ? 2 : 1);
 #define RGBID_FAST_LAUNCH(T, C) \

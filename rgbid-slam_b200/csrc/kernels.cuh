@@ -33,7 +33,8 @@ inline cudaError_t launch_kernel_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
 
 // One-time set-up that lives in a device's context (constant tables, kernel attributes) has to happen once per DEVICE
 // the process uses, not once per process, and two host threads may get here together (the tracker and the keyframe
-// aligner call concurrently).  `once(f)` runs f the first time it is called with a given device current.
+// aligner call concurrently).  `once(f)` runs f the first time it is called with a given device current; f
+// returns whether it succeeded, and a failed set-up is retried by the next call instead of being marked done.
 class PerDevice {
  public:
   template <class F>
@@ -41,7 +42,7 @@ class PerDevice {
   {
     std::lock_guard<std::mutex> guard(mu_);
     const unsigned long long bit = 1ull << (current() & 63);
-    if (!(done_ & bit)) { f(); done_ |= bit; }
+    if (!(done_ & bit) && f()) done_ |= bit;
   }
   // grow-only variant: runs f(value) whenever `value` exceeds what this device has been configured for
   template <class F>
@@ -211,6 +212,9 @@ void launch_gn_build(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P
 void launch_gn_init(const LaunchCtx& L, GnState* states, const double* R_init, const double* t_init, int batch,
                     int levels, float fx0, float fy0, float cx0, float cy0);
 int gn_build_grid_x(int rows, int cols, int batch, int num_sms);
+// One-time per-device set-up of the Gauss-Newton kernels (nu table in constant memory, dynamic shared-memory limits).
+// rgbid_aligner_create calls it, so that nothing of it can fall inside a stream capture; returns a cudaError_t value.
+int gn_prepare_device();
 // [batch][48] doubles (cov 36, R 9, t 3) from the solver state; NaN for lost pairs
 void launch_export_systems(const LaunchCtx& L, const GnState* states, double* out, int batch);
 

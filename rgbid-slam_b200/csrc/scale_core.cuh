@@ -42,7 +42,7 @@ static inline double digamma_host(double x)
 
 // Must be called once per translation unit that launches a kernel using c_nu_float (the table has internal
 // linkage, so this function must too).
-static void upload_nu_table()
+static bool upload_nu_table()
 {
   NuTerms h[17];
   for (int k = 0; k < 17; ++k) {
@@ -53,7 +53,7 @@ static void upload_nu_table()
     h[k].psi_half1 = (float)digamma_host((double)b);
     h[k].log_half1 = logf(b);
   }
-  cudaMemcpyToSymbol(c_nu_table, h, sizeof(h));
+  return cudaMemcpyToSymbol(c_nu_table, h, sizeof(h)) == cudaSuccess;  // synchronous, legacy stream: never inside a capture
 }
 
 __device__ __forceinline__ float c_nu_float(float nu, float fw)

@@ -91,7 +91,7 @@ void launch_scale_from_errors(const LaunchCtx& L, const float* err0, const float
                               float bias0, float sigma0, float bias1, float sigma1, ScaleState* out)
 {
   static PerDevice table;
-  table.once([] { upload_nu_table(); });
+  table.once([] { return upload_nu_table(); });
   scale_from_errors_kernel<<<kScaleCluster, kScaleThreads, 0, L.stream>>>(err0, err1, n, op, mest, bias0, sigma0,
                                                                           bias1, sigma1, out);
   ++*L.launches;

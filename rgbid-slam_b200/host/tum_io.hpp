@@ -51,16 +51,24 @@ inline bool read_png(const std::string& path, Image& img)
   if (buf.size() < 8 || memcmp(buf.data(), sig, 8) != 0) return false;
   size_t pos = 8;
   int width = 0, height = 0, bit_depth = 0, color_type = 0, interlace = 0;
+  bool have_ihdr = false;
   std::vector<uint8_t> idat;
+  // The files come from user-supplied dataset folders: every length is checked before it is used.  (Chunk CRCs are
+  // not verified; the zlib stream carries its own Adler-32, which uncompress() checks.)
   while (pos + 12 <= buf.size()) {
-    uint32_t len = be32(&buf[pos]);
+    const size_t len = be32(&buf[pos]);
     const char* type = (const char*)&buf[pos + 4];
-    if (pos + 12 + len > buf.size()) return false;
+    if (len > buf.size() - pos - 12) return false;  // truncated chunk
     const uint8_t* d = &buf[pos + 8];
     if (!memcmp(type, "IHDR", 4)) {
-      width = (int)be32(d); height = (int)be32(d + 4);
+      if (len != 13 || have_ihdr) return false;
+      const uint32_t w = be32(d), h = be32(d + 4);
+      if (w == 0 || h == 0 || w > 16384 || h > 16384) return false;  // bounds the allocations below
+      width = (int)w; height = (int)h;
       bit_depth = d[8]; color_type = d[9]; interlace = d[12];
+      have_ihdr = true;
     } else if (!memcmp(type, "IDAT", 4)) {
+      if (!have_ihdr) return false;
       idat.insert(idat.end(), d, d + len);
     } else if (!memcmp(type, "IEND", 4)) {
       break;
@@ -68,7 +76,7 @@ inline bool read_png(const std::string& path, Image& img)
     pos += 12 + len;
   }
   int channels = color_type == 0 ? 1 : color_type == 2 ? 3 : color_type == 6 ? 4 : color_type == 4 ? 2 : 0;
-  if (width <= 0 || height <= 0 || channels == 0 || interlace != 0 || (bit_depth != 8 && bit_depth != 16)) return false;
+  if (!have_ihdr || idat.empty() || channels == 0 || interlace != 0 || (bit_depth != 8 && bit_depth != 16)) return false;
   const size_t bpp = (size_t)channels * bit_depth / 8, stride = bpp * width;
   std::vector<uint8_t> raw((stride + 1) * height);
   uLongf out_len = (uLongf)raw.size();

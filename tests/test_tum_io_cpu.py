@@ -57,3 +57,37 @@ def test_sequence_reader_matches_opencv(built, tmp_path, use_match_file):
     w = np.sqrt(1 + np.trace(R)) / 2
     want = np.array([(R[2, 1] - R[1, 2]) / (4 * w), (R[0, 2] - R[2, 0]) / (4 * w), (R[1, 0] - R[0, 1]) / (4 * w), w])
     assert np.allclose(q, want, atol=1e-5)
+
+
+@pytest.mark.parametrize("damage", ["truncated_ihdr", "huge_size", "idat_before_ihdr", "cut_file"])
+def test_malformed_png_is_a_failed_grab_not_a_crash(built, tmp_path, damage):
+    """The PNG reader runs on user-supplied dataset folders: every chunk length is checked before it is used."""
+    import struct
+    import zlib
+    assert os.path.exists(APP), "apps/rgbid_slam_app was not built (see __graft_entry__.build)"
+    seq = synth.make_sequence(seed=6, n_frames=2, rows=48, cols=64, noise=False)
+    folder = str(tmp_path / "fr_bad")
+    synth.write_tum_sequence(seq, folder)
+    path = os.path.join(folder, "depth", "1000.000000.png")
+    raw = open(path, "rb").read()
+
+    def chunk(kind, body):
+        return struct.pack(">I", len(body)) + kind + body + struct.pack(">I", zlib.crc32(kind + body) & 0xffffffff)
+    sig, rest = raw[:8], raw[8:]
+    ihdr_body = rest[8:8 + 13]
+    after_ihdr = rest[8 + 13 + 4:]
+    if damage == "truncated_ihdr":      # IHDR of 8 bytes: d[8], d[9], d[12] would be read past the chunk
+        bad = sig + chunk(b"IHDR", ihdr_body[:8]) + after_ihdr
+    elif damage == "huge_size":         # 2^31 - 1 by 2^31 - 1 pixels
+        bad = sig + chunk(b"IHDR", struct.pack(">II", 0x7fffffff, 0x7fffffff) + ihdr_body[8:]) + after_ihdr
+    elif damage == "idat_before_ihdr":
+        bad = sig + chunk(b"IDAT", zlib.compress(b"\0" * 64)) + rest
+    else:                               # file cut in the middle of a chunk
+        bad = raw[:len(raw) // 2]
+    open(path, "wb").write(bad)
+    r = subprocess.run([APP, "-check_io", "-eval", folder + "/", "-match_file", "matches.txt"], capture_output=True, text=True,
+                       timeout=60)
+    assert r.returncode == 0, (r.returncode, r.stdout + r.stderr)
+    lines = r.stdout.strip().splitlines()
+    assert lines[1] == "frame 0 grab failed", lines[:3]
+    assert lines[2].startswith("frame 1 ") and "grab failed" not in lines[2]
