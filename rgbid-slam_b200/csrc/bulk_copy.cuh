@@ -34,6 +34,23 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
+// The same with an L2 eviction policy.  The fused kernel streams each keyframe map exactly once per launch (236 MB per
+// launch against a 126 MB L2): marked evict-first they pass through without displacing the current-frame maps its
+// texture gathers re-read every iteration, the solver state, the partial sums and the kernels' own instructions.
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+               : "memory");
+}
+
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
   asm volatile(

@@ -492,6 +492,9 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
 #ifndef RGBID_PX
 #define RGBID_PX 4
 #endif
+#ifndef RGBID_EVICT_FIRST
+#define RGBID_EVICT_FIRST 1  // keyframe-map bulk copies carry an L2 evict-first policy (see bulk_copy.cuh)
+#endif
 constexpr int kPx = RGBID_PX;                   // pixels per lane and chunk (4: 128-bit shared-memory loads; 2: half the live gather state)
 constexpr int kChunkPx = 32 * kPx;              // one warp-chunk
 struct __align__(4 * kPx) LaneVec { float v[kPx]; };
@@ -570,22 +573,28 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
   const char* gIy = (const char*)M.gIy.row(b, 0);
   // (one elected lane) bulk copies of this warp's i-th chunk; the last chunk of a stream runs into the map's NaN
   // padding (see launch_gn_build), so every copy is a full 512 bytes
+#if RGBID_EVICT_FIRST
+  const uint64_t l2_stream = l2_policy_evict_first();
+#define RGBID_G2S(dst, src, bytes, bar) bulk_g2s_hint(dst, src, bytes, bar, l2_stream)
+#else
+#define RGBID_G2S(dst, src, bytes, bar) bulk_g2s(dst, src, bytes, bar)
+#endif
   auto issue_w = [&](int i) {
     const int s = i % kStagesW;
     const size_t off = (size_t)(my_first + i * kBuildWarps) * kChunkBytes;
     mbar_arrive_expect_tx(barW + (uint32_t)s * 8u, kChunkBytes);
-    bulk_g2s(ringW + (uint32_t)s * kChunkBytes, gW0 + off, kChunkBytes, barW + (uint32_t)s * 8u);
+    RGBID_G2S(ringW + (uint32_t)s * kChunkBytes, gW0 + off, kChunkBytes, barW + (uint32_t)s * 8u);
   };
   auto issue_l = [&](int i) {
     const int s = i % kStagesL;
     const size_t off = (size_t)(my_first + i * kBuildWarps) * kChunkBytes;
     const uint32_t dst = ringL + (uint32_t)s * kLateBytes, bar = barL + (uint32_t)s * 8u;
     mbar_arrive_expect_tx(bar, kLateBytes);
-    bulk_g2s(dst + 0 * kChunkBytes, gI0 + off, kChunkBytes, bar);
-    bulk_g2s(dst + 1 * kChunkBytes, gWx + off, kChunkBytes, bar);
-    bulk_g2s(dst + 2 * kChunkBytes, gWy + off, kChunkBytes, bar);
-    bulk_g2s(dst + 3 * kChunkBytes, gIx + off, kChunkBytes, bar);
-    bulk_g2s(dst + 4 * kChunkBytes, gIy + off, kChunkBytes, bar);
+    RGBID_G2S(dst + 0 * kChunkBytes, gI0 + off, kChunkBytes, bar);
+    RGBID_G2S(dst + 1 * kChunkBytes, gWx + off, kChunkBytes, bar);
+    RGBID_G2S(dst + 2 * kChunkBytes, gWy + off, kChunkBytes, bar);
+    RGBID_G2S(dst + 3 * kChunkBytes, gIx + off, kChunkBytes, bar);
+    RGBID_G2S(dst + 4 * kChunkBytes, gIy + off, kChunkBytes, bar);
   };
   // the keyframe maps were written before this Gauss-Newton schedule started: the first bulk copies may be in flight
   // while the previous kernel (scale estimation, or the previous iteration's solve) is still finishing
