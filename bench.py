@@ -98,7 +98,11 @@ def dist_setup(args):
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         backend = "nccl" if torch.cuda.is_available() else "gloo"
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        import datetime
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local)
+        # a rank that leaves the collective sequence must fail the run in two minutes, not hold the box for ten
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, timeout=datetime.timedelta(seconds=120))
     return world, rank, local
 
 
@@ -196,7 +200,9 @@ def run_b200(args, world, rank, local):
         n = steps or K
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
         poses0 = []
-        barrier()
+        # the side measurements (tracker != None) run on one rank only: no collective there
+        sync_all = barrier if tracker is None else (lambda: torch.cuda.synchronize(device))
+        sync_all()
         launches0 = ctx.launches
         t0 = time.perf_counter()
         with torch.cuda.stream(ctx.stream):
@@ -215,7 +221,7 @@ def run_b200(args, world, rank, local):
             if side is not None and tracker is None:
                 ctx.stream.wait_stream(side)  # the collective belongs to the step: join it before the closing event
             ev[n].record()
-        barrier()
+        sync_all()
         wall = time.perf_counter() - t0
         per_step = [ev[k].elapsed_time(ev[k + 1]) for k in range(n)]
         dev_s = ev[0].elapsed_time(ev[n]) / 1e3
@@ -242,7 +248,8 @@ def run_b200(args, world, rank, local):
             trk.prefetch(h_depth[k + 1], h_rgb[k + 1])
         trk.track(h_depth[k], h_rgb[k])
     e2e_dev_s, e2e_wall_s, _, _, e2e_per_step, _ = timed(h_depth[1 + W:], h_rgb[1 + W:], True)
-    extras = {} if (args.no_extras or rank != 0) else side_measurements(args, ctx, depth, rgb, h_depth, h_rgb, intr, its, timed)
+    # batch-1 latency and KeyframeAlign mode are single-GPU numbers: the N = 1 run carries them
+    extras = {} if (args.no_extras or world > 1) else side_measurements(args, ctx, depth, rgb, h_depth, h_rgb, intr, its, timed)
 
     def allmax(x):
         if world == 1:
@@ -296,7 +303,8 @@ def run_b200(args, world, rank, local):
                          "ms_per_launch": ms_build, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
                          "timed": "the shipped launch: pixel loop + final sum + 6x6 solve + pose update in the last CTA of every "
                                   "stream (rgbid_aligner_time_build, CUDA events on the launching stream, 20 back-to-back launches)",
-                         "note": "bound by register-file bank conflicts on the FMA pipe (dispatch stalls), see profiles/README.md"},
+                         "note": "pixel loop alone: 64-65 us = 0.74 of the peak (profiles/r02_tail_probe.txt); the launch adds reduction + election "
+                                 "and the single-thread 6x6 solve / pose update on its critical path, see profiles/README.md"},
             "lost_streams": lost,
             "collective": None if world == 1 else "NCCL all-gather of [streams, 48] f64 per step from device memory, side stream, inside `value`",
         }
