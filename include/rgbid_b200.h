@@ -257,6 +257,10 @@ int rgbid_aligner_set_current_rgbd(rgbid_aligner* al, int index, const uint16_t*
 /* Promote the current frame of pair `index` to keyframe (copy + gradients (+ filtered gradients)). */
 int rgbid_aligner_current_to_keyframe(rgbid_aligner* al, int index);
 
+/* The solver records one rgbid_iter_trace per pair and iteration on the device.  rgbid_aligner_run switches the recording
+ * on exactly when trace_out != NULL; callers of rgbid_aligner_enqueue / rgbid_aligner_fetch who do not read traces can
+ * switch it off (it is on after rgbid_aligner_create; the tracker's own aligner runs with it off). */
+int rgbid_aligner_set_trace(rgbid_aligner* aligner, int enable);
 /* Run the whole coarse-to-fine schedule for all `batch` pairs on the device.
  * R_inout: batch x 9 doubles (row-major rotation _{KF}R^{cur}), t_inout: batch x 3 doubles: initial guess
  * in, estimate out.  cov_out: batch x 36 doubles (may be NULL).  status_out: batch ints (RGBID_OK or

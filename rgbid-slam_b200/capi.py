@@ -139,6 +139,7 @@ PROTOTYPES = {
     "rgbid_aligner_set_current": (I, [P, I, P, SZ, P, SZ, I]),
     "rgbid_aligner_set_current_rgbd": (I, [P, I, P, SZ, P, SZ, I]),
     "rgbid_aligner_current_to_keyframe": (I, [P, I]),
+    "rgbid_aligner_set_trace": (I, [P, I]),
     "rgbid_aligner_run": (I, [P, c_double_p, c_double_p, c_double_p, c_int_p, C.POINTER(IterTrace)]),
     "rgbid_aligner_enqueue": (I, [P, c_double_p, c_double_p]),
     "rgbid_aligner_fetch": (I, [P, c_double_p, c_double_p, c_double_p, c_int_p, C.POINTER(IterTrace)]),

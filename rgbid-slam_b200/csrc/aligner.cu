@@ -196,7 +196,8 @@ void aligner_record_schedule(rgbid_aligner* al)
 {
   const rgbid_align_config& c = al->cfg;
   LaunchCtx L = al->ctx->L();
-  launch_gn_init(L, al->d_states, al->d_init, al->d_init + 9 * c.batch, c.batch, c.levels, c.fx, c.fy, c.cx, c.cy);
+  launch_gn_init(L, al->d_states, al->d_init, al->d_init + 9 * c.batch, c.batch, c.levels, c.fx, c.fy, c.cx, c.cy,
+                 al->d_trace_flag);
   if (al->side_stream == nullptr || c.batch < 2) {
     record_chain(al, L, 0, c.batch);
     return;
@@ -287,6 +288,9 @@ int rgbid_aligner_create(rgbid_ctx* ctx, const rgbid_align_config* cfg, rgbid_al
   if (e == cudaSuccess) e = cudaMalloc(&al->d_counters, sizeof(unsigned int) * B);
   if (e == cudaSuccess) e = cudaMalloc(&al->d_trace, sizeof(rgbid_iter_trace) * (size_t)al->trace_stride * B);
   if (e == cudaSuccess) e = cudaMalloc(&al->d_init, sizeof(double) * 12 * B);
+  if (e == cudaSuccess) e = cudaMalloc(&al->d_trace_flag, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemsetAsync(al->d_trace_flag, 1, sizeof(int), ctx->stream);  // traces on by default
+  al->trace_enabled = 1;
   if (e == cudaSuccess) e = cudaMalloc(&al->d_active, sizeof(int) * 4 * B);
   if (e == cudaSuccess) e = cudaMallocHost(&al->h_states, sizeof(GnState) * B);
   if (e == cudaSuccess) e = cudaMallocHost(&al->h_trace, sizeof(rgbid_iter_trace) * (size_t)al->trace_stride * B);
@@ -365,7 +369,7 @@ int rgbid_aligner_destroy(rgbid_aligner* al)
   }
   cudaFree(al->d_tex);
   cudaFree(al->d_arena); cudaFree(al->d_states); cudaFree(al->d_scales); cudaFree(al->d_partials);
-  cudaFree(al->d_counters); cudaFree(al->d_trace); cudaFree(al->d_init); cudaFree(al->d_active);
+  cudaFree(al->d_counters); cudaFree(al->d_trace); cudaFree(al->d_trace_flag); cudaFree(al->d_init); cudaFree(al->d_active);
   if (al->h_states) cudaFreeHost(al->h_states);
   if (al->h_trace) cudaFreeHost(al->h_trace);
   if (al->h_init) cudaFreeHost(al->h_init);
@@ -449,6 +453,17 @@ int rgbid_aligner_enqueue(rgbid_aligner* al, const double* R_init, const double*
   return aligner_enqueue_device_init(al);
 }
 
+int rgbid_aligner_set_trace(rgbid_aligner* al, int enable)
+{
+  if (!al) return RGBID_ERR_ARG;
+  enable = enable ? 1 : 0;
+  if (enable == al->trace_enabled) return RGBID_OK;
+  // read by gn_init_kernel at the start of every run (the recorded schedule itself does not change)
+  RGBID_CUDA_TRY(cudaMemsetAsync(al->d_trace_flag, enable, sizeof(int), al->ctx->stream));
+  al->trace_enabled = enable;
+  return RGBID_OK;
+}
+
 int rgbid_aligner_fetch(rgbid_aligner* al, double* R_out, double* t_out, double* cov_out, int* status_out,
                         rgbid_iter_trace* trace_out)
 {
@@ -476,7 +491,10 @@ int rgbid_aligner_fetch(rgbid_aligner* al, double* R_out, double* t_out, double*
 int rgbid_aligner_run(rgbid_aligner* al, double* R_inout, double* t_inout, double* cov_out, int* status_out,
                       rgbid_iter_trace* trace_out)
 {
-  int rc = rgbid_aligner_enqueue(al, R_inout, t_inout);
+  if (!al) return RGBID_ERR_ARG;
+  int rc = rgbid_aligner_set_trace(al, trace_out != nullptr);  // this call knows whether the trace is wanted
+  if (rc != RGBID_OK) return rc;
+  rc = rgbid_aligner_enqueue(al, R_inout, t_inout);
   if (rc != RGBID_OK) return rc;
   return rgbid_aligner_fetch(al, R_inout, t_inout, cov_out, status_out, trace_out);
 }

@@ -42,6 +42,8 @@ struct rgbid_aligner {
   int* d_active;   // per-stream predicate for keyframe updates (tracker)
   // pinned host mirrors
   rgbid::GnState* h_states;
+  int* d_trace_flag;   // device: non-zero = the solver tail writes the per-iteration trace (rgbid_aligner_set_trace)
+  int trace_enabled;   // host shadow of it
   rgbid_iter_trace* h_trace;
   double* h_init;
   int* h_active;

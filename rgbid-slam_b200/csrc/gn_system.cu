@@ -243,25 +243,35 @@ __device__ __forceinline__ void refresh_proj(GnState& st, const double* R, const
 // CHI_SQUARED termination test (:1134-1164).  Three separate functions, so that the per-iteration path is small (it is
 // cold code executed once per launch by a single thread: RGBID_TAIL_PROBE measured ~11 000 clocks for ~800 instructions)
 // and gets its own register allocation instead of inheriting the spills of the 6x6 Gauss-Jordan inverse.
-__device__ __noinline__ void gn_tail_update(GnState& st, const double* tot, const GnParams& P, double* x)
+#if RGBID_TAIL_PROBE
+__device__ long long g_tail_stamp[8];  // diagnostic build: clock64 at the stages of gn_tail_update, pair 0 only
+__device__ const void* g_tail_probe_state;
+#define RGBID_STAMP(k) if ((const void*)&st == g_tail_probe_state) g_tail_stamp[k] = clock64()
+#else
+#define RGBID_STAMP(k)
+#endif
+
+// The per-iteration tail in three separate (noinline) stages.  They are ~800 instructions of code that was last executed
+// a launch ago: RGBID_TAIL_PROBE shows every stage 2.5-4x slower on its first execution than when repeated (solve
+// 4 200-5 500 clocks against 1 700-2 100, update 1 600-2 800 / 620, commit 4 200-6 400 / 1 100).  Letting idle warps of
+// every CTA pre-execute the stages on dummy data behind the reduction's barrier shortened the tail (17 500 -> 14 000
+// clocks) but made the launch SLOWER (90.4 vs 84.7 us: 4 x 288 lanes of cold double-precision code at once) -- removed,
+// profiles/r02_tail_probe.txt.
+__device__ __noinline__ void gn_stage_solve(const double* tot, double* x) { llt_solve_packed(tot, x); }
+
+__device__ __noinline__ bool gn_stage_update(const double* x, double* R, double* t) { return gn_update_lean(x, R, t); }
+
+__device__ __noinline__ void gn_stage_commit(GnState& st, const double* Rin, const double* tin, const double* x, bool bad,
+                                             const GnParams& P)
 {
-  // pose in registers: every access through `st` is a global load / store the compiler may not reorder
   double R[9], t[3];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) R[i] = st.R[i];
+  for (int i = 0; i < 9; ++i) R[i] = Rin[i];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) t[i] = st.t[i];
-  if (P.termination == RGBID_TERM_CHI_SQUARED) {  // the increment may have to be undone by the next test
-#pragma unroll
-    for (int i = 0; i < 9; ++i) st.Rprev[i] = R[i];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) st.tprev[i] = t[i];
-  }
-  llt_solve_packed(tot, x);
-  bool bad = gn_update_lean(x, R, t);
+  for (int i = 0; i < 3; ++i) t[i] = tin[i];
   if (P.dry_tail) {
-    // everything above and the projection refresh below are executed, but the pose is not committed and the
-    // projection goes to the slot of ANOTHER level than the one being timed (rewritten by gn_init before any real run)
+    // everything is executed, but the pose is not committed and the projection goes to the slot of ANOTHER level than
+    // the one being timed (rewritten by gn_init before any real run)
     refresh_proj(st, R, t, P.levels, P.fx0, P.fy0, P.cx0, P.cy0, (P.level + 1) % P.levels);
     return;
   }
@@ -285,6 +295,33 @@ __device__ __noinline__ void gn_tail_update(GnState& st, const double* tot, cons
     if (n2 < (double)P.conv_eps * (double)P.conv_eps) { st.skip_level = P.sched_level; next = -1; }
   }
   refresh_proj(st, R, t, P.levels, P.fx0, P.fy0, P.cx0, P.cy0, next);
+}
+
+__device__ __forceinline__ void gn_tail_update(GnState& st, const double* tot, const GnParams& P, double* x)
+{
+  RGBID_STAMP(0);
+  // pose in registers: every access through `st` is a global load / store the compiler may not reorder
+  double R[9], t[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = st.R[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) t[i] = st.t[i];
+#if RGBID_TAIL_PROBE
+  if (R[0] + t[0] == 12345.678) st.status = 1;  // consume the loads before the stamp
+#endif
+  RGBID_STAMP(1);
+  if (P.termination == RGBID_TERM_CHI_SQUARED) {  // the increment may have to be undone by the next test
+#pragma unroll
+    for (int i = 0; i < 9; ++i) st.Rprev[i] = R[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) st.tprev[i] = t[i];
+  }
+  gn_stage_solve(tot, x);
+  RGBID_STAMP(2);
+  const bool bad = gn_stage_update(x, R, t);
+  RGBID_STAMP(3);
+  gn_stage_commit(st, R, t, x, bad, P);
+  RGBID_STAMP(4);
 }
 
 __device__ __noinline__ void gn_tail_cov(GnState& st, const double* tot, const GnParams& P, bool chi)
@@ -344,7 +381,9 @@ __device__ __forceinline__ void gn_tail(GnState& st, const double* tot, const Gn
   double x[6] = {0, 0, 0, 0, 0, 0};
   if (P.compute_cov || chi) gn_tail_cov(st, tot, P, chi);
   if (P.update_pose) gn_tail_update(st, tot, P, x);
-  if (trace != nullptr && P.trace_stride > 0 && P.iter_index >= 0 && P.iter_index < P.trace_stride)
+  // the trace record (~60 stores of cold code at the very end of the launch) is only written when the caller of this
+  // run asked for traces (GnState::trace_on, rgbid_aligner_set_trace)
+  if (trace != nullptr && P.trace_stride > 0 && P.iter_index >= 0 && P.iter_index < P.trace_stride && st.trace_on)
     gn_tail_trace(st, tot, P, sc, trace, b, x);
 }
 
@@ -850,28 +889,28 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
   static_assert(kWarpRingBytes >= kAccChi * 32 * (int)sizeof(float), "ring too small for the lane-sum scratch");
 
 #if RGBID_TAIL_PROBE
-  // -DRGBID_TAIL_PROBE=1 (diagnostic build): clocks of the last CTA of pair 0 -- pixel loop,
-  // CTA reduction + election + fixed-order final sum, serial tail (6x6 solve, pose update, projection refresh, trace)
   const long long probe_t1 = clock64();
-  if (!reduce_and_elect<NACC>(sh, acc, wscratch, partials + (size_t)b * gridDim.x * partial_stride, partial_stride,
-                              &counters[b], gridDim.x, blockIdx.x))
-    return;
+#endif
+  const bool last = reduce_and_elect<NACC>(sh, acc, wscratch, partials + (size_t)b * gridDim.x * partial_stride,
+                                           partial_stride, &counters[b], gridDim.x, blockIdx.x);
+  if (!last) return;
+#if RGBID_TAIL_PROBE
+  // -DRGBID_TAIL_PROBE=1 (diagnostic build, tools/scale_round_probe.py): clocks of the last CTA of pair 0 -- pixel loop
+  // (from the end of the dependency wait), CTA reduction + election + final sum, serial tail and its stages
+  if (b == 0 && threadIdx.x == 0) g_tail_probe_state = &st;
   const long long probe_t2 = clock64();
   if (threadIdx.x == 0) {
     gn_tail(st, sh.total, P, sc, trace, b, CHI);
     const long long probe_t3 = clock64();
-    // second call on the same data: the same instructions, now in the instruction cache (the pose of this diagnostic
-    // build is garbage afterwards)
-    gn_tail(st, sh.total, P, sc, trace, b, CHI);
-    const long long probe_t4 = clock64();
-    if (b == 0)
-      printf("tail probe level %d iter %d cta %d | loop %lld reduce+elect %lld tail %lld, repeated %lld\n", P.level, P.iter_index,
-             (int)blockIdx.x, probe_t1 - probe_t0, probe_t2 - probe_t1, probe_t3 - probe_t2, probe_t4 - probe_t3);
+    if (b == 0) {
+      printf("tail probe level %d iter %d cta %d | loop %lld reduce+elect %lld tail %lld\n", P.level, P.iter_index,
+             (int)blockIdx.x, probe_t1 - probe_t0, probe_t2 - probe_t1, probe_t3 - probe_t2);
+      printf("   tail stages | call %lld loads %lld solve %lld update %lld commit %lld return %lld\n", g_tail_stamp[0] - probe_t2,
+             g_tail_stamp[1] - g_tail_stamp[0], g_tail_stamp[2] - g_tail_stamp[1], g_tail_stamp[3] - g_tail_stamp[2],
+             g_tail_stamp[4] - g_tail_stamp[3], probe_t3 - g_tail_stamp[4]);
+    }
   }
 #else
-  if (!reduce_and_elect<NACC>(sh, acc, wscratch, partials + (size_t)b * gridDim.x * partial_stride, partial_stride,
-                              &counters[b], gridDim.x, blockIdx.x))
-    return;
   if (threadIdx.x == 0) gn_tail(st, sh.total, P, sc, trace, b, CHI);
 #endif
 }
@@ -991,7 +1030,7 @@ __global__ void __cluster_dims__(kScaleCluster, 1, 1) __launch_bounds__(kScaleTh
 
 __global__ void gn_init_kernel(GnState* __restrict__ states, const double* __restrict__ R_init,
                                const double* __restrict__ t_init, int batch, int levels, float fx0, float fy0,
-                               float cx0, float cy0)
+                               float cx0, float cy0, const int* __restrict__ trace_flag)
 {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
@@ -1001,6 +1040,7 @@ __global__ void gn_init_kernel(GnState* __restrict__ states, const double* __res
   for (int i = 0; i < 36; ++i) { st.cov[i] = 0.0; st.lastA[i] = 0.0; }
   st.status = RGBID_OK; st.iter_count = 0;
   st.skip_level = -1; st.rmse_prev = 9999.f;
+  st.trace_on = (trace_flag == nullptr) ? 1 : (*trace_flag != 0);
   for (int l = 0; l < RGBID_MAX_LEVELS; ++l) st.iters_done[l] = 0;
   st.chi_square = 0.f; st.chi_test = 0.f; st.ndof = 0.f;
   refresh_proj(st, st.R, st.t, levels, fx0, fy0, cx0, cy0);
@@ -1067,9 +1107,9 @@ void launch_export_systems(const LaunchCtx& L, const GnState* states, double* ou
 }
 
 void launch_gn_init(const LaunchCtx& L, GnState* states, const double* R_init, const double* t_init, int batch,
-                    int levels, float fx0, float fy0, float cx0, float cy0)
+                    int levels, float fx0, float fy0, float cx0, float cy0, const int* trace_flag)
 {
-  gn_init_kernel<<<(batch + 63) / 64, 64, 0, L.stream>>>(states, R_init, t_init, batch, levels, fx0, fy0, cx0, cy0);
+  gn_init_kernel<<<(batch + 63) / 64, 64, 0, L.stream>>>(states, R_init, t_init, batch, levels, fx0, fy0, cx0, cy0, trace_flag);
   ++*L.launches;
 }
 

@@ -167,7 +167,7 @@ struct GnState {
   int iters_done[RGBID_MAX_LEVELS];
   double Rprev[9], tprev[3];
   float rmse_prev;
-  int pad;
+  int trace_on;              // 0: the solver tail skips the per-iteration trace record (set per run by gn_init_kernel)
 };
 
 struct GnParams {
@@ -210,7 +210,7 @@ void launch_gn_build(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P
                      const ScaleState* scales, double* partials, int partial_stride, unsigned int* counters,
                      rgbid_iter_trace* trace);
 void launch_gn_init(const LaunchCtx& L, GnState* states, const double* R_init, const double* t_init, int batch,
-                    int levels, float fx0, float fy0, float cx0, float cy0);
+                    int levels, float fx0, float fy0, float cx0, float cy0, const int* trace_flag);
 int gn_build_grid_x(int rows, int cols, int batch, int num_sms);
 // One-time per-device set-up of the Gauss-Newton kernels (nu table in constant memory, dynamic shared-memory limits).
 // rgbid_aligner_create calls it, so that nothing of it can fall inside a stream capture; returns a cudaError_t value.

@@ -234,6 +234,7 @@ int rgbid_tracker_create(rgbid_ctx* ctx, const rgbid_tracker_config* cfg, rgbid_
   t->copy_stream = nullptr; t->pf_next = 0; t->track_calls = 0; t->pf_issued_at[0] = t->pf_issued_at[1] = 0;
   for (int i = 0; i < 2; ++i) { t->ev_copy[i] = nullptr; t->d_prefetch[i] = nullptr; t->pf_depth[i] = t->pf_rgb[i] = nullptr; t->pf_valid[i] = false; }
   int rc = rgbid_aligner_create(ctx, &t->cfg.align, &t->al);
+  if (rc == RGBID_OK) rc = rgbid_aligner_set_trace(t->al, 0);  // the tracker never reads the per-iteration trace
   if (rc != RGBID_OK) { delete t; return rc; }
   t->al->image_filtering = t->cfg.image_filtering;
   const rgbid_align_config& c = t->al->cfg;
