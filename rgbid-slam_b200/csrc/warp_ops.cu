@@ -82,6 +82,45 @@ __global__ void __launch_bounds__(BX* BY)
   dst_i.row(b, y)[x] = i1;
 }
 
+// Four pixels per thread through the texture unit: one float4 load of the keyframe inverse depth, the four inverse-depth
+// fetches in flight together, then the four intensity fetches (warp_stage1..3 of common.cuh: the arithmetic of
+// warp_pixel without its branches), float4 stores.  The scalar kernel above has one dependent fetch chain per thread.
+__global__ void __launch_bounds__(256)
+    warp_pair_vec_kernel(ImgB src_w, const cudaTextureObject_t* __restrict__ texW,
+                         const cudaTextureObject_t* __restrict__ texI, ImgB kf_w, const GnState* __restrict__ states,
+                         ImgB dst_w, ImgB dst_i, int first)
+{
+  const int b = blockIdx.y + first;
+  const GnState& st = states[b];
+  if (st.status != RGBID_OK) return;  // uniform over the CTA
+  __shared__ Proj s_proj;
+  const int tid = threadIdx.x;
+  if (tid < 12) ((float*)&s_proj)[tid] = ((const float*)&st.proj[0])[tid];
+  __syncthreads();
+  const Proj proj = s_proj;
+  const cudaTextureObject_t tw = texW[b], ti = texI[b];
+  const int cols = src_w.cols, rows = src_w.rows;
+  const int qpr = cols >> 2, total = qpr * rows;
+  for (int q = blockIdx.x * blockDim.x + tid; q < total; q += gridDim.x * blockDim.x) {
+    const int y = q / qpr, x0 = (q - y * qpr) * 4;
+    float w0[4], w1[4], i1[4], fetched[4];
+    *(float4*)w0 = __ldg((const float4*)(kf_w.row(b, y) + x0));
+    WarpCoord wc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wc[k] = warp_stage1(proj, x0 + k, y, w0[k], cols, rows);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) fetched[k] = tex2D<float>(tw, wc[k].xt, wc[k].yt);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w1[k] = warp_stage2(proj, x0 + k, y, w0[k], fetched[k], wc[k], cols, rows, true);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) fetched[k] = tex2D<float>(ti, wc[k].xt, wc[k].yt);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) i1[k] = warp_stage3(fetched[k], wc[k]);
+    *(float4*)(dst_w.row(b, y) + x0) = *(float4*)w1;
+    *(float4*)(dst_i.row(b, y) + x0) = *(float4*)i1;
+  }
+}
+
 // Shared body of K6 (trafo3DKernelInvDepthWeightedGridStride, warping_registration.cu:549-594):
 // returns the warped inverse depth (NaN if rejected) and, through weight / has_weight, the fusion weight
 // (1 - w2 tz)^4 / v1z^2 when it is positive.
@@ -426,7 +465,14 @@ void launch_warp_pair(const LaunchCtx& L, ImgB src_w, ImgB src_i, const cudaText
                       int first, int batch)
 {
   const dim3 grid = grid2d(dst_w.cols, dst_w.rows, batch), block(BX, BY);
-  if (texW != nullptr && texI != nullptr)
+  auto v16 = [](const ImgB& m) { return ((uintptr_t)m.p % 16 == 0) && m.pitch % 16 == 0 && m.sstride % 16 == 0; };
+  if (texW != nullptr && texI != nullptr && dst_w.cols % 4 == 0 && v16(kf_w) && v16(dst_w) && v16(dst_i)) {
+    const int total = (dst_w.cols / 4) * dst_w.rows;
+    int gx = (total + 255) / 256;
+    const int cap = (L.num_sms * 8 + batch - 1) / batch;  // ~8 CTAs of 256 threads per SM over the whole batch
+    if (gx > cap) gx = cap;
+    warp_pair_vec_kernel<<<dim3(gx, batch), 256, 0, L.stream>>>(src_w, texW, texI, kf_w, states, dst_w, dst_i, first);
+  } else if (texW != nullptr && texI != nullptr)
     warp_pair_kernel<true><<<grid, block, 0, L.stream>>>(src_w, src_i, texW, texI, kf_w, states, dst_w, dst_i, first);
   else
     warp_pair_kernel<false><<<grid, block, 0, L.stream>>>(src_w, src_i, texW, texI, kf_w, states, dst_w, dst_i, first);
