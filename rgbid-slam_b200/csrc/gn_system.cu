@@ -558,6 +558,9 @@ struct FastGeom {
   float colsf, rowsf, inv_cols;
 };
 
+// WITH_B = false (covariance pass): only the 21 J^T W J terms -- the pass inverts A and never looks at J^T W r
+// (src/visodo.cpp:1382-1415), so the six residual terms stay zero
+template <bool WITH_B>
 __device__ __forceinline__ void accumulate_scalar(float* acc, float s, const float* r, float e, int flag)
 {
   int shift = 0;
@@ -566,7 +569,8 @@ __device__ __forceinline__ void accumulate_scalar(float* acc, float s, const flo
     const float si = s * r[i];
 #pragma unroll
     for (int j = i; j < 6; ++j) { pfma(acc[shift], si, r[j], flag); ++shift; }
-    pfma(acc[shift], si, e, flag); ++shift;
+    if (WITH_B) pfma(acc[shift], si, e, flag);
+    ++shift;
   }
 }
 
@@ -834,7 +838,7 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
           if (!(isnan(cd) || isinf(cd))) { chi[2] += chi_rho_dev(cd, chi_mest); chi[3] += 1.f; }
         }
       }
-      accumulate_scalar(accs, sd, rd, ed, fd);
+      accumulate_scalar<!CHI>(accs, sd, rd, ed, fd);
     }
 
     // --- S3: intensity constraint + accumulation ---------------------------------------------------------------
@@ -866,7 +870,7 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
           if (!(isnan(ci) || isinf(ci))) { chi[0] += chi_rho_dev(ci, chi_mest); chi[1] += 1.f; }
         }
       }
-      accumulate_scalar(accs, si, ri, ei, fi);
+      accumulate_scalar<!CHI>(accs, si, ri, ei, fi);
     }
     __syncwarp();
     if (elect_one()) {

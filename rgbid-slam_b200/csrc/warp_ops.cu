@@ -370,8 +370,16 @@ __global__ void __launch_bounds__(256) visibility_vec_kernel(ImgB src, ImgB dst,
 // 16 gathers issued together (clamped addresses: memory-level parallelism instead of load-compare-load chains).  The
 // per-pixel test is visibility_vec_kernel's, the counts are integers: bit-identical results.
 // counts[b * 8 + 2 * pass + {0: visible, 1: valid}], transforms P[pass * batch + b].
-__global__ void __launch_bounds__(256) visibility4_vec_kernel(ImgB cur, ImgB kf, ImgB ikf, const Proj* __restrict__ P_dev,
-                                                              unsigned int* __restrict__ counts, int batch)
+#ifndef RGBID_VIS4_MINB
+#define RGBID_VIS4_MINB 4
+#endif
+#ifndef RGBID_VIS4_PX
+#define RGBID_VIS4_PX 4
+#endif
+constexpr int kVisPx = RGBID_VIS4_PX;  // pixels per thread and trip (4: float4 loads, 2: float2)
+struct __align__(4 * kVisPx) VisVec { float v[kVisPx]; };
+__global__ void __launch_bounds__(256, RGBID_VIS4_MINB) visibility4_vec_kernel(ImgB cur, ImgB kf, ImgB ikf, const Proj* __restrict__ P_dev,
+                                                                 unsigned int* __restrict__ counts, int batch)
 {
   const int b = blockIdx.y;
   __shared__ Proj sP[4];
@@ -380,35 +388,54 @@ __global__ void __launch_bounds__(256) visibility4_vec_kernel(ImgB cur, ImgB kf,
   if (tid < 48) ((float*)&sP[tid / 12])[tid % 12] = ((const float*)&P_dev[(tid / 12) * batch + b])[tid % 12];
   if (tid < 8) s_cnt[tid] = 0;
   __syncthreads();
-  const int qpr = cur.cols >> 2, total = qpr * cur.rows;
+  // per-stream base pointers and pitches in floats: a gather is base + (yi * pitch + xi), one 32-bit multiply-add and one
+  // widening add instead of the 64-bit byte arithmetic of ImgB::row (the first version spent 43 % of its issue slots on
+  // the integer pipe and ran at 119 registers, 16 warps per SM: profiles/README.md)
+  const float* __restrict__ bc = cur.row(b, 0);
+  const float* __restrict__ bk = kf.row(b, 0);
+  const float* __restrict__ bi = ikf.row(b, 0);
+  const int pc = (int)(cur.pitch >> 2), pk = (int)(kf.pitch >> 2), pi = (int)(ikf.pitch >> 2);
+  const int qpr = cur.cols / kVisPx, total = qpr * cur.rows;
   const float xmax = __int2float_rn(cur.cols - 1), ymax = __int2float_rn(cur.rows - 1);
   unsigned cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int q = blockIdx.x * blockDim.x + tid; q < total; q += gridDim.x * blockDim.x) {
-    const int y = q / qpr, x0 = (q - y * qpr) * 4;
-    float wc[4], wk[4], wi[4];
-    *(float4*)wc = __ldg((const float4*)(cur.row(b, y) + x0));
-    *(float4*)wk = __ldg((const float4*)(kf.row(b, y) + x0));
-    *(float4*)wi = __ldg((const float4*)(ikf.row(b, y) + x0));
+    const int y = q / qpr, x0 = (q - y * qpr) * kVisPx;
+    float wc[kVisPx], wk[kVisPx], wi[kVisPx];
+    *(VisVec*)wc = *(const VisVec*)(bc + y * pc + x0);
+    *(VisVec*)wk = *(const VisVec*)(bk + y * pk + x0);
+    *(VisVec*)wi = *(const VisVec*)(bi + y * pi + x0);
+    // valid source pixels: pass 0 and pass 2 read the same map
+    {
+      unsigned nc = 0, nk = 0, ni = 0;
+#pragma unroll
+      for (int k = 0; k < kVisPx; ++k) { nc += (wc[k] == wc[k]); nk += (wk[k] == wk[k]); ni += (wi[k] == wi[k]); }
+      cnt[1] += nc; cnt[5] += nc; cnt[3] += nk; cnt[7] += ni;
+    }
 #pragma unroll
     for (int pass = 0; pass < 4; ++pass) {
       const float* src = (pass == 0 || pass == 2) ? wc : (pass == 1 ? wk : wi);
-      const ImgB& dst = (pass == 0) ? kf : (pass == 2 ? ikf : cur);
-      float wd[4], got[4];
-      bool in[4];
+      const float* __restrict__ dbase = (pass == 0) ? bk : (pass == 2 ? bi : bc);
+      const int dpitch = (pass == 0) ? pk : (pass == 2 ? pi : pc);
+      // the pass's transform is re-read from shared memory (volatile: 12 broadcast loads) instead of keeping all four
+      // transforms -- 48 registers -- live across the loop
+      Proj Pp;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int i = 0; i < 12; ++i) ((float*)&Pp)[i] = ((const volatile float*)&sP[pass])[i];
+      float wd[kVisPx], got[kVisPx];
+      bool ok[kVisPx];
+#pragma unroll
+      for (int k = 0; k < kVisPx; ++k) {
         float xd, yd;
-        wd[k] = project_pixel(sP[pass], x0 + k, y, src[k], xd, yd);
-        in[k] = !isnan(src[k]) && xd > 0.f && xd < xmax && yd > 0.f && yd < ymax;
-        const int xi = in[k] ? __float2int_rn(xd) : 0, yi = in[k] ? __float2int_rn(yd) : 0;
-        got[k] = __ldg(dst.row(b, yi) + xi);
+        wd[k] = project_pixel(Pp, x0 + k, y, src[k], xd, yd);
+        // a NaN source gives NaN coordinates: all four comparisons are false
+        ok[k] = xd > 0.f && xd < xmax && yd > 0.f && yd < ymax;
+        const int off = ok[k] ? __float2int_rn(yd) * dpitch + __float2int_rn(xd) : 0;
+        got[k] = __ldg(dbase + off);
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        cnt[2 * pass + 1] += isnan(src[k]) ? 0u : 1u;
+      for (int k = 0; k < kVisPx; ++k)
         // geom_tol is ignored by the reference: 0.020 is hard-coded (warping_registration.cu:332, :405)
-        cnt[2 * pass + 0] += (in[k] && fabsf(wd[k] - got[k]) < 0.020f) ? 1u : 0u;
-      }
+        cnt[2 * pass] += (ok[k] && fabsf(wd[k] - got[k]) < 0.020f) ? 1u : 0u;
     }
   }
 #pragma unroll
@@ -426,7 +453,7 @@ __global__ void __launch_bounds__(256) visibility4_vec_kernel(ImgB cur, ImgB kf,
 
 void launch_visibility4(const LaunchCtx& L, ImgB cur, ImgB kf, ImgB ikf, const Proj* P_dev, unsigned int* counts, int batch)
 {
-  const int total = (cur.cols / 4) * cur.rows;
+  const int total = (cur.cols / kVisPx) * cur.rows;
   int gx = (total + 255) / 256;
   const int cap = (L.num_sms * 8 + batch - 1) / batch;  // ~8 CTAs of 256 threads per SM over the whole batch
   if (gx > cap) gx = cap;
