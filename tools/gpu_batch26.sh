@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/b26_pytest.txt 2>&1
+timeout 900 python bench.py > gpurun_out/b26_bench_full.json 2> gpurun_out/b26_bench_full.err
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/b26_smoke.txt 2>&1
+RGBID_NO_GRAPH=1 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"gn_|pyr_down|ingest|visibility|warp_|vmap|nmap|bilateral|gradient|copy2|control_upload|fill_|export" -c 700 --csv --log-file gpurun_out/r02f_launches_all.csv python tools/profile_step.py 32 6 > gpurun_out/b26_ncu.log 2>&1
+tail -3 gpurun_out/b26_pytest.txt; cut -c1-330 gpurun_out/b26_bench_full.json; tail -2 gpurun_out/b26_smoke.txt
