@@ -548,9 +548,11 @@ constexpr int kChunkBytes = kChunkPx * 4;       // per map
 #endif
 constexpr int kStagesW = RGBID_STAGES_W;        // W0 ring: 5 x 512 B
 constexpr int kStagesL = RGBID_STAGES_L;        // I0, gWx, gWy, gIx, gIy ring: 3 x 2560 B
-constexpr int kLateBytes = 5 * kChunkBytes;
-constexpr int kWarpRingBytes = kStagesW * kChunkBytes + kStagesL * kLateBytes;  // 10 KiB
-constexpr int kFastSmemBytes = kBuildWarps * kWarpRingBytes;                    // 80 KiB per CTA
+// PREW (WARP_ORDER = warpFirst above level 0): the late ring also carries the pre-warped current-frame maps W1, I1
+__host__ __device__ constexpr int late_maps(bool prew) { return prew ? 7 : 5; }
+__host__ __device__ constexpr int late_bytes(bool prew) { return late_maps(prew) * kChunkBytes; }
+__host__ __device__ constexpr int warp_ring_bytes(bool prew) { return kStagesW * kChunkBytes + kStagesL * late_bytes(prew); }  // 10 / 13 KiB
+__host__ __device__ constexpr int fast_smem_bytes(bool prew) { return kBuildWarps * warp_ring_bytes(prew); }               // 80 / 104 KiB per CTA
 
 struct FastGeom {
   int npx;        // rows * cols
@@ -575,13 +577,15 @@ __device__ __forceinline__ void accumulate_scalar(float* acc, float s, const flo
 }
 
 // CHIM: 0 no chi^2 sums, 1 chi^2 with the M-estimator chosen at run time, 2 chi^2 specialised for Student (the default)
-template <bool TRACKER, int CHIM>
+template <bool TRACKER, int CHIM, bool PREW = false>
 __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
     gn_build_fast_kernel(const GnLevelMaps M, const GnParams P, const FastGeom G, GnState* __restrict__ states,
                          const ScaleState* __restrict__ scales, double* __restrict__ partials, int partial_stride,
                          unsigned int* __restrict__ counters, rgbid_iter_trace* __restrict__ trace)
 {
   constexpr bool CHI = (CHIM != 0);
+  constexpr int kLateBytes = late_bytes(PREW), kWarpRingBytes = warp_ring_bytes(PREW);
+  static_assert(!PREW || (TRACKER && CHIM == 0), "pre-warped maps only exist in the tracker's warpFirst iterations");
   constexpr int NACC = CHI ? kAccChi : kAcc;
   const int chi_mest = (CHIM == 2) ? (int)RGBID_STUDENT : P.chi_mestimator;
   extern __shared__ __align__(128) unsigned char ring[];
@@ -614,6 +618,9 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
   const char* gWy = (const char*)M.gWy.row(b, 0);
   const char* gIx = (const char*)M.gIx.row(b, 0);
   const char* gIy = (const char*)M.gIy.row(b, 0);
+  const char* gW1 = (const char*)M.Wc.row(b, 0);  // PREW: pyrDown^level(warp_0(current frame)), src/visodo.cpp:1078-1105
+  const char* gI1 = (const char*)M.Ic.row(b, 0);
+  (void)gW1; (void)gI1;
   // (one elected lane) bulk copies of this warp's i-th chunk; the last chunk of a stream runs into the map's NaN
   // padding (see launch_gn_build), so every copy is a full 512 bytes
 #if RGBID_EVICT_FIRST
@@ -638,6 +645,11 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
     RGBID_G2S(dst + 2 * kChunkBytes, gWy + off, kChunkBytes, bar);
     RGBID_G2S(dst + 3 * kChunkBytes, gIx + off, kChunkBytes, bar);
     RGBID_G2S(dst + 4 * kChunkBytes, gIy + off, kChunkBytes, bar);
+    if (PREW) {
+      // written by the warp / pyramid kernels of this very iteration and read once: same streaming policy
+      RGBID_G2S(dst + 5 * kChunkBytes, gW1 + off, kChunkBytes, bar);
+      RGBID_G2S(dst + 6 * kChunkBytes, gI1 + off, kChunkBytes, bar);
+    }
   };
   // the keyframe maps were written before this Gauss-Newton schedule started: the first bulk copies may be in flight
   // while the previous kernel (scale estimation, or the previous iteration's solve) is still finishing
@@ -645,11 +657,21 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
 #pragma unroll
     for (int i = 0; i < kStagesW; ++i)
       if (i < my_n) issue_w(i);
+    if (!PREW) {
 #pragma unroll
-    for (int i = 0; i < kStagesL; ++i)
-      if (i < my_n) issue_l(i);
+      for (int i = 0; i < kStagesL; ++i)
+        if (i < my_n) issue_l(i);
+    }
   }
   grid_dep_wait();
+  if (PREW) {
+    // the pre-warped maps were written by the kernels of this very iteration: their copies wait for the dependency
+    if (elect_one()) {
+#pragma unroll
+      for (int i = 0; i < kStagesL; ++i)
+        if (i < my_n) issue_l(i);
+    }
+  }
 #if RGBID_TAIL_PROBE
   const long long probe_t0 = clock64();  // the pixel loop is counted from the end of the dependency wait
 #endif
@@ -679,7 +701,7 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
   const float bos_i = bias_i / sigma_i, bos_d = bias_d / sigma_d;
   const float c_i = (nu_i + 1.f) * (is_i * is_i), c_d = (nu_d + 1.f) * (is_d * is_d);  // (nu + 1) / sigma^2
   const float ifx = 1.f / P.fx, ify = 1.f / P.fy;
-  const cudaTextureObject_t texW = M.texW[b], texI = M.texI[b];
+  const cudaTextureObject_t texW = PREW ? 0 : M.texW[b], texI = PREW ? 0 : M.texI[b];
 
   float accs[kAcc];
 #pragma unroll
@@ -777,7 +799,7 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
   // S1 -> S3: warped inverse depth, raw intensity sample, 0 / NaN in-image flag.  Two sets, used alternately by a
   // loop unrolled by two, so that nothing has to be copied between iterations.
   float w1a[kPx], i1a[kPx], pina[kPx], w1b[kPx], i1b[kPx], pinb[kPx];
-  if (my_n > 0) {
+  if (my_n > 0 && !PREW) {
     if (TRACKER) {
       gather(0, w2n, wcn, nullptr, nullptr);
       second_projection(0, w2n, wcn, w1a, i1a, pina);
@@ -789,7 +811,9 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
   // one iteration: S1 + S2 fill the `n` set for chunk i + 1, S3 consumes the `c` set of chunk i
   auto iteration = [&](int i, float* w1c, float* i1c, float* pinc, float* w1n, float* i1n, float* pinn) {
     float* w1 = w1c; float* i1 = i1c; float* pin = pinc;
-    if (TRACKER) {
+    if (PREW) {
+      // nothing to gather: W1 / I1 arrive with the keyframe maps (read below, once the late ring has landed)
+    } else if (TRACKER) {
       if (i + 1 < my_n) second_projection(i + 1, w2n, wcn, w1n, i1n, pinn);  // warp-uniform
       if (i + 2 < my_n) gather(i + 2, w2n, wcn, nullptr, nullptr);
     } else {
@@ -807,9 +831,14 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
     const unsigned char* buf = ringL_p + (size_t)(i % kStagesL) * kLateBytes;
     mbar_wait(barL + (uint32_t)(i % kStagesL) * 8u, (uint32_t)(i / kStagesL) & 1u);
     float w0[kPx], gwx[kPx], gwy[kPx];
+    if (PREW) mbar_wait(barW + (uint32_t)(i % kStagesW) * 8u, (uint32_t)(i / kStagesW) & 1u);  // no gather stage waited for it
     lds_w0(i, w0);
     *(LaneVec*)gwx = *(const LaneVec*)(buf + 1 * kChunkBytes);
     *(LaneVec*)gwy = *(const LaneVec*)(buf + 2 * kChunkBytes);
+    if (PREW) {
+      *(LaneVec*)w1 = *(const LaneVec*)(buf + 5 * kChunkBytes);
+      *(LaneVec*)i1 = *(const LaneVec*)(buf + 6 * kChunkBytes);
+    }
 #pragma unroll
     for (int k = 0; k < kPx; ++k) {
       const float xf = g.xf0 + (float)k;
@@ -852,7 +881,8 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
       const float px = (xf - P.cx) * ifx;
       // max(0, min(r, 255)): a NaN sample becomes 255 like in the reference (warping_registration.cu:493-494);
       // + 0 / NaN: outside the image or invalid geometry
-      const float i1v = fmaxf(0.f, fminf(i1[k], 255.f)) + pin[k];
+      // (PREW: the warp kernel has clamped already and wrote NaN where the sample is invalid)
+      const float i1v = PREW ? i1[k] : fmaxf(0.f, fminf(i1[k], 255.f)) + pin[k];
       // intensityConstraint (estimate_VO.cu:176-212)
       const float gi0 = gix[k] * P.fx, gi1 = giy[k] * P.fy;
       const float gi2 = -fmaf(gi0, px, gi1 * py);
@@ -1094,10 +1124,12 @@ int gn_prepare_device()
     if (!upload_nu_table()) { err = cudaGetLastError(); if (err == cudaSuccess) err = cudaErrorUnknown; return false; }
     cudaError_t e = cudaSuccess;
 #define RGBID_FAST_ATTR(T, C) \
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gn_build_fast_kernel<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes)
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gn_build_fast_kernel<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast_smem_bytes(false))
     RGBID_FAST_ATTR(true, 0); RGBID_FAST_ATTR(true, 1); RGBID_FAST_ATTR(true, 2);
     RGBID_FAST_ATTR(false, 0); RGBID_FAST_ATTR(false, 1); RGBID_FAST_ATTR(false, 2);
 #undef RGBID_FAST_ATTR
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gn_build_fast_kernel<true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast_smem_bytes(true));
     err = e;
     return e == cudaSuccess;
   });
@@ -1160,11 +1192,15 @@ void launch_gn_build(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P
   // nu = 5 of computeWeight(STUDENT): the same expression), INDEPENDENT weighting.
   static const bool no_fast = [] { const char* e = getenv("RGBID_NO_FAST"); return e && e[0] == '1'; }();
   const size_t flat = (size_t)P.cols * sizeof(float);
-  const bool fast = !no_fast && !P.prewarped && vec && tex && M.tex_border && P.weighting == RGBID_INDEPENDENT &&
+  const bool prew = (P.prewarped != 0);
+  const bool fast = !no_fast && vec && (prew ? (P.mode == RGBID_MODE_TRACKER && !chi) : (tex && M.tex_border)) &&
+                    P.weighting == RGBID_INDEPENDENT &&
                     (P.student_nu || P.mestimator == RGBID_STUDENT) && M.W0.pitch == flat && M.I0.pitch == flat &&
                     M.gWx.pitch == flat && M.gWy.pitch == flat && M.gIx.pitch == flat && M.gIy.pitch == flat &&
                     (long long)P.rows * P.cols <= 2500000ll && padded(M.W0, P) && padded(M.I0, P) && padded(M.gWx, P) &&
-                    padded(M.gWy, P) && padded(M.gIx, P) && padded(M.gIy, P);
+                    padded(M.gWy, P) && padded(M.gIx, P) && padded(M.gIy, P) &&
+                    (!prew || (M.Wc.pitch == flat && M.Ic.pitch == flat && padded(M.Wc, P) && padded(M.Ic, P) &&
+                               aligned16(M.Wc) && aligned16(M.Ic)));
   if (fast) {
     FastGeom G;
     G.npx = P.rows * P.cols;
@@ -1181,8 +1217,11 @@ void launch_gn_build(const LaunchCtx& L, const GnLevelMaps& M, const GnParams& P
     const bool tracker = (P.mode == RGBID_MODE_TRACKER);
     const int chim = !chi ? 0 : (P.chi_mestimator == RGBID_STUDENT ? 2 : 1);
 #define RGBID_FAST_LAUNCH(T, C) \
-    launch_kernel_pdl(gn_build_fast_kernel<T, C>, grid, dim3(kBuildThreads), kFastSmemBytes, L.stream, L.pdl, M, P, G, states, scales, partials, partial_stride, counters, trace)
-    if (tracker) { if (chim == 0) RGBID_FAST_LAUNCH(true, 0); else if (chim == 1) RGBID_FAST_LAUNCH(true, 1); else RGBID_FAST_LAUNCH(true, 2); }
+    launch_kernel_pdl(gn_build_fast_kernel<T, C>, grid, dim3(kBuildThreads), fast_smem_bytes(false), L.stream, L.pdl, M, P, G, states, scales, partials, partial_stride, counters, trace)
+    if (prew)
+      launch_kernel_pdl(gn_build_fast_kernel<true, 0, true>, grid, dim3(kBuildThreads), fast_smem_bytes(true), L.stream, L.pdl, M, P, G,
+                        states, scales, partials, partial_stride, counters, trace);
+    else if (tracker) { if (chim == 0) RGBID_FAST_LAUNCH(true, 0); else if (chim == 1) RGBID_FAST_LAUNCH(true, 1); else RGBID_FAST_LAUNCH(true, 2); }
     else { if (chim == 0) RGBID_FAST_LAUNCH(false, 0); else if (chim == 1) RGBID_FAST_LAUNCH(false, 1); else RGBID_FAST_LAUNCH(false, 2); }
 #undef RGBID_FAST_LAUNCH
     ++*L.launches;
