@@ -292,3 +292,35 @@ def test_stale_prefetch_is_dropped(ctx):
     got = np.array(trk.track(sd, sc)[0].t[:])  # the refilled buffer must be read again, not served from the old upload
     trk.close()
     assert np.array_equal(got, want[3])
+
+
+def test_trace_is_only_recorded_on_request(ctx):
+    """rgbid_aligner_run records the per-iteration trace exactly when trace_out != NULL (rgbid_aligner_set_trace): a run
+    without it leaves the device-side trace of the previous traced run untouched and still returns the right pose."""
+    import ctypes as C
+    rows, cols, levels, its = 240, 320, 3, [4, 3, 2]
+    PA = pair_maps(seed=31, rows=rows, cols=cols, noise=True)
+    PB = pair_maps(seed=32, rows=rows, cols=cols, noise=True)
+    al = _gpu_align(ctx, PA, rows, cols, levels, capi.MODE_TRACKER, its)
+    outA = al.run(want_trace=True)
+    sumsA = np.array([np.asarray(tr["sums27"]) for tr in outA["trace"][0]])
+    assert np.abs(sumsA).max() > 0
+    # pair B, no trace
+    al.set_keyframe(0, cuda(PB["WA"]), cuda(PB["IA"]))
+    al.set_current_rgbd(0, cuda(PB["dB"]), cuda(PB["cB"]))
+    outB = al.run(want_trace=False)
+    refB = _oracle_align(PB, rows, cols, levels, orc.MODE_TRACKER, its)
+    _check(outB, refB, label="untraced run")
+    n = sum(its) + 1
+    raw = (capi.IterTrace * n)()
+    R, t = np.zeros((1, 9)), np.zeros((1, 3))
+    capi.check(al.lib.rgbid_aligner_fetch(al.h, R.ctypes.data_as(capi.c_double_p), t.ctypes.data_as(capi.c_double_p), None, None, raw),
+               "aligner_fetch")
+    still = np.array([np.array(raw[i].sums27[:]) for i in range(n)])
+    assert np.array_equal(still[:len(sumsA)], sumsA), "the untraced run overwrote the trace"
+    # pair B again, traced: now the records are B's
+    outB2 = al.run(want_trace=True)
+    sumsB = np.array([np.asarray(tr["sums27"]) for tr in outB2["trace"][0]])
+    assert not np.array_equal(sumsB[0], sumsA[0])
+    assert sums_rel_err(sumsB[0], refB["trace"][0]["sums27"]) < SUMS_TOL
+    assert np.allclose(outB2["t"], outB["t"], atol=1e-12) and np.allclose(outB2["R"], outB["R"], atol=1e-12)
