@@ -33,6 +33,16 @@ void aligner_current_pyramid(rgbid_aligner* al, int first, int batch)
 void aligner_copy_current_to_keyframe(rgbid_aligner* al, int first, int batch, const int* active)
 {
   LaunchCtx L = al->ctx->L();
+  {
+    // all levels of both maps in one launch
+    ImgB src[2 * RGBID_MAX_LEVELS], dst[2 * RGBID_MAX_LEVELS];
+    int n = 0;
+    for (int l = 0; l < al->cfg.levels; ++l) {
+      src[n] = sub(al->maps[MAP_W_CUR][l], first); dst[n++] = sub(al->maps[MAP_W_KF][l], first);
+      src[n] = sub(al->maps[MAP_I_CUR][l], first); dst[n++] = sub(al->maps[MAP_I_KF][l], first);
+    }
+    if (launch_copy_list(L, src, dst, n, batch, active)) return;
+  }
   for (int l = 0; l < al->cfg.levels; ++l)  // copyImages per level, src/visodo.cpp:837-840
     launch_copy2(L, sub(al->maps[MAP_W_CUR][l], first), sub(al->maps[MAP_W_KF][l], first),
                  sub(al->maps[MAP_I_CUR][l], first), sub(al->maps[MAP_I_KF][l], first), batch, active);
@@ -53,6 +63,18 @@ void aligner_keyframe_derivatives(rgbid_aligner* al, int first, int batch, const
     launch_bilateral2(L, M(MAP_W_KF, 0), M(MAP_WF, 0), 2.f * 0.0025f, M(MAP_I_KF, 0), M(MAP_IF, 0), 3.f, batch, active);
     for (int l = 1; l < levels; ++l)
       launch_pyr_down2(L, M(MAP_WF, l - 1), M(MAP_WF, l), M(MAP_IF, l - 1), M(MAP_IF, l), batch, active);
+    if (al->image_filtering != RGBID_FILTER_GRADS && 4 * levels <= 16) {
+      // the Sobel passes of every level of the filtered AND of the raw pyramid in one launch
+      ImgB src[16], gx[16], gy[16];
+      int n = 0;
+      for (int l = 0; l < levels; ++l) {
+        src[n] = M(MAP_IF, l); gx[n] = M(MAP_CGIX, l); gy[n++] = M(MAP_CGIY, l);
+        src[n] = M(MAP_WF, l); gx[n] = M(MAP_CGWX, l); gy[n++] = M(MAP_CGWY, l);
+        src[n] = M(MAP_I_KF, l); gx[n] = M(MAP_GIX, l); gy[n++] = M(MAP_GIY, l);
+        src[n] = M(MAP_W_KF, l); gx[n] = M(MAP_GWX, l); gy[n++] = M(MAP_GWY, l);
+      }
+      if (launch_gradient_list(L, src, gx, gy, n, batch, active)) return;
+    }
     for (int l = 0; l < levels; ++l)
       launch_gradient2(L, M(MAP_IF, l), M(MAP_CGIX, l), M(MAP_CGIY, l), M(MAP_WF, l), M(MAP_CGWX, l), M(MAP_CGWY, l),
                        batch, active);
@@ -63,6 +85,15 @@ void aligner_keyframe_derivatives(rgbid_aligner* al, int first, int batch, const
       launch_copy2(L, M(MAP_CGWX, l), M(MAP_GWX, l), M(MAP_CGWY, l), M(MAP_GWY, l), batch, active);
     }
   } else {
+    if (2 * levels <= 16) {
+      ImgB src[16], gx[16], gy[16];
+      int n = 0;
+      for (int l = 0; l < levels; ++l) {
+        src[n] = M(MAP_I_KF, l); gx[n] = M(MAP_GIX, l); gy[n++] = M(MAP_GIY, l);
+        src[n] = M(MAP_W_KF, l); gx[n] = M(MAP_GWX, l); gy[n++] = M(MAP_GWY, l);
+      }
+      if (launch_gradient_list(L, src, gx, gy, n, batch, active)) return;
+    }
     for (int l = 0; l < levels; ++l)  // src/visodo.cpp:869-877, keyframe_align.cpp:168-176
       launch_gradient2(L, M(MAP_I_KF, l), M(MAP_GIX, l), M(MAP_GIY, l), M(MAP_W_KF, l), M(MAP_GWX, l), M(MAP_GWY, l),
                        batch, active);

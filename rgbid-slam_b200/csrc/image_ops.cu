@@ -238,6 +238,76 @@ __global__ void __launch_bounds__(BX* BY) gradient2_vec_kernel(ImgB srcA, ImgB g
   *(float4*)(gy.row(b, y) + x0) = make_float4(rv[0] / 8.f, rv[1] / 8.f, rv[2] / 8.f, rv[3] / 8.f);
 }
 
+// One launch for a LIST of maps of different sizes (all pyramid levels of the raw and of the filtered keyframe: 16
+// Sobel passes, or the 8 copies of saveCurrentImagesAsOdoKeyframes): the coarse levels are a few microseconds of work
+// each and paid a launch apiece.  blockIdx.x walks the tiles of all list entries; per entry the body is the per-map
+// kernel's (same taps, same order: bit-identical).
+constexpr int kMaxListMaps = 16;
+struct MapList {
+  ImgB a[kMaxListMaps], b[kMaxListMaps], c[kMaxListMaps];  // gradient: src, gx, gy; copy: src, dst, -
+  int tile_begin[kMaxListMaps + 1];
+  int tiles_x[kMaxListMaps];
+  int n;
+};
+
+__device__ __forceinline__ bool list_locate(const MapList& Lm, int& slot, int& x0, int& y)
+{
+  const int t = blockIdx.x;
+  slot = 0;
+#pragma unroll 1
+  while (slot + 1 < Lm.n && t >= Lm.tile_begin[slot + 1]) ++slot;
+  const int tile = t - Lm.tile_begin[slot];
+  const int tx = tile % Lm.tiles_x[slot], ty = tile / Lm.tiles_x[slot];
+  x0 = 4 * (tx * BX + threadIdx.x);
+  y = ty * BY + threadIdx.y;
+  return x0 < Lm.a[slot].cols && y < Lm.a[slot].rows;
+}
+
+__global__ void __launch_bounds__(BX* BY) gradient_list_kernel(const __grid_constant__ MapList Lm, const int* __restrict__ active)
+{
+  const int b = blockIdx.z;
+  RGBID_ACTIVE_GUARD(b);
+  int slot, x0, y;
+  if (!list_locate(Lm, slot, x0, y)) return;
+  const ImgB& src = Lm.a[slot];
+  const ImgB& gx = Lm.b[slot];
+  const ImgB& gy = Lm.c[slot];
+  float v[3][6];
+#pragma unroll
+  for (int dy = -1; dy < 2; ++dy) {
+    const float* srow = src.row(b, min(max(0, y + dy), src.rows - 1));
+    const float4 c = __ldg((const float4*)(srow + x0));
+    v[dy + 1][0] = __ldg(srow + max(x0 - 1, 0));
+    v[dy + 1][1] = c.x; v[dy + 1][2] = c.y; v[dy + 1][3] = c.z; v[dy + 1][4] = c.w;
+    v[dy + 1][5] = __ldg(srow + min(x0 + 4, src.cols - 1));
+  }
+  float rh[4], rv[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    rh[k] = 0.f; rv[k] = 0.f;
+#pragma unroll
+    for (int dx = -1; dx < 2; ++dx) {
+#pragma unroll
+      for (int dy = -1; dy < 2; ++dy) {
+        const float t = v[dy + 1][k + dx + 1];
+        rh[k] += t * (float)(dx * (2 - dy * dy));
+        rv[k] += t * (float)(dy * (2 - dx * dx));
+      }
+    }
+  }
+  *(float4*)(gx.row(b, y) + x0) = make_float4(rh[0] / 8.f, rh[1] / 8.f, rh[2] / 8.f, rh[3] / 8.f);
+  *(float4*)(gy.row(b, y) + x0) = make_float4(rv[0] / 8.f, rv[1] / 8.f, rv[2] / 8.f, rv[3] / 8.f);
+}
+
+__global__ void __launch_bounds__(BX* BY) copy_list_kernel(const __grid_constant__ MapList Lm, const int* __restrict__ active)
+{
+  const int b = blockIdx.z;
+  RGBID_ACTIVE_GUARD(b);
+  int slot, x0, y;
+  if (!list_locate(Lm, slot, x0, y)) return;
+  *(float4*)(Lm.b[slot].row(b, y) + x0) = *(const float4*)(Lm.a[slot].row(b, y) + x0);
+}
+
 // ---- bilateral: K23 (src/cuda/filters.cu:86-135) ----------------------------------------------------
 __global__ void __launch_bounds__(BX* BY) bilateral2_kernel(ImgB srcA, ImgB dstA, float sigmaA, ImgB srcB,
                                                              ImgB dstB, float sigmaB, int batch,
@@ -545,6 +615,51 @@ void launch_copy2(const LaunchCtx& L, ImgB srcA, ImgB dstA, ImgB srcB, ImgB dstB
     copy2_kernel<<<grid2d(srcA.cols, srcA.rows, batch * nm), dim3(BX, BY), 0, L.stream>>>(srcA, dstA, srcB, dstB, batch,
                                                                                           active);
   ++*L.launches;
+}
+
+static bool list_ok(const ImgB& m) { return m.cols % 4 == 0 && aligned(m.p, 16) && m.pitch % 16 == 0 && m.sstride % 16 == 0; }
+
+static void list_finish(MapList& Lm)
+{
+  int t = 0;
+  for (int i = 0; i < Lm.n; ++i) {
+    Lm.tile_begin[i] = t;
+    Lm.tiles_x[i] = (Lm.a[i].cols / 4 + BX - 1) / BX;
+    t += Lm.tiles_x[i] * ((Lm.a[i].rows + BY - 1) / BY);
+  }
+  Lm.tile_begin[Lm.n] = t;
+}
+
+bool launch_gradient_list(const LaunchCtx& L, const ImgB* src, const ImgB* gx, const ImgB* gy, int n, int batch, const int* active)
+{
+  if (n < 1 || n > kMaxListMaps) return false;
+  MapList Lm;
+  memset(&Lm, 0, sizeof(Lm));
+  for (int i = 0; i < n; ++i) {
+    if (!list_ok(src[i]) || !list_ok(gx[i]) || !list_ok(gy[i])) return false;
+    Lm.a[i] = src[i]; Lm.b[i] = gx[i]; Lm.c[i] = gy[i];
+  }
+  Lm.n = n;
+  list_finish(Lm);
+  gradient_list_kernel<<<dim3(Lm.tile_begin[n], 1, batch), dim3(BX, BY), 0, L.stream>>>(Lm, active);
+  ++*L.launches;
+  return true;
+}
+
+bool launch_copy_list(const LaunchCtx& L, const ImgB* src, const ImgB* dst, int n, int batch, const int* active)
+{
+  if (n < 1 || n > kMaxListMaps) return false;
+  MapList Lm;
+  memset(&Lm, 0, sizeof(Lm));
+  for (int i = 0; i < n; ++i) {
+    if (!list_ok(src[i]) || !list_ok(dst[i])) return false;
+    Lm.a[i] = src[i]; Lm.b[i] = dst[i];
+  }
+  Lm.n = n;
+  list_finish(Lm);
+  copy_list_kernel<<<dim3(Lm.tile_begin[n], 1, batch), dim3(BX, BY), 0, L.stream>>>(Lm, active);
+  ++*L.launches;
+  return true;
 }
 
 void launch_fill(const LaunchCtx& L, ImgB dst, float value, int batch, const int* active)

@@ -72,6 +72,11 @@ void launch_pyr_down2(const LaunchCtx& L, ImgB srcA, ImgB dstA, ImgB srcB, ImgB 
                       const int* active = nullptr);
 void launch_gradient2(const LaunchCtx& L, ImgB srcA, ImgB gxA, ImgB gyA, ImgB srcB, ImgB gxB, ImgB gyB, int batch,
                       const int* active = nullptr);
+// one launch for up to 16 maps of different sizes (all levels of both keyframe pyramids); false = not applicable
+// (unaligned maps): the caller falls back to the per-level launches
+bool launch_gradient_list(const LaunchCtx& L, const ImgB* src, const ImgB* gx, const ImgB* gy, int n, int batch,
+                          const int* active = nullptr);
+bool launch_copy_list(const LaunchCtx& L, const ImgB* src, const ImgB* dst, int n, int batch, const int* active = nullptr);
 void launch_bilateral2(const LaunchCtx& L, ImgB srcA, ImgB dstA, float sigmaA, ImgB srcB, ImgB dstB, float sigmaB,
                        int batch, const int* active = nullptr);
 void launch_copy2(const LaunchCtx& L, ImgB srcA, ImgB dstA, ImgB srcB, ImgB dstB, int batch,
