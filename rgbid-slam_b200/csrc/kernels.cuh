@@ -76,6 +76,9 @@ void launch_gradient2(const LaunchCtx& L, ImgB srcA, ImgB gxA, ImgB gyA, ImgB sr
 // (unaligned maps): the caller falls back to the per-level launches
 bool launch_gradient_list(const LaunchCtx& L, const ImgB* src, const ImgB* gx, const ImgB* gy, int n, int batch,
                           const int* active = nullptr);
+// vertex map + Sobel gradients + normal map of a (fused) inverse-depth map in one pass; false = unaligned maps
+bool launch_keyframe_maps(const LaunchCtx& L, ImgB depth_inv, ImgB gx, ImgB gy, ImgB vmap, ImgB nmap, float fx, float fy,
+                          float cx, float cy, int batch);
 bool launch_copy_list(const LaunchCtx& L, const ImgB* src, const ImgB* dst, int n, int batch, const int* active = nullptr);
 void launch_bilateral2(const LaunchCtx& L, ImgB srcA, ImgB dstA, float sigmaA, ImgB srcB, ImgB dstB, float sigmaB,
                        int batch, const int* active = nullptr);

@@ -155,6 +155,7 @@ void refresh_integration_maps(rgbid_tracker* t)
   LaunchCtx L = t->ctx->L();
   const rgbid_align_config& c = al->cfg;
   ImgB none = make_img(nullptr, 0, 0, 0);
+  if (launch_keyframe_maps(L, t->intW, t->intGx, t->intGy, t->vmap, t->nmap, c.fx, c.fy, c.cx, c.cy, c.batch)) return;
   launch_vmap(L, t->intW, t->vmap, c.fx, c.fy, c.cx, c.cy, c.batch);
   launch_gradient2(L, t->intW, t->intGx, t->intGy, none, none, none, c.batch);
   launch_nmap_gradients(L, t->intW, t->intGx, t->intGy, t->nmap, c.fx, c.fy, c.cx, c.cy, c.batch);
