@@ -506,10 +506,11 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
 
 // ------------------------------------------------------------------------------------------------------------
 // gn_build_fast_kernel: the shipped configuration (Student-t weights, INDEPENDENT weighting, texture gathers, flat
-// keyframe maps) of gn_build_kernel, rebuilt around the measured limits of the B200 SM (tools/ubench/pipes.cu):
-// an FP32 FMA-pipe instruction on three distinct registers issues at ~0.7 / clk / SMSP and the path needs ~140 of them
-// per pixel, so the kernel is bound by the FMA pipe before DRAM (profiles/README.md).  What it does differently from
-// the generic kernel:
+// keyframe maps) of gn_build_kernel, rebuilt around the measured limits of the B200 SM (tools/ubench/pipes.cu,
+// texpat.cu): the path needs ~140 FP32 FMA-pipe instructions out of 200 per pixel, half of them lose a dispatch cycle to
+// register-bank conflicts, and its two gathers per pixel keep the texture unit ~2/3 busy -- the pixel loop runs at 0.74
+// of the HBM peak, limited by the dispatch port and the texture unit, not by DRAM (profiles/README.md, round 2).
+// What it does differently from the generic kernel:
 //   * the six keyframe maps arrive through the TMA engine: each warp owns two rings of shared-memory slots (W0:
 //     kStagesW x 512 B, the five other maps: kStagesL x 2560 B), one elected lane issues 1-D bulk copies
 //     (cp.async.bulk, SASS UBLKCP) several chunks ahead and the warp waits on an mbarrier -- no CTA-wide barrier in
@@ -521,7 +522,9 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
 //   * the inverse-depth texture uses border addressing (0 outside), so "outside the image" falls out of the
 //     reference's own `res > 0` test and only the intensity fetch needs an explicit in-image test (four compares on
 //     the ALU pipe); validity is carried by NaN propagation into the weight and ONE compare per constraint;
-//   * the 2 x 27 accumulations are FMAs predicated on that compare (no selects, no sanitising of the rows).
+//   * the 2 x 27 accumulations are FMAs predicated on that compare (no selects, no sanitising of the rows);
+//   * the bulk copies carry an L2 evict-first policy (streamed once per launch), and in the warpFirst schedule above
+//     level 0 (PREW) the pre-warped current-frame maps travel through the same ring instead of being gathered.
 // Arithmetic differs from the generic kernel only in rounding (same formulas re-associated); the parity tests
 // hold both against the oracle and the reference's own kernels.
 // ------------------------------------------------------------------------------------------------------------
@@ -651,6 +654,7 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
       RGBID_G2S(dst + 6 * kChunkBytes, gI1 + off, kChunkBytes, bar);
     }
   };
+#undef RGBID_G2S
   // the keyframe maps were written before this Gauss-Newton schedule started: the first bulk copies may be in flight
   // while the previous kernel (scale estimation, or the previous iteration's solve) is still finishing
   if (elect_one()) {
