@@ -147,7 +147,8 @@ static GnLevelMaps level_maps(const rgbid_aligner* al, int level, bool cov_gradi
 // could run under the other group's latency-bound scale estimation and 6x6 solve.  Measured on B200 (32 streams):
 // 2.98 ms per step against 2.82 ms for the single chain -- the two kernels do not share an SM (different shared-memory
 // carve-outs), so the chains only interleave at kernel granularity and pay twice the launches.  Off by default.
-static void record_chain(rgbid_aligner* al, LaunchCtx L, int first, int count, cudaEvent_t after_first_launch = nullptr)
+static void record_chain(rgbid_aligner* al, LaunchCtx L, int first, int count, cudaEvent_t after_first_launch = nullptr,
+                         int part = ALIGN_PART_ALL)
 {
   bool signalled = (after_first_launch == nullptr);
   const rgbid_align_config& c = al->cfg;
@@ -156,7 +157,7 @@ static void record_chain(rgbid_aligner* al, LaunchCtx L, int first, int count, c
   const bool estimate_scale = tracker ? (c.sigma_estimator == RGBID_SIGMA_PDF) : true;
   const bool warp_first = tracker && c.warp_first;  // KeyframeAlign has no such option (src/keyframe_align.cpp:178-350)
   int done = 0;
-  for (int level = c.levels - 1; level >= c.finest_level; --level) {
+  for (int level = c.levels - 1; level >= c.finest_level && part != ALIGN_PART_COV; --level) {
     for (int it = 0; it < c.iterations[level]; ++it) {
       GnParams P = base_params(al, level);
       P.first = first; P.batch = count; P.batch_total = c.batch;
@@ -210,7 +211,7 @@ static void record_chain(rgbid_aligner* al, LaunchCtx L, int first, int count, c
       launch_gn_build(L, M, P, al->d_states, al->d_scales, al->d_partials, 32, al->d_counters, al->d_trace);
     }
   }
-  if (tracker) {
+  if (tracker && part != ALIGN_PART_ITERATIONS) {
     // covariance pass at the finest level on the bilateral-filtered gradients with fixed scales and
     // Student(5) weights, no pose update (src/visodo.cpp:1283-1409) + end-of-frame chi^2 (:1411-1415)
     GnParams P = base_params(al, c.finest_level);
@@ -223,16 +224,18 @@ static void record_chain(rgbid_aligner* al, LaunchCtx L, int first, int count, c
   }
 }
 
-void aligner_record_schedule(rgbid_aligner* al)
+void aligner_record_schedule(rgbid_aligner* al, int part)
 {
   const rgbid_align_config& c = al->cfg;
   LaunchCtx L = al->ctx->L();
-  launch_gn_init(L, al->d_states, al->d_init, al->d_init + 9 * c.batch, c.batch, c.levels, c.fx, c.fy, c.cx, c.cy,
-                 al->d_trace_flag);
+  if (part != ALIGN_PART_COV)
+    launch_gn_init(L, al->d_states, al->d_init, al->d_init + 9 * c.batch, c.batch, c.levels, c.fx, c.fy, c.cx, c.cy,
+                   al->d_trace_flag);
   if (al->side_stream == nullptr || c.batch < 2) {
-    record_chain(al, L, 0, c.batch);
+    record_chain(al, L, 0, c.batch, nullptr, part);
     return;
   }
+  // (the two-chain experiment is only ever recorded whole: aligner_can_split() is false with a side stream)
   const int half = c.batch / 2;
   LaunchCtx L2 = L;
   L2.stream = al->side_stream;
@@ -389,7 +392,8 @@ int rgbid_aligner_destroy(rgbid_aligner* al)
 {
   if (!al) return RGBID_OK;
   cudaStreamSynchronize(al->ctx->stream);
-  if (al->gn_exec) cudaGraphExecDestroy(al->gn_exec);
+  for (int i = 0; i < 3; ++i)
+    if (al->gn_exec[i]) cudaGraphExecDestroy(al->gn_exec[i]);
   if (al->side_stream) { cudaStreamSynchronize(al->side_stream); cudaStreamDestroy(al->side_stream); }
   if (al->ev_fork) cudaEventDestroy(al->ev_fork);
   if (al->ev_join) cudaEventDestroy(al->ev_join);
@@ -609,29 +613,39 @@ int rgbid_aligner_map(rgbid_aligner* al, int which, int level, int index, float*
 namespace rgbid {
 
 // Launch (or replay) the schedule; d_init must already hold the initial guesses.
-int aligner_enqueue_device_init(rgbid_aligner* al)
+bool aligner_can_split(const rgbid_aligner* al)
+{
+  return al->cfg.mode == RGBID_MODE_TRACKER && al->side_stream == nullptr;
+}
+
+// part: the whole schedule, or -- tracker mode -- the iterations and the covariance pass as two graphs, so that the caller
+// can read the pose back and go on with its host work while the covariance pass runs (tracker.cu)
+int aligner_enqueue_part(rgbid_aligner* al, int part)
 {
   cudaStream_t s = al->ctx->stream;
+  if (part != ALIGN_PART_ALL && !aligner_can_split(al)) return RGBID_ERR_STATE;
   if (!al->use_graph) {
-    aligner_record_schedule(al);
+    aligner_record_schedule(al, part);
     return check_last(al->ctx);
   }
-  if (!al->gn_exec) {
+  if (!al->gn_exec[part]) {
     long long before = al->ctx->launches;
     cudaGraph_t graph = nullptr;
     RGBID_CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    aligner_record_schedule(al);
+    aligner_record_schedule(al, part);
     cudaError_t e = cudaStreamEndCapture(s, &graph);
     if (e != cudaSuccess) return RGBID_ERR_CUDA_BASE + (int)e;
-    al->gn_graph_launches = al->ctx->launches - before;
+    al->gn_graph_launches[part] = al->ctx->launches - before;
     al->ctx->launches = before;
-    e = cudaGraphInstantiate(&al->gn_exec, graph, 0);
+    e = cudaGraphInstantiate(&al->gn_exec[part], graph, 0);
     cudaGraphDestroy(graph);
-    if (e != cudaSuccess) { al->gn_exec = nullptr; return RGBID_ERR_CUDA_BASE + (int)e; }
+    if (e != cudaSuccess) { al->gn_exec[part] = nullptr; return RGBID_ERR_CUDA_BASE + (int)e; }
   }
-  RGBID_CUDA_TRY(cudaGraphLaunch(al->gn_exec, s));
-  al->ctx->launches += al->gn_graph_launches;
+  RGBID_CUDA_TRY(cudaGraphLaunch(al->gn_exec[part], s));
+  al->ctx->launches += al->gn_graph_launches[part];
   return RGBID_OK;
 }
+
+int aligner_enqueue_device_init(rgbid_aligner* al) { return aligner_enqueue_part(al, ALIGN_PART_ALL); }
 
 }  // namespace rgbid

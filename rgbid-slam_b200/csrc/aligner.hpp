@@ -50,8 +50,8 @@ struct rgbid_aligner {
   // CUDA graph of the whole schedule
   bool use_graph;
   bool use_pdl;  // programmatic dependent launch between the Gauss-Newton kernels (RGBID_NO_PDL=1 disables)
-  cudaGraphExec_t gn_exec;
-  long long gn_graph_launches;
+  cudaGraphExec_t gn_exec[3];       // indexed by ALIGN_PART_*
+  long long gn_graph_launches[3];
   int image_filtering;
   // second stream + fork / join events: the schedule is issued as two chains of frame-pair groups
   cudaStream_t side_stream;
@@ -76,7 +76,11 @@ namespace rgbid {
 void aligner_keyframe_derivatives(rgbid_aligner* al, int first, int batch, const int* active, bool pyramid_from_l0);
 void aligner_current_pyramid(rgbid_aligner* al, int first, int batch);
 void aligner_copy_current_to_keyframe(rgbid_aligner* al, int first, int batch, const int* active);
-void aligner_record_schedule(rgbid_aligner* al);
+enum { ALIGN_PART_ALL = 0, ALIGN_PART_ITERATIONS = 1, ALIGN_PART_COV = 2 };
+void aligner_record_schedule(rgbid_aligner* al, int part = ALIGN_PART_ALL);
 int aligner_enqueue_device_init(rgbid_aligner* al);
+// tracker mode: the Gauss-Newton iterations and the covariance pass as two separately launched graphs
+bool aligner_can_split(const rgbid_aligner* al);
+int aligner_enqueue_part(rgbid_aligner* al, int part);
 
 }  // namespace rgbid

@@ -133,6 +133,9 @@ struct rgbid_tracker {
   const void* pf_depth[2]; const void* pf_rgb[2]; bool pf_valid[2]; int pf_next;
   long long pf_issued_at[2], track_calls;  // a prefetched frame is good for the current or the next track call only
   cudaEvent_t ev_track_done; bool ev_track_done_valid;  // end of the device work queued by the last track call
+  // split read-back: the pose is read when the iterations are done, the covariance / chi^2 (second copy of the solver
+  // state) with the covisibility counts, so that the host's pose bookkeeping runs under the covariance pass
+  GnState* h_states_cov; cudaEvent_t ev_pose, ev_iter_done; cudaStream_t rb_stream; bool split_cov;
 };
 
 namespace {
@@ -232,6 +235,7 @@ int rgbid_tracker_create(rgbid_ctx* ctx, const rgbid_tracker_config* cfg, rgbid_
   t->custom_on = false; t->d_custom = nullptr; t->d_canvas = nullptr;
   t->sink = nullptr; t->sink_user = nullptr; t->h_handoff = nullptr; t->handoff_bytes = 0;
   t->ev_track_done = nullptr; t->ev_track_done_valid = false;
+  t->h_states_cov = nullptr; t->ev_pose = nullptr; t->ev_iter_done = nullptr; t->rb_stream = nullptr; t->split_cov = false;
   t->copy_stream = nullptr; t->pf_next = 0; t->track_calls = 0; t->pf_issued_at[0] = t->pf_issued_at[1] = 0;
   for (int i = 0; i < 2; ++i) { t->ev_copy[i] = nullptr; t->d_prefetch[i] = nullptr; t->pf_depth[i] = t->pf_rgb[i] = nullptr; t->pf_valid[i] = false; }
   int rc = rgbid_aligner_create(ctx, &t->cfg.align, &t->al);
@@ -259,6 +263,10 @@ int rgbid_tracker_create(rgbid_ctx* ctx, const rgbid_tracker_config* cfg, rgbid_
   if (e == cudaSuccess) e = cudaMallocHost(&t->h_proj, sizeof(Proj) * 4 * B);
   if (e == cudaSuccess) e = cudaMalloc(&t->d_counts, sizeof(unsigned int) * 8 * B);
   if (e == cudaSuccess) e = cudaMallocHost(&t->h_counts, sizeof(unsigned int) * 8 * B);
+  if (e == cudaSuccess) e = cudaMallocHost(&t->h_states_cov, sizeof(GnState) * B);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_pose, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_iter_done, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&t->rb_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaMalloc(&t->d_flags, sizeof(int) * 4 * B);
   if (e == cudaSuccess) e = cudaMallocHost(&t->h_flags, sizeof(int) * 4 * B);
   if (e != cudaSuccess) { rgbid_tracker_destroy(t); return RGBID_ERR_CUDA_BASE + (int)e; }
@@ -282,6 +290,10 @@ int rgbid_tracker_destroy(rgbid_tracker* t)
   if (t->h_handoff) cudaFreeHost(t->h_handoff);
   if (t->h_proj) cudaFreeHost(t->h_proj);
   if (t->h_counts) cudaFreeHost(t->h_counts);
+  if (t->h_states_cov) cudaFreeHost(t->h_states_cov);
+  if (t->ev_pose) cudaEventDestroy(t->ev_pose);
+  if (t->ev_iter_done) cudaEventDestroy(t->ev_iter_done);
+  if (t->rb_stream) cudaStreamDestroy(t->rb_stream);
   if (t->h_flags) cudaFreeHost(t->h_flags);
   delete t;
   return RGBID_OK;
@@ -604,10 +616,28 @@ static int track_core(rgbid_tracker* t, const uint16_t* depth, const uint8_t* rg
     }
   }
   upload_control(L, al->d_init, al->h_init, sizeof(double) * 12 * B);
-  int rc = aligner_enqueue_device_init(al);
-  if (rc != RGBID_OK) return rc;
-  RGBID_CUDA_TRY(cudaMemcpyAsync(al->h_states, al->d_states, sizeof(GnState) * B, cudaMemcpyDeviceToHost, s));
-  RGBID_CUDA_TRY(cudaStreamSynchronize(s));
+  // The pose is final when the iterations are: it is read back there, and the covariance pass (a whole level-0 launch
+  // with the chi^2 sums) runs while the host does the pose bookkeeping below and queues the covisibility kernel behind
+  // it; its results (covariance, chi^2) come back with the covisibility counts.  RGBID_NO_SPLIT_COV=1: one read-back.
+  static const bool no_split = [] { const char* e = getenv("RGBID_NO_SPLIT_COV"); return e && e[0] == '1'; }();
+  t->split_cov = aligner_can_split(al) && !no_split;
+  int rc;
+  if (t->split_cov) {
+    if ((rc = aligner_enqueue_part(al, ALIGN_PART_ITERATIONS)) != RGBID_OK) return rc;
+    // the pose copy goes through a stream of its own, so that the covariance pass does not queue behind it (the pass
+    // only writes the covariance / chi^2 fields of the state, which this copy is not read for)
+    RGBID_CUDA_TRY(cudaEventRecord(t->ev_iter_done, s));
+    RGBID_CUDA_TRY(cudaStreamWaitEvent(t->rb_stream, t->ev_iter_done, 0));
+    RGBID_CUDA_TRY(cudaMemcpyAsync(al->h_states, al->d_states, sizeof(GnState) * B, cudaMemcpyDeviceToHost, t->rb_stream));
+    RGBID_CUDA_TRY(cudaEventRecord(t->ev_pose, t->rb_stream));
+    if ((rc = aligner_enqueue_part(al, ALIGN_PART_COV)) != RGBID_OK) return rc;
+    RGBID_CUDA_TRY(cudaMemcpyAsync(t->h_states_cov, al->d_states, sizeof(GnState) * B, cudaMemcpyDeviceToHost, s));
+    RGBID_CUDA_TRY(cudaEventSynchronize(t->ev_pose));
+  } else {
+    if ((rc = aligner_enqueue_device_init(al)) != RGBID_OK) return rc;
+    RGBID_CUDA_TRY(cudaMemcpyAsync(al->h_states, al->d_states, sizeof(GnState) * B, cudaMemcpyDeviceToHost, s));
+    RGBID_CUDA_TRY(cudaStreamSynchronize(s));
+  }
   if ((rc = check_last(ctx)) != RGBID_OK) return rc;
 
   // ---- pose bookkeeping (:1463-1468, :2059-2117) + covisibility transforms (:1481-1514, :2172-2186) ----------
@@ -620,12 +650,12 @@ static int track_core(rgbid_tracker* t, const uint16_t* depth, const uint8_t* rg
     // stream is already lost does not, src/visodo.cpp:2111-2116)
     r.frame_index = S.global_time;
     r.status = g.status;
-    r.chi_square = g.chi_square; r.chi_test = g.chi_test; r.ndof = g.ndof;
+    r.chi_square = g.chi_square; r.chi_test = g.chi_test; r.ndof = g.ndof;  // (split read-back: filled in below)
     const bool ok = (g.status == RGBID_OK);
     if (ok) {
       memcpy(S.dR, g.R, sizeof(double) * 9);
       memcpy(S.dt, g.t, sizeof(double) * 3);
-      memcpy(S.dcov, g.cov, sizeof(double) * 36);
+      memcpy(S.dcov, g.cov, sizeof(double) * 36);                            // (split read-back: filled in below)
       double Rt[9], dRc[9], dtc[3], diff[3], twist[6];
       mat3_transpose(&prevR[9 * b], Rt);
       mat3_mul(Rt, S.dR, dRc);
@@ -670,6 +700,16 @@ static int track_core(rgbid_tracker* t, const uint16_t* depth, const uint8_t* rg
   }
   RGBID_CUDA_TRY(cudaMemcpyAsync(t->h_counts, t->d_counts, sizeof(unsigned int) * 8 * B, cudaMemcpyDeviceToHost, s));
   RGBID_CUDA_TRY(cudaStreamSynchronize(s));
+  if (t->split_cov) {
+    // the covariance pass has long finished: its part of the solver state
+    for (int b = 0; b < B; ++b) {
+      const GnState& g = t->h_states_cov[b];
+      rgbid_frame_result& r = results[b];
+      r.chi_square = g.chi_square; r.chi_test = g.chi_test; r.ndof = g.ndof;
+      if (g.status == RGBID_OK) memcpy(t->st[b].dcov, g.cov, sizeof(double) * 36);
+      memcpy(&al->h_states[b], &g, sizeof(GnState));  // rgbid_aligner_* accessors see the complete state
+    }
+  }
 
   // ---- keyframe decisions (:2175-2215) ----------------------------------------------------------------------------
   bool any_odo = false, any_int = false, any_fuse = false, any_mask = false;
