@@ -50,7 +50,10 @@ struct PixelParams {
   int chi_mestimator;
 };
 
-__device__ __forceinline__ float chi_rho_dev(float e, int mest)
+// fast_log: the end-of-frame chi^2 is a reported statistic (compared at 1e-3): log via lg2.approx (2 ulp) instead of the
+// ~20-instruction logf, twice per pixel of the covariance pass.  The CHI_SQUARED termination test compares consecutive
+// RMSEs and keeps the precise logarithm.
+__device__ __forceinline__ float chi_rho_dev(float e, int mest, bool fast_log = false)
 {
   float rho = (e * e) / 2.f;
   if (mest == RGBID_HUBER) { if (fabsf(e) > 1.345f) rho = 1.345f * (fabsf(e) - 1.345f / 2.f); }
@@ -60,7 +63,7 @@ __device__ __forceinline__ float chi_rho_dev(float e, int mest)
       float a2 = (1.f - a1) * (1.f - a1) * (1.f - a1);
       rho = ((4.685f * 4.685f) / 6.f) * (1.f - a2);
     } else rho = (4.685f * 4.685f) / 6.f;
-  } else if (mest == RGBID_STUDENT) rho = ((5.f + 1.f) / 2.f) * logf(1.f + (e * e) / 5.f);
+  } else if (mest == RGBID_STUDENT) rho = ((5.f + 1.f) / 2.f) * (fast_log ? __logf(1.f + (e * e) / 5.f) : logf(1.f + (e * e) / 5.f));
   return rho;
 }
 
@@ -868,7 +871,7 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
         // sigmaFuncs.cu:137-150, 541-611) with the reference scales 5 / 0.0025
         if (P.chi_mestimator >= 0) {
           const float cd = (w1[k] - w0[k]) / 0.0025f;
-          if (!(isnan(cd) || isinf(cd))) { chi[2] += chi_rho_dev(cd, chi_mest); chi[3] += 1.f; }
+          if (!(isnan(cd) || isinf(cd))) { chi[2] += chi_rho_dev(cd, chi_mest, P.chi_test == 0); chi[3] += 1.f; }
         }
       }
       accumulate_scalar<!CHI>(accs, sd, rd, ed, fd);
@@ -901,7 +904,7 @@ __global__ void __launch_bounds__(kBuildThreads, kBuildMinBlocks)
       if (CHI) {
         if (P.chi_mestimator >= 0) {
           const float ci = (i1v - i0[k]) / 5.f;
-          if (!(isnan(ci) || isinf(ci))) { chi[0] += chi_rho_dev(ci, chi_mest); chi[1] += 1.f; }
+          if (!(isnan(ci) || isinf(ci))) { chi[0] += chi_rho_dev(ci, chi_mest, P.chi_test == 0); chi[1] += 1.f; }
         }
       }
       accumulate_scalar<!CHI>(accs, si, ri, ei, fi);

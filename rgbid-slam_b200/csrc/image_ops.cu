@@ -238,6 +238,59 @@ __global__ void __launch_bounds__(BX* BY) gradient2_vec_kernel(ImgB srcA, ImgB g
   *(float4*)(gy.row(b, y) + x0) = make_float4(rv[0] / 8.f, rv[1] / 8.f, rv[2] / 8.f, rv[3] / 8.f);
 }
 
+// Four outputs per thread: per source row two or three float4 loads instead of 20 scalar ones (the scalar kernel issues
+// ~250 instructions per pixel and is bound by the issue slots, not by its 25 ex2).  Columns outside the image enter the
+// window as NaN, which the tap loop skips exactly like a NaN texel; taps, order and arithmetic are the scalar kernel's
+// (bit-identical output).
+__global__ void __launch_bounds__(BX* BY) bilateral2_vec_kernel(ImgB srcA, ImgB dstA, float sigmaA, ImgB srcB, ImgB dstB,
+                                                                float sigmaB, int batch, const int* __restrict__ active)
+{
+  const int z = blockIdx.z;
+  const int b = z % batch;
+  RGBID_ACTIVE_GUARD(b);
+  const ImgB& src = (z < batch) ? srcA : srcB;
+  const ImgB& dst = (z < batch) ? dstA : dstB;
+  const float sigma_floatmap = (z < batch) ? sigmaA : sigmaB;
+  const int x0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x), y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x0 >= src.cols || y >= src.rows) return;
+  const float nan = qnanf();
+  const bool has_left = x0 > 0, has_right = x0 + 4 < src.cols;
+  float value[4];
+  *(float4*)value = __ldg((const float4*)(src.row(b, y) + x0));
+  const float s2ih = 0.5f / (5.f * 5.f);  // sigma_space = 5 (filters.cu:83)
+  const float rsigma = __fdividef(1.f, sigma_floatmap);
+  float sum1[4] = {0.f, 0.f, 0.f, 0.f}, sum2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int dy = -2; dy <= 2; ++dy) {
+    const int cy = y + dy;
+    if (cy < 0 || cy >= src.rows) continue;
+    const float* srow = src.row(b, cy) + x0;
+    const float4 M = __ldg((const float4*)srow);
+    float4 Lf = make_float4(nan, nan, nan, nan), Rf = make_float4(nan, nan, nan, nan);
+    if (has_left) Lf = __ldg((const float4*)(srow - 4));
+    if (has_right) Rf = __ldg((const float4*)(srow + 4));
+    const float w[8] = {Lf.z, Lf.w, M.x, M.y, M.z, M.w, Rf.x, Rf.y};  // columns x0 - 2 .. x0 + 5
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int dx = -2; dx <= 2; ++dx) {
+        const float tmp = w[k + dx + 2];
+        if (!isnan(tmp)) {
+          const float space2 = (float)(dx * dx + dy * dy);
+          const float fn = (value[k] - tmp) * rsigma;
+          const float weight = __expf(-(s2ih * space2 + 0.5f * fn * fn));
+          sum1[k] += tmp * weight;
+          sum2[k] += weight;
+        }
+      }
+    }
+  }
+  float out[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) out[k] = isnan(value[k]) ? nan : sum1[k] / sum2[k];
+  *(float4*)(dst.row(b, y) + x0) = *(float4*)out;
+}
+
 // One launch for a LIST of maps of different sizes (all pyramid levels of the raw and of the filtered keyframe: 16
 // Sobel passes, or the 8 copies of saveCurrentImagesAsOdoKeyframes): the coarse levels are a few microseconds of work
 // each and paid a launch apiece.  blockIdx.x walks the tiles of all list entries; per entry the body is the per-map
@@ -597,8 +650,15 @@ void launch_bilateral2(const LaunchCtx& L, ImgB srcA, ImgB dstA, float sigmaA, I
                        int batch, const int* active)
 {
   int nm = srcB.p ? 2 : 1;
-  bilateral2_kernel<<<grid2d(srcA.cols, srcA.rows, batch * nm), dim3(BX, BY), 0, L.stream>>>(
-      srcA, dstA, sigmaA, srcB, dstB, sigmaB, batch, active);
+  auto v16 = [](const ImgB& m) { return aligned(m.p, 16) && m.pitch % 16 == 0 && m.sstride % 16 == 0; };
+  bool vec = srcA.cols % 4 == 0 && v16(srcA) && v16(dstA);
+  if (nm == 2) vec = vec && v16(srcB) && v16(dstB);
+  if (vec)
+    bilateral2_vec_kernel<<<grid2d(srcA.cols / 4, srcA.rows, batch * nm), dim3(BX, BY), 0, L.stream>>>(
+        srcA, dstA, sigmaA, srcB, dstB, sigmaB, batch, active);
+  else
+    bilateral2_kernel<<<grid2d(srcA.cols, srcA.rows, batch * nm), dim3(BX, BY), 0, L.stream>>>(
+        srcA, dstA, sigmaA, srcB, dstB, sigmaB, batch, active);
   ++*L.launches;
 }
 
