@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+RGBID_NO_GRAPH=1 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"gn_|pyr_down|ingest|visibility|warp_|vmap|nmap|bilateral|gradient|copy|control_upload|fill_|export|keyframe_maps" -c 700 --csv --log-file gpurun_out/r02h_launches_all.csv python tools/profile_step.py 32 6 > gpurun_out/b36_ncu.log 2>&1
+tail -1 gpurun_out/b36_ncu.log
