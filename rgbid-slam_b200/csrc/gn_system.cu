@@ -999,7 +999,7 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
 // Sampling geometry of computeErrorGridStride (sigmaFuncs.cu:711-747): sample (s y, s x) -> index y*kept_cols+x.
 // ------------------------------------------------------------------------------------------------------------
 template <bool TEX>
-__global__ void __cluster_dims__(kScaleCluster, 1, 1) __launch_bounds__(kScaleThreads, 2)
+__global__ void __cluster_dims__(kScaleCluster, 1, 1) __launch_bounds__(kScaleThreads, kScaleMinBlocks)
     gn_scale_kernel(const GnLevelMaps M, const GnParams P, const GnState* __restrict__ states,
                     ScaleState* __restrict__ scales)
 {
@@ -1137,6 +1137,10 @@ int gn_prepare_device()
 #undef RGBID_FAST_ATTR
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(gn_build_fast_kernel<true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast_smem_bytes(true));
+    if (kScaleCluster > 8) {  // more than the portable cluster size
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(gn_scale_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(gn_scale_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    }
     err = e;
     return e == cudaSuccess;
   });

@@ -18,8 +18,18 @@ namespace rgbid {
 
 namespace cg = cooperative_groups;
 
-constexpr int kScaleCluster = 8;    // CTAs per frame pair (portable cluster size limit)
-constexpr int kScaleThreads = 512;  // threads per CTA (256 measured the same: the per-SM instruction total of a round does not change, see profiles/README.md)
+#ifndef RGBID_SCALE_CLUSTER
+#define RGBID_SCALE_CLUSTER 8
+#endif
+#ifndef RGBID_SCALE_THREADS
+#define RGBID_SCALE_THREADS 512
+#endif
+#ifndef RGBID_SCALE_MINB
+#define RGBID_SCALE_MINB 2
+#endif
+constexpr int kScaleCluster = RGBID_SCALE_CLUSTER;  // CTAs per frame pair (8 = portable cluster size limit; 16 needs the non-portable attribute)
+constexpr int kScaleMinBlocks = RGBID_SCALE_MINB;
+constexpr int kScaleThreads = RGBID_SCALE_THREADS;  // threads per CTA (256 measured the same: the per-SM instruction total of a round does not change, see profiles/README.md)
 constexpr int kScaleVals = 12;      // reduced values per round (6 per residual slot)
 
 // C(nu) = -psi(nu/2) + ln(nu/2) + f + 1 + psi((nu+1)/2) - ln((nu+1)/2)   (sigmaFuncs.cu:966), float arithmetic

@@ -15,7 +15,7 @@ __global__ void compute_error_kernel(ImgB im1, ImgB im0, float* __restrict__ err
 }
 
 // K12 / K13 / K14 on explicit error vectors: one 8-CTA cluster, samples read from global memory.
-__global__ void __cluster_dims__(kScaleCluster, 1, 1) __launch_bounds__(kScaleThreads, 2)
+__global__ void __cluster_dims__(kScaleCluster, 1, 1) __launch_bounds__(kScaleThreads, kScaleMinBlocks)
     scale_from_errors_kernel(const float* __restrict__ err0, const float* __restrict__ err1, int n, int op, int mest,
                              float bias0, float sigma0, float bias1, float sigma1, ScaleState* __restrict__ out)
 {
@@ -91,7 +91,12 @@ void launch_scale_from_errors(const LaunchCtx& L, const float* err0, const float
                               float bias0, float sigma0, float bias1, float sigma1, ScaleState* out)
 {
   static PerDevice table;
-  table.once([] { return upload_nu_table(); });
+  table.once([] {
+    if (kScaleCluster > 8 &&
+        cudaFuncSetAttribute(scale_from_errors_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
+      return false;
+    return upload_nu_table();
+  });
   scale_from_errors_kernel<<<kScaleCluster, kScaleThreads, 0, L.stream>>>(err0, err1, n, op, mest, bias0, sigma0,
                                                                           bias1, sigma1, out);
   ++*L.launches;
