@@ -260,11 +260,19 @@ __device__ const void* g_tail_probe_state;
 // every CTA pre-execute the stages on dummy data behind the reduction's barrier shortened the tail (17 500 -> 14 000
 // clocks) but made the launch SLOWER (90.4 vs 84.7 us: 4 x 288 lanes of cold double-precision code at once) -- removed,
 // profiles/r02_tail_probe.txt.
-__device__ __noinline__ void gn_stage_solve(const double* tot, double* x) { llt_solve_packed(tot, x); }
+#ifndef RGBID_TAIL_INLINE
+#define RGBID_TAIL_INLINE 1  // the three stages fall through behind the reduction (sequential instruction prefetch): 0.4-0.6 us per launch
+#endif
+#if RGBID_TAIL_INLINE
+#define RGBID_STAGE_ATTR __forceinline__
+#else
+#define RGBID_STAGE_ATTR __noinline__
+#endif
+__device__ RGBID_STAGE_ATTR void gn_stage_solve(const double* tot, double* x) { llt_solve_packed(tot, x); }
 
-__device__ __noinline__ bool gn_stage_update(const double* x, double* R, double* t) { return gn_update_lean(x, R, t); }
+__device__ RGBID_STAGE_ATTR bool gn_stage_update(const double* x, double* R, double* t) { return gn_update_lean(x, R, t); }
 
-__device__ __noinline__ void gn_stage_commit(GnState& st, const double* Rin, const double* tin, const double* x, bool bad,
+__device__ RGBID_STAGE_ATTR void gn_stage_commit(GnState& st, const double* Rin, const double* tin, const double* x, bool bad,
                                              const GnParams& P)
 {
   double R[9], t[3];
