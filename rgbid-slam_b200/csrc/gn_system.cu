@@ -341,7 +341,14 @@ __device__ __noinline__ void gn_tail_cov(GnState& st, const double* tot, const G
     double A[36], bv[6];
     unpack_system(tot, A, bv);
     for (int i = 0; i < 36; ++i) st.lastA[i] = A[i];
-    inverse6(A, st.cov);
+    // the normal matrix is symmetric positive definite: Cholesky-based inverse in registers; the general Gauss-Jordan
+    // (pivot search, row swaps through local memory, six divisions) only for a matrix that is not
+    double Ai[36];
+    if (inverse6_spd_packed(tot, Ai)) {
+      for (int i = 0; i < 36; ++i) st.cov[i] = Ai[i];
+    } else {
+      inverse6(A, st.cov);
+    }
   }
   if (chi && P.chi_mestimator >= 0) {
     // computeChiSquare host part, sigmaFuncs.cu:1286-1287

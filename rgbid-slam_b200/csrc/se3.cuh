@@ -334,6 +334,61 @@ RGBID_HD bool inverse6(const double* A, double* Ai)
   return true;
 }
 
+// Inverse of a symmetric positive definite 6x6 matrix given as the 27 packed sums (upper triangle row by row, the
+// residual column ignored): A = U^T U (rsqrt pivots, as llt_solve_packed), V = U^-1, A^-1 = V V^T.  Straight-line,
+// register resident, no divisions and no pivot search -- the covariance pass's A is the Gauss-Newton normal matrix.
+// Returns false (Ai untouched) when a pivot is not positive; the caller then takes the general inverse6.
+RGBID_HD bool inverse6_spd_packed(const double* s27, double* Ai)
+{
+  double u[6][6], inv[6];
+  {
+    int shift = 0;
+    RGBID_UNROLL
+    for (int i = 0; i < 6; ++i) {
+      RGBID_UNROLL
+      for (int j = i; j < 6; ++j) u[i][j] = s27[shift++];
+      ++shift;  // J^T r
+    }
+  }
+  bool ok = true;
+  RGBID_UNROLL
+  for (int k = 0; k < 6; ++k) {
+    ok = ok && (u[k][k] > 0.0);
+    const double r = rsqrt_d(u[k][k]);
+    inv[k] = r;
+    RGBID_UNROLL
+    for (int j = k; j < 6; ++j) u[k][j] *= r;
+    RGBID_UNROLL
+    for (int i = k + 1; i < 6; ++i)
+      RGBID_UNROLL
+      for (int j = i; j < 6; ++j) u[i][j] -= u[k][i] * u[k][j];
+  }
+  if (!ok) return false;
+  double v[6][6];  // upper triangular inverse of U
+  RGBID_UNROLL
+  for (int i = 0; i < 6; ++i) {
+    v[i][i] = inv[i];
+    RGBID_UNROLL
+    for (int j = i + 1; j < 6; ++j) {
+      double s = 0.0;
+      RGBID_UNROLL
+      for (int k = i; k < j; ++k) s += v[i][k] * u[k][j];
+      v[i][j] = -s * inv[j];
+    }
+  }
+  RGBID_UNROLL
+  for (int i = 0; i < 6; ++i)
+    RGBID_UNROLL
+    for (int j = i; j < 6; ++j) {
+      double s = 0.0;
+      RGBID_UNROLL
+      for (int k = j; k < 6; ++k) s += v[i][k] * v[j][k];
+      Ai[i * 6 + j] = s;
+      Ai[j * 6 + i] = s;
+    }
+  return true;
+}
+
 // One Gauss-Newton update T <- T_inc T with x = [trans; rot], R_inc^-1 = expMapRot(rot),
 // t_inc = -R_inc trans (src/visodo.cpp:1252-1263).  Returns true if the pose became NaN.
 RGBID_HD bool gn_update(const double* x, double* R, double* t)
