@@ -335,7 +335,10 @@ __device__ __forceinline__ void gn_tail_update(GnState& st, const double* tot, c
   RGBID_STAMP(4);
 }
 
-__device__ __noinline__ void gn_tail_cov(GnState& st, const double* tot, const GnParams& P, bool chi)
+// GnParams BY VALUE in the two out-of-line functions: a reference would take the address of the kernel parameter and make
+// every thread of every CTA copy it to its local-memory frame in the prologue (160 B x 73 728 threads = the ~12 MB of
+// DRAM writes per launch the round-1 captures show); by value the copy is made by the one thread that calls
+__device__ __noinline__ void gn_tail_cov(GnState& st, const double* tot, const GnParams P, bool chi)
 {
   if (P.compute_cov) {
     double A[36], bv[6];
@@ -374,7 +377,7 @@ __device__ __noinline__ void gn_tail_cov(GnState& st, const double* tot, const G
   }
 }
 
-__device__ __noinline__ void gn_tail_trace(const GnState& st, const double* tot, const GnParams& P, const ScaleState* sc,
+__device__ __noinline__ void gn_tail_trace(const GnState& st, const double* tot, const GnParams P, const ScaleState* sc,
                                            rgbid_iter_trace* __restrict__ trace, int b, const double* x)
 {
   rgbid_iter_trace& T = trace[(size_t)b * P.trace_stride + P.iter_index];
