@@ -137,6 +137,19 @@ __device__ __forceinline__ void slot_accumulate(const ScaleSlot& s, float e, flo
   }
 }
 
+// RGBID_FAST_NU_LOG=1 (default): ln of the Student weights through lg2.approx (3 instructions, 2 ulp) instead of logf
+// (~20 instructions) in the nu rounds.  The sums feed only the SIGN of C(nu) in the bisection (nu itself is one of
+// {2, 2.5, ..., 10}); the parity suite and tools/stress_parity.py see identical nu with both.  The kernel is half issue
+// bound: 21.6 -> 19.7 us per launch at level 0, 35.0 -> 28.3 us at levels 1 and 2 (tools/gpu_batch48.sh).
+#ifndef RGBID_FAST_NU_LOG
+#define RGBID_FAST_NU_LOG 1
+#endif
+#if RGBID_FAST_NU_LOG
+#define RGBID_NU_LOG(x) __logf(x)
+#else
+#define RGBID_NU_LOG(x) logf(x)
+#endif
+
 // One round over this CTA's samples.  The phase is uniform over the cluster, so it is tested once per round, not
 // once per sample; the Student-t phases (every round of the shipped configuration) are written out with the
 // divisions as multiplications by one reciprocal -- what div.approx computes, minus its per-call range fix-up.
@@ -177,7 +190,7 @@ __device__ __forceinline__ void slot_accumulate_all(const ScaleSlot& s, const fl
         const float en = (e - bias) * rsigma;
         const float e2 = en * en;
         const float w2 = (2.f + 1.f) * (1.f / (2.f + e2)), w10 = (10.f + 1.f) * (1.f / (10.f + e2));
-        acc[0] += logf(w2); acc[1] += w2; acc[2] += logf(w10); acc[3] += w10; acc[5] += 1.f;
+        acc[0] += RGBID_NU_LOG(w2); acc[1] += w2; acc[2] += RGBID_NU_LOG(w10); acc[3] += w10; acc[5] += 1.f;
       }
     }
   } else if (s.phase == PH_NU_BISECT) {
@@ -188,7 +201,7 @@ __device__ __forceinline__ void slot_accumulate_all(const ScaleSlot& s, const fl
       if (fabsf(e) < __int_as_float(0x7f800000)) {
         const float en = (e - bias) * rsigma;
         const float w = nu1 * (1.f / (nu + en * en));
-        acc[0] += logf(w); acc[1] += w; acc[5] += 1.f;
+        acc[0] += RGBID_NU_LOG(w); acc[1] += w; acc[5] += 1.f;
       }
     }
   } else {
